@@ -1,0 +1,198 @@
+// fl_patch.cu -- inverse path: unpatchify / patchify permutations, the fused rollout step, and the
+// grid -> node nearest-cell resample.
+//
+//   fl_patch_to_img   src/utils_model.py:77-92   (reshape + transpose + F.fold, non-overlapping)
+//   fl_img_to_patch   src/utils_model.py:95-109  (F.unfold + view + permute)
+//   fl_rollout_step   src/models/model.py:164,206,210 (img_to_patch; diffs[mask] = 0; last + diffs)
+//   fl_grid2mesh      eagle/Dataloader/IMG_Eagle.py:93-123
+//
+// The two permutations move 16-byte units: a patch row (py elements) is contiguous on both
+// sides, so every thread copies one 128-bit piece of a row; the destination side is fully
+// coalesced and the source side is read in whole 32-byte sectors.
+#include "fl_common.cuh"
+
+namespace {
+
+// unit = 16 bytes; upr = units per patch row (py * elem_size / 16)
+template <bool TO_IMG>
+__global__ void k_permute16(const uint4* __restrict__ src, uint4* __restrict__ dst, long total_units, int n_bx, int n_by,
+                            int C, int px, int upr) {
+    long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= total_units) return;
+    // decompose the IMAGE-side unit index: [b][c][X][Yu] with Yu over n_by*upr units
+    long img_u, pat_u;
+    if (TO_IMG) {
+        img_u = u;
+        int yu = (int)(u % ((long)n_by * upr));
+        long r = u / ((long)n_by * upr);
+        int X = (int)(r % ((long)n_bx * px));
+        r /= (long)n_bx * px;
+        int c = (int)(r % C);
+        long b = r / C;
+        int by = yu / upr, ju = yu - by * upr, bx = X / px, i = X - bx * px;
+        pat_u = ((((b * n_bx + bx) * n_by + by) * C + c) * px + i) * upr + ju;
+    } else {
+        pat_u = u;
+        int ju = (int)(u % upr);
+        long r = u / upr;
+        int i = (int)(r % px); r /= px;
+        int c = (int)(r % C); r /= C;
+        int by = (int)(r % n_by); r /= n_by;
+        int bx = (int)(r % n_bx);
+        long b = r / n_bx;
+        img_u = (((b * C + c) * n_bx + bx) * px + i) * ((long)n_by * upr) + (long)by * upr + ju;
+    }
+    if (TO_IMG) dst[img_u] = __ldg(src + pat_u);
+    else dst[pat_u] = __ldg(src + img_u);
+}
+
+// scalar fallback (row bytes not a multiple of 16, or unaligned pointers)
+template <typename T, bool TO_IMG>
+__global__ void k_permute_elem(const T* __restrict__ src, T* __restrict__ dst, long total, int n_bx, int n_by, int C,
+                               int px, int py) {
+    long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= total) return;
+    int j = (int)(u % py);
+    long r = u / py;
+    int i = (int)(r % px); r /= px;
+    int c = (int)(r % C); r /= C;
+    int by = (int)(r % n_by); r /= n_by;
+    int bx = (int)(r % n_bx);
+    long b = r / n_bx;
+    long img = (((b * C + c) * n_bx + bx) * px + i) * ((long)n_by * py) + (long)by * py + j;
+    if (TO_IMG) dst[img] = src[u]; else dst[u] = src[img];
+}
+
+// patch-side unit of 4 floats: diffs = img gather, zero where mask, next = last + diffs
+__global__ void k_rollout_step(const float4* __restrict__ img, const uchar4* __restrict__ mask,
+                               const float4* __restrict__ last, float4* __restrict__ diffs, float4* __restrict__ next,
+                               long total_units, int n_bx, int n_by, int C, int px, int upr) {
+    long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= total_units) return;
+    int ju = (int)(u % upr);
+    long r = u / upr;
+    int i = (int)(r % px); r /= px;
+    int c = (int)(r % C); r /= C;
+    int by = (int)(r % n_by); r /= n_by;
+    int bx = (int)(r % n_bx);
+    long b = r / n_bx;
+    long img_u = (((b * C + c) * n_bx + bx) * px + i) * ((long)n_by * upr) + (long)by * upr + ju;
+    float4 d = fl_ldg_stream4(img + img_u);
+    uchar4 m = mask[u];
+    if (m.x) d.x = 0.f;
+    if (m.y) d.y = 0.f;
+    if (m.z) d.z = 0.f;
+    if (m.w) d.w = 0.f;
+    float4 l = fl_ldg_stream4(last + u);
+    fl_stg_stream4(diffs + u, d);
+    fl_stg_stream4(next + u, make_float4(l.x + d.x, l.y + d.y, l.z + d.z, l.w + d.w));
+}
+
+// NumPy's npy_floor_dividef (numpy/core/src/npymath/npy_math_internal.h.src), float32 throughout
+__device__ __forceinline__ float np_floor_divide_f(float a, float b) {
+    if (b == 0.f) return __fdiv_rn(a, b);
+    float mod = fmodf(a, b);
+    float div = __fdiv_rn(__fsub_rn(a, mod), b);
+    if (mod != 0.f && ((b < 0.f) != (mod < 0.f))) div = __fsub_rn(div, 1.0f);
+    if (div != 0.f) {
+        float fl = floorf(div);
+        if (__fsub_rn(div, fl) > 0.5f) fl = __fadd_rn(fl, 1.0f);
+        return fl;
+    }
+    return copysignf(0.f, __fdiv_rn(a, b));
+}
+
+__global__ void k_grid2mesh(const float* __restrict__ grid, const float* __restrict__ mesh_pos, float* __restrict__ out,
+                            int T, int N, int H, int W, int C, float x_min, float y_min, float half_sx, float half_sy,
+                            float sx, float neg_sy) {
+    long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long)T * N) return;
+    long t = g / N;
+    const float2 p = __ldg((const float2*)mesh_pos + g);
+    // IMG_Eagle.py:111-112 in float32 (NumPy 1.26 keeps float32 arrays float32 against scalars)
+    float fx = np_floor_divide_f(__fadd_rn(__fsub_rn(p.x, x_min), half_sx), sx);
+    float fy = np_floor_divide_f(__fadd_rn(__fsub_rn(p.y, y_min), half_sy), neg_sy);
+    long ix = (long)fx, iy = (long)fy;
+    if (ix < 0) ix += W;                       // NumPy negative indices wrap once
+    if (iy < 0) iy += H;
+    ix = ix < 0 ? 0 : (ix >= W ? W - 1 : ix);  // the reference raises IndexError beyond that; clamp
+    iy = iy < 0 ? 0 : (iy >= H ? H - 1 : iy);
+    long row = H - 1 - iy;                     // np.flip(grid, axis=1), IMG_Eagle.py:105-106
+    const float* s = grid + ((t * H + row) * W + ix) * C;
+    float* d = out + g * C;
+    for (int c = 0; c < C; ++c) d[c] = __ldg(s + c);
+}
+
+template <bool TO_IMG>
+int permute(const void* src, void* dst, int B, int n_bx, int n_by, int C, int px, int py, int es, cudaStream_t st) {
+    long total = (long)B * n_bx * n_by * C * px * py;
+    bool vec = ((py * es) % 16 == 0) && (((uintptr_t)src | (uintptr_t)dst) % 16 == 0);
+    if (vec) {
+        int upr = py * es / 16;
+        long units = total * es / 16;
+        k_permute16<TO_IMG><<<(unsigned)((units + 255) / 256), 256, 0, st>>>((const uint4*)src, (uint4*)dst, units, n_bx,
+                                                                             n_by, C, px, upr);
+    } else if (es == 4) {
+        k_permute_elem<uint32_t, TO_IMG><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint32_t*)src, (uint32_t*)dst,
+                                                                                       total, n_bx, n_by, C, px, py);
+    } else {
+        k_permute_elem<uint16_t, TO_IMG><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint16_t*)src, (uint16_t*)dst,
+                                                                                       total, n_bx, n_by, C, px, py);
+    }
+    FL_LAUNCH_CHECK();
+    return FL_OK;
+}
+
+int check_perm_args(const char* who, const void* a, const void* b, int B, int n_bx, int n_by, int C, int px, int py, int es) {
+    FL_REQUIRE(a && b, FL_E_ARG, "%s: null pointer", who);
+    FL_REQUIRE(B > 0 && n_bx > 0 && n_by > 0 && C > 0 && px > 0 && py > 0, FL_E_ARG, "%s: sizes must be positive", who);
+    FL_REQUIRE(es == 2 || es == 4, FL_E_ARG, "%s: elem_size must be 2 or 4, got %d", who, es);
+    FL_REQUIRE((long)B * n_bx * n_by * C * px * py < (1L << 40), FL_E_ARG, "%s: tensor too large", who);
+    return FL_OK;
+}
+
+}  // namespace
+
+extern "C" int fl_patch_to_img(const void* d_patches, void* d_img, int B, int n_bx, int n_by, int C, int px, int py,
+                               int elem_size, void* stream) {
+    int rc = check_perm_args("fl_patch_to_img", d_patches, d_img, B, n_bx, n_by, C, px, py, elem_size);
+    if (rc) return rc;
+    return permute<true>(d_patches, d_img, B, n_bx, n_by, C, px, py, elem_size, (cudaStream_t)stream);
+}
+
+extern "C" int fl_img_to_patch(const void* d_img, void* d_patches, int B, int n_bx, int n_by, int C, int px, int py,
+                               int elem_size, void* stream) {
+    int rc = check_perm_args("fl_img_to_patch", d_img, d_patches, B, n_bx, n_by, C, px, py, elem_size);
+    if (rc) return rc;
+    return permute<false>(d_img, d_patches, B, n_bx, n_by, C, px, py, elem_size, (cudaStream_t)stream);
+}
+
+extern "C" int fl_rollout_step(const float* d_pred_img, const uint8_t* d_mask, const float* d_last, float* d_diffs,
+                               float* d_next, int B, int n_bx, int n_by, int C, int px, int py, void* stream) {
+    FL_REQUIRE(d_pred_img && d_mask && d_last && d_diffs && d_next, FL_E_ARG, "fl_rollout_step: null pointer");
+    FL_REQUIRE(B > 0 && n_bx > 0 && n_by > 0 && C > 0 && px > 0 && py > 0, FL_E_ARG, "fl_rollout_step: sizes must be positive");
+    FL_REQUIRE(py % 4 == 0, FL_E_ARG, "fl_rollout_step: patch width %d must be a multiple of 4", py);
+    FL_REQUIRE((((uintptr_t)d_pred_img | (uintptr_t)d_last | (uintptr_t)d_diffs | (uintptr_t)d_next) % 16 == 0) &&
+                   ((uintptr_t)d_mask % 4 == 0),
+               FL_E_ALIGN, "fl_rollout_step: float buffers must be 16-byte aligned, mask 4-byte aligned");
+    long units = (long)B * n_bx * n_by * C * px * py / 4;
+    k_rollout_step<<<(unsigned)((units + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)d_pred_img, (const uchar4*)d_mask, (const float4*)d_last, (float4*)d_diffs, (float4*)d_next, units,
+        n_bx, n_by, C, px, py / 4);
+    FL_LAUNCH_CHECK();
+    return FL_OK;
+}
+
+extern "C" int fl_grid2mesh(const float* d_grid, const float* d_mesh_pos, float* d_out, int T, int N, int H, int W, int C,
+                            float x_min, float y_min, double step_x, double step_y, void* stream) {
+    FL_REQUIRE(d_grid && d_mesh_pos && d_out, FL_E_ARG, "fl_grid2mesh: null pointer");
+    FL_REQUIRE(T > 0 && N > 0 && H > 0 && W > 0 && C > 0, FL_E_ARG, "fl_grid2mesh: sizes must be positive");
+    FL_REQUIRE(step_x != 0.0 && step_y != 0.0, FL_E_ARG, "fl_grid2mesh: zero grid step");
+    FL_REQUIRE((uintptr_t)d_mesh_pos % 8 == 0, FL_E_ALIGN, "fl_grid2mesh: mesh_pos must be 8-byte aligned");
+    long n = (long)T * N;
+    k_grid2mesh<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_grid, d_mesh_pos, d_out, T, N, H, W, C, x_min, y_min, (float)(step_x / 2), (float)(step_y / 2), (float)step_x,
+        (float)(-step_y));
+    FL_LAUNCH_CHECK();
+    return FL_OK;
+}

@@ -1,0 +1,109 @@
+"""The per-step field data path as one batched call: node fields of many trajectories ->
+normalised, patchified states (+ mask) on the device.
+
+This is the engine behind `MGNDataset.ds_get` / `AirfoilDataset.ds_get` (the host-side mirrors of
+`/root/reference/src/dataloader/simple_dataloader.py:72-102` and `airfoil_ds.py:71-103`) and what
+bench.py times.  One launch of csrc/fl_interp.cu processes every requested frame of every
+trajectory in the batch; trajectories may have different meshes as long as they share the patch
+grid (which the reference's DataLoader collation requires anyway).
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FL_MASK_AWARE_NORM, FL_NO_NORM, FlTraj, check, load, stream_ptr
+from .mesh_utils import MeshPlan, PatchTable
+
+
+@dataclass(frozen=True)
+class Personality:
+    """Dataset-specific geometry/normalisation rules (SURVEY.md 'two dataset personalities')."""
+    name: str
+    flip_y: bool            # airfoil_ds.py:80
+    crop_patches: int       # airfoil_ds.py:132-133 (outer ring of patches dropped)
+    mask_aware_norm: bool   # airfoil_ds.py:236-242
+    means: tuple
+    stds: tuple
+
+
+CYLINDER = Personality("cylinder", False, 0, False, (0.823, 0.0005865, 0.04763), (0.275, 0.275, 0.275))
+AIRFOIL = Personality("airfoil", True, 1, True, (170.1, -1.183, 9.935e+04), (50.0, 50.0, 6197.0))
+
+
+class DeviceTrajectory:
+    """Node fields of one trajectory resident in HBM, in the pickle's own layout
+    (velocity f32[T,N,2], pressure f32[T,N,1]; max/ds_download/torch_MGN.py:68-95)."""
+
+    def __init__(self, velocity, pressure, plan: MeshPlan):
+        dev = plan.device
+        v = velocity if torch.is_tensor(velocity) else torch.from_numpy(np.ascontiguousarray(velocity, dtype=np.float32))
+        p = pressure if torch.is_tensor(pressure) else torch.from_numpy(np.ascontiguousarray(pressure, dtype=np.float32))
+        if v.dim() != 3 or v.shape[2] != 2 or v.shape[1] != plan.n_nodes:
+            raise ValueError(f"velocity must be (T, {plan.n_nodes}, 2), got {tuple(v.shape)}")
+        if p.dim() == 2:
+            p = p.unsqueeze(-1)
+        if p.shape != (v.shape[0], plan.n_nodes, 1):
+            raise ValueError(f"pressure must be ({v.shape[0]}, {plan.n_nodes}, 1), got {tuple(p.shape)}")
+        self.velocity = v.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        self.pressure = p.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        self.plan = plan
+        self.n_steps = int(v.shape[0])
+
+
+class TrajBatch:
+    """Pre-built launch descriptors for a fixed batch (descriptor array already on the device), so
+    the steady-state call is exactly one kernel launch and no host->device traffic."""
+
+    def __init__(self, trajs, tables, t0s, interval, n_frames, want_mask=True):
+        if not (len(trajs) == len(tables) == len(t0s)) or not trajs:
+            raise ValueError("trajs, tables and t0s must be non-empty and of equal length")
+        tab0 = tables[0]
+        for tab in tables:
+            if (tab.n_bx, tab.n_by, tab.px, tab.py) != (tab0.n_bx, tab0.n_by, tab0.px, tab0.py):
+                raise ValueError("all trajectories of a batch must share the patch grid")
+        self.n_traj, self.n_frames, self.tab0 = len(trajs), int(n_frames), tab0
+        dev = trajs[0].plan.device
+        self.device = dev
+        L, px, py = tab0.n_patches, tab0.px, tab0.py
+        for tr, t0 in zip(trajs, t0s):
+            last = int(t0) + (self.n_frames - 1) * int(interval)
+            if t0 < 0 or last >= tr.n_steps or interval < 1 or n_frames < 1:
+                raise ValueError(f"frames {t0}..{last} step {interval} outside trajectory of {tr.n_steps} steps")
+        self.states = torch.empty((self.n_traj, self.n_frames, L, 3, px, py), dtype=torch.float32, device=dev)
+        self.mask = torch.empty((self.n_traj, self.n_frames, L, px, py), dtype=torch.uint8, device=dev) if want_mask else None
+        arr = (FlTraj * self.n_traj)()
+        for i, (tr, tab, t0) in enumerate(zip(trajs, tables, t0s)):
+            arr[i] = FlTraj(tr.velocity.data_ptr(), tr.pressure.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(),
+                            self.states[i].data_ptr(), self.mask[i].data_ptr() if want_mask else 0,
+                            tr.plan.n_nodes, int(t0), int(interval), self.n_frames)
+        raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
+        self.desc = torch.from_numpy(raw).to(dev)
+        self._keep = (trajs, tables)   # keep the device buffers alive
+
+    def run(self, personality: Personality, normalize=True, means=None, stds=None):
+        """Enqueue the fused kernel on the current stream; returns (states, mask) device tensors."""
+        flags = (FL_MASK_AWARE_NORM if personality.mask_aware_norm else 0) | (0 if normalize else FL_NO_NORM)
+        m = (ctypes.c_float * 3)(*(means if means is not None else personality.means))
+        s = (ctypes.c_float * 3)(*(stds if stds is not None else personality.stds))
+        tab = self.tab0
+        with torch.cuda.device(self.device):
+            check(load().fl_interp_patchify_dev(ctypes.c_void_p(self.desc.data_ptr()), self.n_traj, self.n_frames,
+                                                tab.n_patches, tab.px, tab.py, m, s, flags, stream_ptr()),
+                  "fl_interp_patchify")
+        return self.states, self.mask
+
+
+def interp_patchify(traj: DeviceTrajectory, step_num: int, seq_len: int, seq_interval: int, patch_size,
+                    personality: Personality, normalize=True, means=None, stds=None):
+    """One trajectory, frames step_num, step_num+interval, ... -> (states (T,L,3,px,py) f32,
+    mask (T,L,px,py) u8, table)."""
+    _lib.require_cuda()
+    tab = traj.plan.patch_table(patch_size, personality.crop_patches, personality.flip_y)
+    batch = TrajBatch([traj], [tab], [step_num], seq_interval, seq_len)
+    states, mask = batch.run(personality, normalize, means, stds)
+    return states[0], mask[0], tab

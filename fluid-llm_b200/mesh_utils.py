@@ -1,0 +1,225 @@
+"""Mesh -> regular grid on the GPU, behind the reference's own call signatures.
+
+Mirror of `/root/reference/src/dataloader/mesh_utils.py:64-106` (`grid_pos`, `to_grid`,
+`get_mesh_interpolation`).  The matplotlib objects the reference passes around (`triang`, the
+trifinder) become a `MeshPlan`: device-resident node positions, corrected triangles, triangle id
+per grid cell and the static (vertex ids, barycentric weights) table the per-step kernel reads.
+All arithmetic happens in libfluidgrid.so (csrc/fl_locate.cu, fl_interp.cu); this file only
+moves arrays and keeps the reference's argument checks and error behaviour.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from functools import lru_cache
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FL_FLIP_Y, check, load, ptr, stream_ptr
+
+F32, F64 = np.float32, np.float64
+
+
+def default_numpy_semantics() -> str:
+    """The reference pins NumPy 1.26.3 (environemnt.yml:177); its scalar promotion decides the last
+    bit of the grid coordinates.  "1.26" reproduces the pinned environment, "2.x" reproduces the
+    reference's code run under NumPy >= 2 (NEP 50)."""
+    return os.environ.get("FLUIDGRID_NUMPY_SEMANTICS", "1.26")
+
+
+def _grid_shape(x_min, x_max, y_min, y_max, grid_res, sem):
+    x_min, x_max, y_min, y_max = F32(x_min), F32(x_max), F32(y_min), F32(y_max)
+    dx, dy = F32(x_max - x_min), F32(y_max - y_min)
+    ratio = F32(min(dx, dy) / max(dx, dy))                       # mesh_utils.py:67-69, float32 scalars
+    n_short = int(F64(grid_res) * F64(ratio)) if sem == "1.26" else int(F32(F32(grid_res) * ratio))
+    return (int(grid_res), n_short) if dx > dy else (n_short, int(grid_res))   # :71-76
+
+
+def _grid_axis(start, stop, n, sem):
+    # np.mgrid[start:stop:n*1j]: indices * step + start with step = (stop - start) / (n - 1);
+    # float64 arithmetic under NumPy 1.26 (legacy promotion of the float32 scalars), float32 under 2.x
+    start, stop = F32(start), F32(stop)
+    i = np.arange(n)
+    if sem == "1.26":
+        step = F64(F32(stop - start)) / F64(n - 1) if n != 1 else F64(n)
+        return (i.astype(F64) * step + F64(start)).astype(F32)
+    step = F32(F32(stop - start) / F32(n - 1)) if n != 1 else F32(n)
+    return (i.astype(F32) * step + start).astype(F32)
+
+
+@lru_cache(maxsize=64)
+def _grid_axes(x_min, x_max, y_min, y_max, grid_res, sem):
+    nx, ny = _grid_shape(x_min, x_max, y_min, y_max, grid_res, sem)
+    if nx < 1 or ny < 1:
+        raise ValueError(f"degenerate grid {nx} x {ny} for extents ({x_min}, {x_max}) x ({y_min}, {y_max})")
+    return _grid_axis(x_min, x_max, nx, sem), _grid_axis(y_min, y_max, ny, sem)
+
+
+def grid_pos(x_min, x_max, y_min, y_max, grid_res, numpy_semantics=None):
+    """mesh_utils.py:64-79 -> (grid_x, grid_y) float32 (nx, ny), index order [ix, iy]."""
+    sem = numpy_semantics or default_numpy_semantics()
+    ax, ay = _grid_axes(float(x_min), float(x_max), float(y_min), float(y_max), int(grid_res), sem)
+    nx, ny = len(ax), len(ay)
+    return (np.ascontiguousarray(np.broadcast_to(ax[:, None], (nx, ny))),
+            np.ascontiguousarray(np.broadcast_to(ay[None, :], (nx, ny))))
+
+
+class PatchTable:
+    """The static table re-ordered into output-pixel order for one dataset personality."""
+
+    def __init__(self, idx, w, n_bx, n_by, px, py):
+        self.idx, self.w, self.n_bx, self.n_by, self.px, self.py = idx, w, n_bx, n_by, px, py
+        self.n_patches = n_bx * n_by
+
+
+class MeshPlan:
+    """Device-side stand-in for `matplotlib.tri.Triangulation` + its trifinder (mesh_utils.py:103-104).
+
+    Opaque to callers, exactly like the reference's `triang`: it is only handed back to `to_grid`.
+    `x`, `y`, `triangles` are kept (host) because the reference's interpolator checks `z` against
+    `triangulation.x.shape` (src/_triinterpolate.py:37-39)."""
+
+    def __init__(self, pos, faces, grid_res=238, numpy_semantics=None, device=None):
+        _lib.require_cuda()
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        pos = np.asarray(pos)
+        if pos.ndim != 2 or pos.shape[1] != 2:
+            raise ValueError(f"x and y must be equal-length 1D arrays, but found pos of shape {pos.shape!r}")
+        try:
+            tri = np.array(faces, dtype=np.int32, order="C")   # matplotlib: int32 C-contiguous copy
+        except (ValueError, TypeError) as e:
+            raise ValueError(f"triangles must be a (N, 3) int array, not {faces!r}") from e
+        if tri.ndim != 2 or tri.shape[1] != 3:
+            raise ValueError(f"triangles must be a (N, 3) int array, but found shape {tri.shape!r}")
+        if tri.size and tri.max() >= len(pos):
+            raise ValueError("triangles are indices into the points and must be in the range "
+                             f"0 <= i < {len(pos)} but found value {tri.max()}")
+        if tri.size and tri.min() < 0:
+            raise ValueError("triangles are indices into the points and must be in the range "
+                             f"0 <= i < {len(pos)} but found value {tri.min()}")
+        if tri.shape[0] == 0:
+            raise ValueError("triangles must be a (N, 3) int array with N >= 1")
+        pos32 = np.ascontiguousarray(pos, dtype=F32)
+        self.x, self.y, self.triangles = pos32[:, 0].astype(F64), pos32[:, 1].astype(F64), tri
+        self.n_nodes, self.n_cells = len(pos32), len(tri)
+        self.numpy_semantics = numpy_semantics or default_numpy_semantics()
+        x_min, y_min = np.min(pos32, axis=0)                    # mesh_utils.py:99-100
+        x_max, y_max = np.max(pos32, axis=0)
+        self.ax, self.ay = _grid_axes(float(x_min), float(x_max), float(y_min), float(y_max), int(grid_res),
+                                      self.numpy_semantics)
+        self.nx, self.ny = len(self.ax), len(self.ay)
+        dev = self.device
+        with torch.cuda.device(dev):
+            self.pos_d = torch.from_numpy(pos32).to(dev)
+            self.cells_d = torch.from_numpy(tri).to(dev)
+            self.ax_d = torch.from_numpy(self.ax).to(dev)
+            self.ay_d = torch.from_numpy(self.ay).to(dev)
+            n = self.nx * self.ny
+            self.tri_index_d = torch.empty((self.nx, self.ny), dtype=torch.int32, device=dev)
+            self.cell_idx_d = torch.empty((n, 4), dtype=torch.int32, device=dev)
+            self.cell_w_d = torch.empty((n, 2), dtype=torch.float64, device=dev)
+            lib = load()
+            ws_bytes = int(lib.fl_locate_workspace_bytes(self.n_nodes, self.n_cells))
+            for _ in range(2):
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                rc = lib.fl_locate(ptr(self.pos_d), ptr(self.cells_d), self.n_nodes, self.n_cells, ptr(self.ax_d),
+                                   ptr(self.ay_d), self.nx, self.ny, ptr(self.tri_index_d), ptr(self.cell_idx_d),
+                                   ptr(self.cell_w_d), ptr(ws), ws_bytes, stream_ptr())
+                if rc != -3:
+                    break
+                ws_bytes *= 8          # very uneven meshes: retry once with a larger bin-item store
+            check(rc, "fl_locate")
+        self._tables = {}
+        self._tri_index_host = None
+
+    # -- reference-shaped views -------------------------------------------------------------
+    @property
+    def grid_x(self):
+        return np.ascontiguousarray(np.broadcast_to(self.ax[:, None], (self.nx, self.ny)))
+
+    @property
+    def grid_y(self):
+        return np.ascontiguousarray(np.broadcast_to(self.ay[None, :], (self.nx, self.ny)))
+
+    @property
+    def tri_index(self):
+        """int32 (nx, ny) on the host, what `triang.get_trifinder()(grid_x, grid_y)` returns."""
+        if self._tri_index_host is None:
+            self._tri_index_host = self.tri_index_d.cpu().numpy()
+        return self._tri_index_host
+
+    def patch_table(self, patch_size, crop_patches=0, flip_y=False) -> PatchTable:
+        key = (int(patch_size[0]), int(patch_size[1]), int(crop_patches), bool(flip_y))
+        tab = self._tables.get(key)
+        if tab is None:
+            px, py = key[0], key[1]
+            lib = load()
+            nbx, nby = ctypes.c_int(0), ctypes.c_int(0)
+            flags = FL_FLIP_Y if flip_y else 0
+            check(lib.fl_plan_patch_table(None, None, self.nx, self.ny, px, py, key[2], flags, None, None,
+                                          ctypes.byref(nbx), ctypes.byref(nby), None), "fl_plan_patch_table")
+            if nbx.value < 1 or nby.value < 1:
+                raise ValueError(f"no patches left: grid {self.nx}x{self.ny}, patch {px}x{py}, crop {key[2]}")
+            total = nbx.value * nby.value * px * py
+            with torch.cuda.device(self.device):
+                idx = torch.empty((total, 4), dtype=torch.int32, device=self.device)
+                w = torch.empty((total, 2), dtype=torch.float64, device=self.device)
+                check(lib.fl_plan_patch_table(ptr(self.cell_idx_d), ptr(self.cell_w_d), self.nx, self.ny, px, py, key[2],
+                                              flags, ptr(idx), ptr(w), ctypes.byref(nbx), ctypes.byref(nby),
+                                              stream_ptr()), "fl_plan_patch_table")
+            tab = PatchTable(idx, w, nbx.value, nby.value, px, py)
+            self._tables[key] = tab
+        return tab
+
+
+def get_mesh_interpolation(pos, faces, grid_res=238, numpy_semantics=None, device=None):
+    """mesh_utils.py:94-106: -> (triang, tri_index int32 (nx,ny), grid_x, grid_y float32 (nx,ny)).
+
+    `triang` is a MeshPlan; `tri_index`/`grid_*` are host arrays as in the reference."""
+    if torch.is_tensor(pos):
+        pos = pos.detach().cpu().numpy()
+    if torch.is_tensor(faces):
+        faces = faces.detach().cpu().numpy()
+    plan = MeshPlan(pos, faces, grid_res, numpy_semantics, device)
+    return plan, plan.tri_index, plan.grid_x, plan.grid_y
+
+
+def to_grid(val, grid_x, grid_y, triang: MeshPlan, tri_index):
+    """mesh_utils.py:82-91: one scalar node field -> (data float32 (nx,ny), mask bool (nx,ny)).
+
+    NumPy in -> NumPy out (the reference's contract); a CUDA tensor in -> CUDA tensors out.
+    `val` may also be (n_fields, N): all fields are gridded in one launch."""
+    if not isinstance(triang, MeshPlan):
+        raise TypeError("triang must be the MeshPlan returned by get_mesh_interpolation")
+    as_torch = torch.is_tensor(val)
+    v = val if as_torch else torch.from_numpy(np.ascontiguousarray(np.asarray(val), dtype=F32))
+    single = v.dim() == 1
+    if v.shape[-1:] != (triang.n_nodes,) or v.dim() > 2:
+        raise ValueError("z array must have same length as triangulation x and y arrays")
+    if tuple(np.shape(grid_x)) != tuple(np.shape(grid_y)):
+        raise ValueError(f"x and y shall have same shapes. Given: {np.shape(grid_x)} and {np.shape(grid_y)}")
+    if tuple(np.shape(tri_index)) != tuple(np.shape(grid_x)):
+        raise ValueError("tri_index array is provided and shall have same shape as x and y. "
+                         f"Given: {np.shape(tri_index)} and {np.shape(grid_x)}")
+    if tuple(np.shape(grid_x)) != (triang.nx, triang.ny):
+        raise ValueError(f"grid of shape {np.shape(grid_x)} does not belong to this mesh plan "
+                         f"({triang.nx}, {triang.ny})")
+    dev = triang.device
+    with torch.cuda.device(dev):
+        v = v.to(device=dev, dtype=torch.float32).reshape(-1, triang.n_nodes).contiguous()
+        nf = v.shape[0]
+        data = torch.empty((nf, triang.nx, triang.ny), dtype=torch.float32, device=dev)
+        mask = torch.empty((nf, triang.nx, triang.ny), dtype=torch.uint8, device=dev)
+        check(load().fl_to_grid(ptr(triang.cell_idx_d), ptr(triang.cell_w_d), triang.nx, triang.ny, ptr(v), nf,
+                                triang.n_nodes, ptr(data), ptr(mask), stream_ptr()), "fl_to_grid")
+    mask = mask.bool()
+    if single:
+        data, mask = data[0], mask[0]
+    if as_torch:
+        return data, mask
+    return data.cpu().numpy(), mask.cpu().numpy()

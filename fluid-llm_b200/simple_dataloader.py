@@ -1,0 +1,142 @@
+"""`MGNDataset` (Cylinder flow) on the GPU data path.
+
+Host-side mirror of `/root/reference/src/dataloader/simple_dataloader.py:23-229`: same constructor,
+same attributes (`N_x_patch`, `N_y_patch`, `N_patch`, `patch_size`, `seq_len`, `ds_min_max`,
+`save_files`), same 5-tuple from `__getitem__` / `ds_get`.  The per-frame work (3x to_grid, pad,
+mask concat, unfold, permute, normalise) is one launch of csrc/fl_interp.cu; the triangle finder
+is built once per trajectory file and cached (the reference rebuilds it on every `__getitem__`,
+simple_dataloader.py:181), together with the node fields resident in HBM.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import random
+from collections import OrderedDict
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from .field_path import CYLINDER, DeviceTrajectory, Personality, interp_patchify
+from .mesh_utils import MeshPlan
+
+
+def num_patches(dim_size, kern_size, stride, padding=0):
+    """simple_dataloader.py:16-20."""
+    return (dim_size + 2 * padding - kern_size) // stride + 1
+
+
+class _GpuFieldDataset(Dataset):
+    """Shared machinery of MGNDataset / AirfoilDataset."""
+
+    personality: Personality = CYLINDER
+    cache_size = 8   # trajectories kept resident on the device (plan + node fields)
+
+    def __init__(self, load_dir, resolution: int, patch_size: tuple, stride: tuple, seq_len: int, seq_interval=1,
+                 pad=True, mode="train", normalize=True, noise=None, device=None, output_device=None,
+                 numpy_semantics=None):
+        super().__init__()
+        assert mode in ["train", "valid", "test"]
+        if tuple(patch_size) != tuple(stride):
+            raise ValueError("the GPU data path patchifies with stride == patch_size (as the reference's configs do)")
+        if not pad:
+            raise ValueError("pad=False is not supported: the reference's unfold would silently drop the remainder")
+        self.mode = mode
+        self.load_dir = load_dir
+        self.resolution = resolution
+        self.patch_size = patch_size
+        self.stride = stride
+        self.pad = pad
+        self.seq_len = seq_len
+        self.seq_interval = seq_interval
+        self.max_step_num = 600 - self.seq_len * self.seq_interval
+        self.normalize = normalize
+        self.noise = noise
+        self.device = device
+        self.output_device = output_device     # None: tensors stay on the GPU; "cpu": reference-style host tensors
+        self.numpy_semantics = numpy_semantics
+        self._cache = OrderedDict()
+        self._pos_ids = None
+
+        self.save_files = self._list_files()
+        # simple_dataloader.py:45-56: probe file [1], step 20, for value ranges and the patch grid
+        traj = self._load_step(self.save_files[1])
+        states, _, tab = interp_patchify(traj, 20, 1, 1, self.patch_size, self.personality, normalize=False)
+        lo, hi = states[0].amin(dim=(0, 2, 3)).cpu().numpy(), states[0].amax(dim=(0, 2, 3)).cpu().numpy()
+        self.ds_min_max = [(lo[0], hi[0]), (lo[1], hi[1]), (lo[2], hi[2])]
+        self.N_x_patch, self.N_y_patch = tab.n_bx, tab.n_by
+        self.N_patch = self.N_x_patch * self.N_y_patch
+
+    # -- file handling ----------------------------------------------------------------------
+    def _list_files(self):
+        return sorted([f for f in os.listdir(f"{self.load_dir}/") if f.endswith('.pkl')])
+
+    def _prepare_mesh(self, save_data):
+        """-> (pos, faces, velocity, pressure) as the locate step should see them."""
+        return save_data['mesh_pos'], save_data['cells'], save_data['velocity'], save_data['pressure']
+
+    def _load_step(self, save_file) -> DeviceTrajectory:
+        """simple_dataloader.py:154-164: unpickle + mesh interpolation set-up (cached per file)."""
+        path = f"{self.load_dir}/{save_file}"
+        key = (path, os.path.getmtime(path))
+        traj = self._cache.get(key)
+        if traj is not None:
+            self._cache.move_to_end(key)
+            return traj
+        with open(path, 'rb') as f:
+            save_data = pickle.load(f)
+        pos, faces, vel, prs = self._prepare_mesh(save_data)
+        plan = MeshPlan(pos, faces, self.resolution, self.numpy_semantics, self.device)
+        traj = DeviceTrajectory(vel, prs, plan)
+        self._cache[key] = traj
+        while len(self._cache) > self.cache_size:
+            self._cache.popitem(last=False)
+        return traj
+
+    # -- reference API ------------------------------------------------------------------------
+    def __getitem__(self, idx):
+        # simple_dataloader.py:67-70: random start in train, fixed 100 otherwise
+        step_num = random.randint(0, self.max_step_num)
+        step_num = 100 if self.mode in ["test", "valid"] else step_num
+        return self.ds_get(save_file=self.save_files[idx], step_num=step_num)
+
+    def ds_get(self, save_file=None, step_num=None):
+        """simple_dataloader.py:72-102 -> (input_states, next_state, diffs, masks, position_ids)."""
+        if save_file is None:
+            save_file = random.choice(self.save_files)
+        elif isinstance(save_file, int):
+            save_file = self.save_files[save_file]
+        if step_num is None:
+            step_num = np.random.randint(0, self.max_step_num)
+        if step_num > self.max_step_num:          # simple_dataloader.py:177-179
+            step_num = self.max_step_num
+        traj = self._load_step(save_file)
+        states, mask, _ = interp_patchify(traj, step_num, self.seq_len, self.seq_interval, self.patch_size,
+                                          self.personality, normalize=self.normalize)
+        diffs = states[1:] - states[:-1]                                  # :93
+        masks = mask[1:].unsqueeze(2).repeat(1, 1, 3, 1, 1).bool()         # :100
+        out = (states[:-1], states[1:], diffs, masks, self._get_pos_id().to(states.device))
+        if self.output_device is not None:
+            out = tuple(t.to(self.output_device) for t in out)
+        return out
+
+    def _get_pos_id(self):
+        """simple_dataloader.py:218-226 (the labelling quirk is reproduced as is)."""
+        if self._pos_ids is None:
+            seq_dim = (self.seq_len - 1) * self.N_patch
+            arange = np.arange(seq_dim)
+            x_idx = arange % self.N_x_patch
+            y_idx = (arange // self.N_x_patch) % self.N_y_patch
+            t_idx = arange // self.N_patch
+            ids = np.stack([x_idx, y_idx, t_idx], axis=1).reshape(self.seq_len - 1, self.N_patch, 3)
+            self._pos_ids = torch.from_numpy(ids.astype(np.int64))
+        return self._pos_ids
+
+    def __len__(self):
+        return len(self.save_files)
+
+
+class MGNDataset(_GpuFieldDataset):
+    """Load a sequence of timesteps of one Cylinder-flow trajectory (simple_dataloader.py:23)."""
+    personality = CYLINDER

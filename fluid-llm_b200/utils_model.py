@@ -1,0 +1,115 @@
+"""Patch <-> image ops and the rollout-step glue on the GPU.
+
+Mirror of `/root/reference/src/utils_model.py:77-109` (`patch_to_img`, `img_to_patch`) and of the
+per-step glue of `/root/reference/src/models/model.py:164,206,210`.  Both permutations are
+dtype-preserving and differentiable (the reference uses them inside the training graph,
+src/trainer.py:95-98): the backward of one is the other.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, load, ptr, stream_ptr
+from .ds_props import DSProps
+
+
+def _perm(fn_name, src, dst, B, n_bx, n_by, C, px, py):
+    with torch.cuda.device(src.device):
+        check(getattr(load(), fn_name)(ptr(src), ptr(dst), B, n_bx, n_by, C, px, py, src.element_size(), stream_ptr()),
+              fn_name)
+
+
+def _check_tensor(t, name):
+    if not t.is_cuda:
+        raise _lib.FluidGridError(f"{name}: expected a CUDA tensor (the fluidgrid data path has no CPU fallback)")
+    if t.element_size() not in (2, 4):
+        raise ValueError(f"{name}: only 2- and 4-byte element types are supported, got {t.dtype}")
+
+
+class _PatchToImg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, patches, n_bx, n_by):
+        B, L, C, px, py = patches.shape
+        ctx.geom = (n_bx, n_by)
+        img = torch.empty((B, C, n_bx * px, n_by * py), dtype=patches.dtype, device=patches.device)
+        _perm("fl_patch_to_img", patches.contiguous(), img, B, n_bx, n_by, C, px, py)
+        return img
+
+    @staticmethod
+    def backward(ctx, g):
+        n_bx, n_by = ctx.geom
+        B, C, X, Y = g.shape
+        px, py = X // n_bx, Y // n_by
+        out = torch.empty((B, n_bx * n_by, C, px, py), dtype=g.dtype, device=g.device)
+        _perm("fl_img_to_patch", g.contiguous(), out, B, n_bx, n_by, C, px, py)
+        return out, None, None
+
+
+class _ImgToPatch(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, n_bx, n_by):
+        B, C, X, Y = img.shape
+        px, py = X // n_bx, Y // n_by
+        ctx.geom = (n_bx, n_by)
+        out = torch.empty((B, n_bx * n_by, C, px, py), dtype=img.dtype, device=img.device)
+        _perm("fl_img_to_patch", img.contiguous(), out, B, n_bx, n_by, C, px, py)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n_bx, n_by = ctx.geom
+        B, L, C, px, py = g.shape
+        img = torch.empty((B, C, n_bx * px, n_by * py), dtype=g.dtype, device=g.device)
+        _perm("fl_patch_to_img", g.contiguous(), img, B, n_bx, n_by, C, px, py)
+        return img, None, None
+
+
+def patch_to_img(patches, ds_props: DSProps):
+    """utils_model.py:77-92: (bs, seq_len, N_patch, C, px, py) -> (bs, seq_len, C, tot_px, tot_py)."""
+    _check_tensor(patches, "patch_to_img")
+    bs, seq_len, N_patch, channel, px, py = patches.shape
+    px_patch, py_patch = ds_props.patch_size
+    channel = ds_props.channel
+    tot_px, tot_py = ds_props.input_tot_size
+    if N_patch != ds_props.N_patch or (px, py) != (px_patch, py_patch) or patches.shape[3] != channel:
+        raise ValueError(f"patches of shape {tuple(patches.shape)} do not match ds_props "
+                         f"(N_patch={ds_props.N_patch}, channel={channel}, patch_size={ds_props.patch_size})")
+    img = _PatchToImg.apply(patches.reshape(bs * seq_len, N_patch, channel, px, py), ds_props.Nx_patch, ds_props.Ny_patch)
+    return img.view(bs, seq_len, channel, tot_px, tot_py)
+
+
+def img_to_patch(img, ds_props: DSProps):
+    """utils_model.py:95-109: (bs, seq_len, C, tot_px, tot_py) -> (bs, seq_len, N_patch, C, px, py)."""
+    _check_tensor(img, "img_to_patch")
+    bs, seq_len, channel, tot_px, tot_py = img.shape
+    px_patch, py_patch = ds_props.patch_size
+    if (tot_px, tot_py) != (ds_props.Nx_patch * px_patch, ds_props.Ny_patch * py_patch) or channel != ds_props.channel:
+        raise ValueError(f"image of shape {tuple(img.shape)} does not match ds_props "
+                         f"(input_tot_size={ds_props.input_tot_size}, channel={ds_props.channel})")
+    out = _ImgToPatch.apply(img.reshape(bs * seq_len, channel, tot_px, tot_py), ds_props.Nx_patch, ds_props.Ny_patch)
+    return out.view(bs, seq_len, ds_props.N_patch, channel, px_patch, py_patch)
+
+
+def rollout_step(last_state, pred_diff_img, mask, ds_props: DSProps):
+    """model.py:164,206,210 fused into one kernel (fp32, inference only):
+
+        diffs = img_to_patch(pred_diff_img);  diffs[mask] = 0.;  next_state = last_state + diffs
+
+    last_state (bs, 1, N_patch, C, px, py), pred_diff_img (bs, 1, C, tot_px, tot_py),
+    mask bool (bs, 1, N_patch, C, px, py) -> (next_state, diffs)."""
+    for t, n in ((last_state, "last_state"), (pred_diff_img, "pred_diff_img"), (mask, "mask")):
+        if not t.is_cuda:
+            raise _lib.FluidGridError(f"rollout_step: {n} must be a CUDA tensor")
+    if last_state.dtype != torch.float32 or pred_diff_img.dtype != torch.float32:
+        raise ValueError("rollout_step computes in float32 (model.py keeps states in fp32)")
+    bs, T, N_patch, C, px, py = last_state.shape
+    if mask.shape != last_state.shape or pred_diff_img.shape != (bs, T, C, ds_props.Nx_patch * px, ds_props.Ny_patch * py):
+        raise ValueError("rollout_step: shapes of last_state, mask and pred_diff_img do not agree with ds_props")
+    last_c, img_c = last_state.contiguous(), pred_diff_img.contiguous()
+    m = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous()
+    diffs, nxt = torch.empty_like(last_c), torch.empty_like(last_c)
+    with torch.cuda.device(last_c.device):
+        check(load().fl_rollout_step(ptr(img_c), ptr(m), ptr(last_c), ptr(diffs), ptr(nxt), bs * T, ds_props.Nx_patch,
+                                     ds_props.Ny_patch, C, px, py, stream_ptr()), "fl_rollout_step")
+    return nxt, diffs

@@ -1,0 +1,146 @@
+/* fluidgrid.h -- C ABI of libfluidgrid.so: FLUID-LLM's per-timestep field data path on B200.
+ *
+ * The reference (dewan1988/FLUID-LLM) has no FFI: the path sits behind plain Python call
+ * signatures whose arithmetic lives in matplotlib's C++ `_tri` module.  Each entry point below
+ * names the reference interface it replaces (paths relative to the reference root); the Python
+ * host package (fluid-llm_b200/) keeps the reference's own names on top of these calls and
+ * INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  Pointers named d_* are DEVICE pointers owned by the
+ *     caller (torch owns the memory; the library never frees or keeps them past the call);
+ *     h_* are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     enqueued asynchronously on it; nothing synchronises unless stated.
+ *   - return 0 = ok, < 0 = argument error (FL_E_*), > 0 = a cudaError_t.  fl_last_error()
+ *     returns a thread-local message for the last non-zero return.
+ *   - there is NO CPU fallback: without a CUDA device every compute call returns an error.
+ */
+#ifndef FLUIDGRID_H
+#define FLUIDGRID_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FL_OK 0
+#define FL_E_ARG (-1)      /* null pointer / non-positive size / bad flag */
+#define FL_E_RANGE (-2)    /* index out of range (e.g. a cell vertex >= n_nodes) */
+#define FL_E_WORKSPACE (-3)/* workspace too small */
+#define FL_E_ALIGN (-4)    /* pointer not aligned as documented */
+
+#define FL_ABI_VERSION 1
+
+/* personality flags of fl_plan_patch_table / fl_interp_patchify */
+#define FL_FLIP_Y 1u          /* airfoil_ds.py:80  -- y axis reversed after padding */
+#define FL_MASK_AWARE_NORM 2u /* airfoil_ds.py:236-242 -- masked pixels stay 0, others normalised */
+#define FL_NO_NORM 4u         /* normalize=False */
+
+/* One grid cell of the static per-mesh table (the product's own intermediate; the reference
+ * recomputes the plane coefficients of every triangle per channel per frame instead,
+ * src/_triinterpolate.py:262-263).  v[k] = node ids of the containing triangle in its
+ * counter-clockwise-corrected order, tri = its index (-1: outside the mesh / in a hole / pad),
+ * w1, w2 = barycentric weights of v[1], v[2] in fp64 (weight of v[0] is 1 - w1 - w2). */
+typedef struct FlCellIdx { int32_t v0, v1, v2, tri; } FlCellIdx;   /* 16 B */
+typedef struct FlCellW { double w1, w2; } FlCellW;                 /* 16 B */
+
+int fl_abi_version(void);
+const char* fl_last_error(void);
+/* number of CUDA devices visible (0 if none / driver missing); never fails */
+int fl_device_count(void);
+
+/* ---- one-off per mesh: point location --------------------------------------------------------
+ * Replaces  src/dataloader/mesh_utils.py:103-104  (matplotlib Triangulation + TrapezoidMapTriFinder
+ * .find_many over the grid) and the per-triangle set-up of calculate_plane_coefficients.
+ * d_pos f32[n_nodes,2], d_cells i32[n_cells,3] (any winding), d_grid_ax f32[nx], d_grid_ay f32[ny]
+ * (the axes of grid_pos, mesh_utils.py:64-79; cell (ix,iy) is at (ax[ix], ay[iy])).
+ * Outputs, all [nx*ny] in the reference's [ix, iy] order (iy fastest):
+ *   d_tri_index i32 -- bit-exact with TrapezoidMapTriFinder incl. its tie-breaks: a query on a
+ *       mesh vertex -> lowest-index triangle listing it; on an edge -> the triangle above the
+ *       edge (left of the edge directed from its lexicographically smaller to larger end point),
+ *       else the one below; else the containing triangle; -1 if none.
+ *   d_cell_idx / d_cell_w -- the static table (may be NULL to skip).
+ * Workspace: fl_locate_workspace_bytes(n_nodes, n_cells) bytes, 256-B aligned. */
+size_t fl_locate_workspace_bytes(int n_nodes, int n_cells);
+int fl_locate(const float* d_pos, const int32_t* d_cells, int n_nodes, int n_cells,
+              const float* d_grid_ax, const float* d_grid_ay, int nx, int ny,
+              int32_t* d_tri_index, FlCellIdx* d_cell_idx, FlCellW* d_cell_w,
+              void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Re-order the static table into output-pixel order for one dataset personality:
+ * pad to multiples of the patch (simple_dataloader.py:137-152), optional y flip
+ * (airfoil_ds.py:80), optional removal of `crop` outer rings of patches (airfoil_ds.py:132-133).
+ * Output index = (l*px + i)*py + j with l = bx*n_by + by (F.unfold order,
+ * simple_dataloader.py:131).  Padded pixels get tri = -1.
+ * d_out_idx/d_out_w: [n_bx*n_by*px*py].  n_bx/n_by are returned through out pointers (host). */
+int fl_plan_patch_table(const FlCellIdx* d_cell_idx, const FlCellW* d_cell_w, int nx, int ny,
+                        int px, int py, int crop_patches, unsigned flags,
+                        FlCellIdx* d_out_idx, FlCellW* d_out_w, int* h_n_bx, int* h_n_by, void* stream);
+
+/* ---- per step: gather -> fp64 FMA -> fp32 -> mask -> normalise -> patchify --------------------
+ * Replaces the body of  simple_dataloader.py:72-121,166-216 / airfoil_ds.py:71-122,189-244
+ * (3x to_grid per frame, pad, concat mask, F.unfold, permute, _normalize).
+ * One trajectory: d_velocity f32[T,n_nodes,2], d_pressure f32[T,n_nodes,1]; frames
+ * t0, t0+interval, ... (n_frames of them) are processed.
+ * d_states f32[n_frames, L, 3, px, py]; d_mask u8[n_frames, L, px, py] (NULL to skip; 1 = masked).
+ * mean[3], stds[3] are host floats.  flags: FL_MASK_AWARE_NORM, FL_NO_NORM. */
+typedef struct FlTraj {
+    const float* d_velocity;   /* [T, n_nodes, 2] */
+    const float* d_pressure;   /* [T, n_nodes, 1] */
+    const FlCellIdx* d_idx;    /* patch-ordered table of this trajectory's mesh */
+    const FlCellW* d_w;
+    float* d_states;           /* [n_frames, L, 3, px, py] */
+    uint8_t* d_mask;           /* [n_frames, L, px, py] or NULL */
+    int32_t n_nodes, t0, interval, n_frames;
+} FlTraj;
+
+int fl_interp_patchify(const FlTraj* h_trajs, int n_traj, int n_patches, int px, int py,
+                       const float* h_mean, const float* h_std, unsigned flags, void* stream);
+/* same, descriptors already on the device (no host->device copy of descriptors inside) */
+int fl_interp_patchify_dev(const FlTraj* d_trajs, int n_traj, int max_frames, int n_patches, int px, int py,
+                           const float* h_mean, const float* h_std, unsigned flags, void* stream);
+
+/* Plain-grid variant (no pad/patchify): replaces mesh_utils.to_grid (src/dataloader/mesh_utils.py:82-91)
+ * for n_fields scalar node fields at once.  d_val f32[n_fields, n_nodes] -> d_data f32[n_fields, nx*ny],
+ * d_mask u8[n_fields, nx*ny] (1 = outside mesh or non-finite). */
+int fl_to_grid(const FlCellIdx* d_cell_idx, const FlCellW* d_cell_w, int nx, int ny,
+               const float* d_val, int n_fields, int n_nodes, float* d_data, uint8_t* d_mask, void* stream);
+
+/* ---- inverse path --------------------------------------------------------------------------- */
+/* src/utils_model.py:77-92 patch_to_img: patches [B, L, C, px, py] -> img [B, C, n_bx*px, n_by*py].
+ * elem_size 2 or 4 (bf16/fp16 or fp32; pure permutation). */
+int fl_patch_to_img(const void* d_patches, void* d_img, int B, int n_bx, int n_by, int C, int px, int py,
+                    int elem_size, void* stream);
+/* src/utils_model.py:95-109 img_to_patch: the inverse permutation. */
+int fl_img_to_patch(const void* d_img, void* d_patches, int B, int n_bx, int n_by, int C, int px, int py,
+                    int elem_size, void* stream);
+/* src/models/model.py:164,206,210 fused: diffs = img_to_patch(pred_img); diffs[mask] = 0;
+ * next = last + diffs.  fp32.  d_pred_img [B, C, X, Y], d_mask u8 [B, L, C, px, py],
+ * d_last [B, L, C, px, py] -> d_diffs, d_next same shape. */
+int fl_rollout_step(const float* d_pred_img, const uint8_t* d_mask, const float* d_last,
+                    float* d_diffs, float* d_next, int B, int n_bx, int n_by, int C, int px, int py,
+                    void* stream);
+/* eagle/Dataloader/IMG_Eagle.py:93-123 grid2mesh: nearest-cell grid -> node resample.
+ * d_grid f32[T, H, W, C] (row 0 = Ymin, flipped inside as the reference does), d_mesh_pos f32[T, N, 2]
+ * -> d_out f32[T, N, C].  Extents/steps are the reference's constants unless overridden;
+ * index arithmetic in float32 exactly as NumPy 1.26 evaluates it.  Negative row indices wrap. */
+int fl_grid2mesh(const float* d_grid, const float* d_mesh_pos, float* d_out, int T, int N, int H, int W, int C,
+                 float x_min, float y_min, double step_x, double step_y, void* stream);
+
+/* ---- dataset statistics (max/compute_ds_stats.py:20-34,52-62) ---------------------------------
+ * Per-channel (n, mean, M2) of states and of diffs (states[t+1]-states[t]) over unmasked pixels.
+ * d_states f32[T, L, 3, px, py], d_mask u8[T, L, px, py]; d_agg f64[18] =
+ * {state ch0..2, diff ch0..2} x {n, mean, M2}; overwritten.  Masked diff pixels use mask[t+1]. */
+size_t fl_stats_workspace_bytes(void);
+int fl_ds_stats(const float* d_states, const uint8_t* d_mask, int T, int L, int px, int py,
+                double* d_agg, void* d_workspace, size_t workspace_bytes, void* stream);
+/* fixed-order Chan merge of n_parts aggregates (each f64[18]) -> d_out f64[18] */
+int fl_stats_merge(const double* d_parts, int n_parts, double* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUIDGRID_H */

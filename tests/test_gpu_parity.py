@@ -1,0 +1,168 @@
+"""-m gpu: the CUDA path (through the C ABI) against the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpl_tri
+from oracle import pipeline as P
+
+from helpers import PATCH, oracle_ds_get, personality_of, tie_mesh, trajectory
+
+pytestmark = pytest.mark.gpu
+
+
+def _plan(kind, sem="1.26", res=238):
+    from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    tr = trajectory(kind)
+    pos, faces = tr["mesh_pos"], tr["cells"]
+    if kind == "airfoil":
+        _, pos, faces = crop_airfoil_mesh(pos, faces)
+    return MeshPlan(pos, faces, res, sem), pos, faces
+
+
+@pytest.mark.parametrize("kind", ["cylinder", "airfoil", "eagle"])
+@pytest.mark.parametrize("sem", ["1.26", "2.x"])
+def test_locate_tri_ids_bit_exact(kind, sem):
+    plan, pos, faces = _plan(kind, sem)
+    triang, tri_o, gx, gy = P.get_mesh_interpolation(pos, faces, 238, sem)
+    assert plan.tri_index.dtype == np.int32 and plan.tri_index.shape == tri_o.shape
+    assert np.array_equal(plan.grid_x, gx) and np.array_equal(plan.grid_y, gy)
+    assert np.array_equal(plan.tri_index, tri_o)
+    assert (tri_o == -1).sum() > 0 or kind == "airfoil"
+
+
+def test_locate_tie_breaks_hand_built():
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    pos, tris = tie_mesh()
+    # resolution 9 puts grid points on every lattice vertex and edge midpoint of the 4x4 lattice
+    for res in (9, 5, 17, 33):
+        plan = MeshPlan(pos, tris, res, "1.26")
+        triang, tri_o, gx, gy = P.get_mesh_interpolation(pos, tris, res, "1.26")
+        assert np.array_equal(plan.tri_index, tri_o), res
+        assert np.array_equal(plan.tri_index, mpl_tri.rule_find_many(triang, gx, gy, bucketed=False))
+
+
+def test_locate_weights():
+    plan, pos, faces = _plan("cylinder")
+    triang, tri_o, gx, gy = P.get_mesh_interpolation(pos, faces, 238, "1.26")
+    idx = plan.cell_idx_d.cpu().numpy().reshape(plan.nx, plan.ny, 4)
+    w = plan.cell_w_d.cpu().numpy().reshape(plan.nx, plan.ny, 2)
+    ct = triang.corrected_triangles
+    inside = tri_o >= 0
+    assert np.array_equal(idx[..., 3], tri_o)
+    assert np.array_equal(idx[inside][:, :3], ct[tri_o[inside]])
+    x, y = pos[:, 0].astype(np.float64), pos[:, 1].astype(np.float64)
+    v = idx[inside][:, :3]
+    w1, w2 = w[inside][:, 0], w[inside][:, 1]
+    w0 = 1 - w1 - w2
+    rx = w0 * x[v[:, 0]] + w1 * x[v[:, 1]] + w2 * x[v[:, 2]]
+    ry = w0 * y[v[:, 0]] + w1 * y[v[:, 1]] + w2 * y[v[:, 2]]
+    assert np.abs(rx - gx[inside]).max() < 1e-12 and np.abs(ry - gy[inside]).max() < 1e-12
+    assert w0.min() > -1e-12 and w1.min() > -1e-12 and w2.min() > -1e-12    # partition of unity, inside
+
+
+def test_locate_rejects_bad_indices():
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    pos, tris = tie_mesh()
+    bad = tris.copy()
+    bad[3, 1] = 99
+    with pytest.raises(ValueError):
+        MeshPlan(pos, bad, 9)
+    with pytest.raises(ValueError):
+        MeshPlan(pos, tris[:, :2], 9)
+
+
+@pytest.mark.parametrize("kind", ["cylinder", "airfoil", "eagle"])
+def test_to_grid_matches_oracle(kind):
+    from fluid_llm_b200.mesh_utils import get_mesh_interpolation, to_grid
+    tr = trajectory(kind)
+    plan, pos, faces = _plan(kind)
+    nmask = slice(None)
+    if kind == "airfoil":
+        from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
+        nmask, _, _ = crop_airfoil_mesh(tr["mesh_pos"], tr["cells"])
+    triang_o, tri_o, gx, gy = P.get_mesh_interpolation(pos, faces, 238, "1.26")
+    triang, tri_index, grid_x, grid_y = get_mesh_interpolation(pos, faces, 238, "1.26")
+    assert np.array_equal(tri_index, tri_o)
+    for ch, val in enumerate([tr["velocity"][3][nmask][:, 0], tr["velocity"][3][nmask][:, 1], tr["pressure"][3][nmask][:, 0]]):
+        d, m = to_grid(val, grid_x, grid_y, triang, tri_index)
+        d_o, m_o = P.to_grid(val, gx, gy, triang_o, tri_o)
+        assert d.dtype == np.float32 and m.dtype == bool
+        assert np.array_equal(m, m_o)
+        assert np.array_equal(d, d_o), f"{kind} ch{ch}: {(d != d_o).sum()} of {d.size} values differ"
+    with pytest.raises(ValueError):
+        to_grid(val[:-1], grid_x, grid_y, triang, tri_index)
+    with pytest.raises(ValueError):
+        to_grid(val, grid_x, grid_y, triang, tri_index[:-1])
+
+
+def test_to_grid_nonfinite_values_are_masked():
+    from fluid_llm_b200.mesh_utils import get_mesh_interpolation, to_grid
+    tr = trajectory("cylinder")
+    pos, faces = tr["mesh_pos"], tr["cells"]
+    triang_o, tri_o, gx, gy = P.get_mesh_interpolation(pos, faces, 238)
+    triang, tri_index, grid_x, grid_y = get_mesh_interpolation(pos, faces, 238)
+    val = tr["pressure"][0][:, 0].copy()
+    val[100] = np.nan
+    val[200] = np.inf
+    d, m = to_grid(val, grid_x, grid_y, triang, tri_index)
+    d_o, m_o = P.to_grid(val, gx, gy, triang_o, tri_o)
+    assert np.array_equal(m, m_o) and np.array_equal(d, d_o)
+    assert m.sum() > (tri_o == -1).sum()
+
+
+@pytest.mark.parametrize("kind", ["cylinder", "airfoil", "eagle"])
+@pytest.mark.parametrize("normalize", [True, False])
+def test_interp_patchify_matches_oracle(kind, normalize):
+    """states / mask of the fused kernel == the oracle's unfold+normalise pipeline, bit for bit
+    (north_star tolerance: 1e-6 relative; achieved: exact on these inputs)."""
+    from fluid_llm_b200.field_path import AIRFOIL, CYLINDER, DeviceTrajectory, interp_patchify
+    from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
+    tr = trajectory(kind)
+    plan, pos, faces = _plan(kind)
+    vel, prs = tr["velocity"], tr["pressure"]
+    if kind == "airfoil":
+        nmask, _, _ = crop_airfoil_mesh(tr["mesh_pos"], tr["cells"])
+        vel, prs = vel[:, nmask], prs[:, nmask]
+    pers = AIRFOIL if kind == "airfoil" else CYLINDER
+    states, mask, tab = interp_patchify(DeviceTrajectory(vel, prs, plan), 1, 3, 2, PATCH, pers, normalize=normalize)
+    (_, _, _, _, _), extra = oracle_ds_get(kind, 1, 3, 2, normalize=normalize)
+    assert (tab.n_bx, tab.n_by) == (extra["N_x_patch"], extra["N_y_patch"])
+    assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
+    s, so = states.cpu().numpy(), extra["states"]
+    assert s.shape == so.shape and s.dtype == so.dtype
+    np.testing.assert_allclose(s, so, rtol=1e-6, atol=0)
+    assert np.array_equal(s, so), f"{(s != so).sum()} of {s.size} values differ in the last bit"
+
+
+def test_interp_patchify_batch_of_meshes():
+    """One launch over several trajectories with different meshes, different start frames."""
+    from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, TrajBatch
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    trajs, tabs, t0s, want = [], [], [1, 0, 3], []
+    for seed, t0 in zip((0, 1, 2), t0s):
+        tr = trajectory("cylinder", 8, seed, 10 + seed)
+        plan = MeshPlan(tr["mesh_pos"], tr["cells"], 238)
+        trajs.append(DeviceTrajectory(tr["velocity"], tr["pressure"], plan))
+        tabs.append(plan.patch_table(PATCH))
+        want.append(oracle_ds_get("cylinder", t0, 4, 1, mesh_seed=seed, field_seed=10 + seed)[1])
+    batch = TrajBatch(trajs, tabs, t0s, 1, 4)
+    states, mask = batch.run(CYLINDER)
+    torch.cuda.synchronize()
+    for i, ex in enumerate(want):
+        assert np.array_equal(states[i].cpu().numpy(), ex["states"])
+        assert np.array_equal(mask[i].cpu().numpy().astype(bool), ex["masks"].astype(bool))
+    with pytest.raises(ValueError):
+        TrajBatch(trajs, tabs, [0, 0, 7], 1, 4)      # runs past the end of the trajectory
+
+
+def test_custom_mean_std():
+    from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
+    tr = trajectory("eagle")
+    plan, _, _ = _plan("eagle")
+    means, stds = (0.1, -0.2, 0.3), (1.5, 1.9, 6.3)
+    states, _, _ = interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 0, 2, 1, PATCH, CYLINDER,
+                                   means=means, stds=stds)
+    _, extra = oracle_ds_get("eagle", 0, 2, 1, means=means, stds=stds)
+    assert np.array_equal(states.cpu().numpy(), extra["states"])
