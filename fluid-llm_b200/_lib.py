@@ -12,12 +12,14 @@ LIB_PATH = os.path.join(HERE, "libfluidgrid.so")
 FL_FLIP_Y = 1
 FL_MASK_AWARE_NORM = 2
 FL_NO_NORM = 4
+FL_FORCE_GATHER = 8
 
 
 class FlTraj(ctypes.Structure):
     _fields_ = [("d_velocity", c_void_p), ("d_pressure", c_void_p), ("d_idx", c_void_p), ("d_w", c_void_p),
                 ("d_states", c_void_p), ("d_mask", c_void_p),
-                ("n_nodes", c_int32), ("t0", c_int32), ("interval", c_int32), ("n_frames", c_int32)]
+                ("n_nodes", c_int32), ("t0", c_int32), ("interval", c_int32), ("n_frames", c_int32),
+                ("vel_stride", c_int32), ("prs_stride", c_int32)]
 
 
 class FluidGridError(RuntimeError):
@@ -36,8 +38,8 @@ SIGNATURES = {
                                     POINTER(c_int), POINTER(c_int), c_void_p]),
     "fl_interp_patchify": (c_int, [POINTER(FlTraj), c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                    c_uint, c_void_p]),
-    "fl_interp_patchify_dev": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
-                                       c_uint, c_void_p]),
+    "fl_interp_patchify_dev": (c_int, [c_void_p, POINTER(FlTraj), c_int, c_int, c_int, c_int, POINTER(c_float),
+                                       POINTER(c_float), c_uint, c_void_p]),
     "fl_to_grid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "fl_patch_to_img": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fl_img_to_patch": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

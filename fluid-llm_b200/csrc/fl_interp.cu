@@ -10,6 +10,8 @@
 // fp64, from the static table), rounded once to fp32, then (v - mean) and / std in fp32 with
 // IEEE division, i.e. the same two roundings as simple_dataloader.py:213-214.
 #include "fl_common.cuh"
+#include <string.h>
+#include <math.h>
 
 namespace {
 
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(256) k_interp_patchify_gather(const FlTraj* __
         float v[3] = {0.f, 0.f, 0.f};
         bool masked = outside;
         if (!outside) {
-            interp3(tr.d_velocity + t * tr.n_nodes * 2, tr.d_pressure + t * tr.n_nodes, id, w0, w.w1, w.w2, v);
+            interp3(tr.d_velocity + t * tr.vel_stride, tr.d_pressure + t * tr.prs_stride, id, w0, w.w1, w.w2, v);
             masked = !finite_f(v[2]);                 // only the pressure mask is kept (simple_dataloader.py:114,119)
 #pragma unroll
             for (int c = 0; c < 3; ++c) if (!finite_f(v[c])) v[c] = 0.f;   // mesh_utils.py:89, per channel
@@ -93,11 +95,229 @@ __global__ void k_to_grid(const FlCellIdx* __restrict__ idx, const FlCellW* __re
     }
 }
 
-int launch_interp(const FlTraj* d_trajs, int n_traj, int max_frames, int n_patches, int px, int py, const float* h_mean,
-                  const float* h_std, unsigned flags, cudaStream_t st) {
+
+// ------------------------------------------------------------------------------------------
+// Staged kernel (the fast path).  One persistent CTA per SM; a work item is TF consecutive
+// selected frames of one trajectory.  The frames' node arrays are bulk-copied (TMA,
+// cp.async.bulk + mbarrier) into shared memory in their global layout, every thread then walks
+// quads of 4 consecutive output pixels: the 4 table records are read once (coalesced 128-bit
+// loads, L2-resident) and reused for all TF frames, node values are gathered from shared memory,
+// results leave as 128-bit streaming stores (each warp store covers 512 contiguous bytes).
+//   HBM traffic: 12 N + 12 P bytes per frame (compulsory) ; L2 -> SM: + 32 P / TF (table).
+// Arithmetic per pixel-frame: 9 f32->f64, 3 DMUL + 6 DFMA, 3 f64->f32, then (v - mean) / std as
+// a reciprocal multiply with one Markstein correction step (bit-identical to IEEE division for
+// the ranges checked on the host and in the staging scan; anything else takes the checked path).
+// ------------------------------------------------------------------------------------------
+constexpr int ST_THREADS = 512;
+
+struct StagedConst {
+    float mean[3], stdv[3], rcp[3];
+    int fast_div;        // 1: Markstein division valid for these constants
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FL_DONE;\n"
+        "bra FL_WAIT;\n"
+        "FL_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// (x - mean) / std, correctly rounded: q = d*r, then one Markstein step with the exact remainder
+__device__ __forceinline__ float norm_fast(float x, float mean, float stdv, float rcp) {
+    float d = __fsub_rn(x, mean);
+    float q = __fmul_rn(d, rcp);
+    float e = __fmaf_rn(-q, stdv, d);
+    return __fmaf_rn(e, rcp, q);
+}
+
+template <bool CHECKED>
+__device__ __forceinline__ void staged_item(const FlTraj& tr, const float* __restrict__ s_vel, const float* __restrict__ s_prs,
+                                            int slot_vel, int slot_prs, int fbeg, int nf, int n_patches, int ppx,
+                                            const StagedConst& sc, unsigned flags) {
+    const bool mask_aware = flags & FL_MASK_AWARE_NORM, no_norm = flags & FL_NO_NORM;
+    const int nquads = n_patches * ppx / 4;
+    const size_t frame_out = (size_t)n_patches * 3 * ppx;
+    for (int q = threadIdx.x; q < nquads; q += ST_THREADS) {
+        int4 id[4];
+        double w0[4], w1[4], w2[4];
+        unsigned mbits = 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            id[r] = __ldg((const int4*)tr.d_idx + 4 * q + r);
+            const double2 ww = __ldg((const double2*)tr.d_w + 4 * q + r);
+            const bool out = id[r].w < 0;
+            mbits |= out ? (1u << (8 * r)) : 0u;
+            w1[r] = out ? 0.0 : ww.x;
+            w2[r] = out ? 0.0 : ww.y;
+            w0[r] = out ? 0.0 : 1.0 - ww.x - ww.y;
+            if (out) id[r].x = id[r].y = id[r].z = 0;
+        }
+        const int o = 4 * q, l = o / ppx, k = o - l * ppx;
+        float* dst = tr.d_states + ((size_t)fbeg * n_patches + l) * 3 * ppx + k;
+        uint8_t* mdst = tr.d_mask ? tr.d_mask + ((size_t)fbeg * n_patches + l) * ppx + k : nullptr;
+        for (int f = 0; f < nf; ++f) {
+            const float2* V = (const float2*)(s_vel + (size_t)f * slot_vel);
+            const float* Pr = s_prs + (size_t)f * slot_prs;
+            float res[3][4];
+            unsigned fm = mbits;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float2 a0 = V[id[r].x], a1 = V[id[r].y], a2 = V[id[r].z];
+                const float p0 = Pr[id[r].x], p1 = Pr[id[r].y], p2 = Pr[id[r].z];
+                res[0][r] = (float)fma(w2[r], (double)a2.x, fma(w1[r], (double)a1.x, w0[r] * (double)a0.x));
+                res[1][r] = (float)fma(w2[r], (double)a2.y, fma(w1[r], (double)a1.y, w0[r] * (double)a0.y));
+                res[2][r] = (float)fma(w2[r], (double)p2, fma(w1[r], (double)p1, w0[r] * (double)p0));
+                if (CHECKED) {
+                    if (!finite_f(res[2][r])) fm |= 1u << (8 * r);           // pressure mask only
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) if (!finite_f(res[c][r])) res[c][r] = 0.f;
+                }
+            }
+            if (!no_norm) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float x = res[c][r];
+                        float y = CHECKED ? __fdiv_rn(__fsub_rn(x, sc.mean[c]), sc.stdv[c])
+                                          : norm_fast(x, sc.mean[c], sc.stdv[c], sc.rcp[c]);
+                        if (mask_aware && ((fm >> (8 * r)) & 1u)) y = x;   // airfoil_ds.py:241-242
+                        res[c][r] = y;
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                fl_stg_stream4((float4*)(dst + (size_t)c * ppx), make_float4(res[c][0], res[c][1], res[c][2], res[c][3]));
+            dst += frame_out;
+            if (mdst) { *(unsigned*)mdst = fm; mdst += (size_t)n_patches * ppx; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 1)
+k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int groups_per_traj, int TF, int n_patches,
+                         int ppx, int slot_vel, int slot_prs, StagedConst sc, unsigned flags) {
+    extern __shared__ __align__(128) unsigned char fl_smem[];
+    uint64_t* bar = (uint64_t*)fl_smem;
+    float* s_vel = (float*)(fl_smem + 128);
+    float* s_prs = s_vel + (size_t)TF * slot_vel;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned parity = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int j = item / groups_per_traj, g = item - j * groups_per_traj;
+        const FlTraj tr = trajs[j];
+        const int fbeg = g * TF;
+        if (fbeg >= tr.n_frames) continue;                     // uniform across the CTA
+        const int nf = min(TF, tr.n_frames - fbeg);
+        const unsigned vb = (unsigned)tr.vel_stride * 4u, pb = (unsigned)tr.prs_stride * 4u;
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, (unsigned)nf * (vb + pb));
+            for (int f = 0; f < nf; ++f) {
+                const size_t t = (size_t)tr.t0 + (size_t)(fbeg + f) * tr.interval;
+                bulk_g2s(s_vel + (size_t)f * slot_vel, tr.d_velocity + t * tr.vel_stride, vb, bar);
+                bulk_g2s(s_prs + (size_t)f * slot_prs, tr.d_pressure + t * tr.prs_stride, pb, bar);
+            }
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        // staging scan: any non-finite or huge node value sends the whole item down the checked path
+        float nanacc = 0.f, amax = 0.f;
+        for (int f = 0; f < nf; ++f) {
+            const float4* v4 = (const float4*)(s_vel + (size_t)f * slot_vel);
+            for (int i = threadIdx.x; i < tr.vel_stride / 4; i += ST_THREADS) {
+                const float4 v = v4[i];
+                nanacc = fmaf(v.x, 0.f, fmaf(v.y, 0.f, fmaf(v.z, 0.f, fmaf(v.w, 0.f, nanacc))));
+                amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fmaxf(fabsf(v.z), fabsf(v.w)), amax));
+            }
+            const float4* p4 = (const float4*)(s_prs + (size_t)f * slot_prs);
+            for (int i = threadIdx.x; i < tr.prs_stride / 4; i += ST_THREADS) {
+                const float4 v = p4[i];
+                nanacc = fmaf(v.x, 0.f, fmaf(v.y, 0.f, fmaf(v.z, 0.f, fmaf(v.w, 0.f, nanacc))));
+                amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fmaxf(fabsf(v.z), fabsf(v.w)), amax));
+            }
+        }
+        const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || !sc.fast_div);
+        if (bad) staged_item<true>(tr, s_vel, s_prs, slot_vel, slot_prs, fbeg, nf, n_patches, ppx, sc, flags);
+        else staged_item<false>(tr, s_vel, s_prs, slot_vel, slot_prs, fbeg, nf, n_patches, ppx, sc, flags);
+        __syncthreads();   // every gather of this item is done before the next bulk copies land
+    }
+}
+
+// host: is (x - mean) / std safe for the reciprocal + Markstein path?
+bool fast_div_ok(const float* mean, const float* stdv) {
+    for (int c = 0; c < 3; ++c) {
+        float s = fabsf(stdv[c]), m = fabsf(mean[c]);
+        uint32_t bits;
+        memcpy(&bits, &s, 4);
+        if (!(s >= 9.5367431640625e-07f && s <= 1048576.f)) return false;        // 2^-20 .. 2^20
+        if ((bits & 0x007fffffu) == 0x007fffffu) return false;                     // Markstein's excluded significand
+        if (!(m >= 9.094947017729282e-13f && m <= 1.152921504606847e18f)) return false;  // 2^-40 .. 2^60, non-zero
+    }
+    return true;
+}
+
+int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int max_frames, int n_patches, int px, int py,
+                  const float* h_mean, const float* h_std, unsigned flags, cudaStream_t st) {
     NormConst nc;
     for (int c = 0; c < 3; ++c) { nc.mean[c] = h_mean ? h_mean[c] : 0.f; nc.stdv[c] = h_std ? h_std[c] : 1.f; }
     const int ppx = px * py;
+    // ---- staged path: needs the host copy of the descriptors to check strides / alignment ----
+    if (h_trajs && ppx % 4 == 0 && !(flags & FL_FORCE_GATHER)) {
+        bool ok = true;
+        int slot_vel = 0, slot_prs = 0;
+        for (int i = 0; i < n_traj && ok; ++i) {
+            const FlTraj& t = h_trajs[i];
+            ok = t.vel_stride % 4 == 0 && t.prs_stride % 4 == 0 && t.vel_stride >= 2 * t.n_nodes && t.prs_stride >= t.n_nodes &&
+                 ((uintptr_t)t.d_velocity % 16 == 0) && ((uintptr_t)t.d_pressure % 16 == 0) && ((uintptr_t)t.d_states % 16 == 0) &&
+                 (t.d_mask == nullptr || (uintptr_t)t.d_mask % 4 == 0);
+            slot_vel = t.vel_stride > slot_vel ? t.vel_stride : slot_vel;
+            slot_prs = t.prs_stride > slot_prs ? t.prs_stride : slot_prs;
+        }
+        const size_t frame_bytes = 4 * ((size_t)slot_vel + slot_prs);
+        const size_t budget = 227 * 1024 - 128;
+        int TF = ok && frame_bytes ? (int)(budget / frame_bytes) : 0;
+        if (TF > 16) TF = 16;
+        if (TF > max_frames) TF = max_frames;
+        if (TF >= 2 && (size_t)TF * frame_bytes < (1u << 20)) {       // mbarrier tx-count limit
+            StagedConst sc;
+            for (int c = 0; c < 3; ++c) { sc.mean[c] = nc.mean[c]; sc.stdv[c] = nc.stdv[c]; sc.rcp[c] = 1.0f / nc.stdv[c]; }
+            sc.fast_div = (flags & FL_NO_NORM) ? 1 : (fast_div_ok(nc.mean, nc.stdv) ? 1 : 0);
+            const int gpt = (max_frames + TF - 1) / TF;
+            const long n_items = (long)gpt * n_traj;
+            const size_t smem = 128 + (size_t)TF * frame_bytes;
+            static bool attr_set = false;
+            if (!attr_set) {
+                FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                attr_set = true;
+            }
+            int grid = n_items < FL_SM_COUNT ? (int)n_items : FL_SM_COUNT;
+            k_interp_patchify_staged<<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, slot_vel,
+                                                                    slot_prs, sc, flags);
+            FL_LAUNCH_CHECK();
+            return FL_OK;
+        }
+    }
+    // ---- gather path ----
     // enough CTAs to fill 148 SMs x 8 resident CTAs a few times over, but keep the per-thread
     // record reuse: at least 4 frames per CTA when there is that much work
     long ctas_per_frame = (long)n_patches * n_traj;
@@ -111,35 +331,51 @@ int launch_interp(const FlTraj* d_trajs, int n_traj, int max_frames, int n_patch
 
 }  // namespace
 
-extern "C" int fl_interp_patchify_dev(const FlTraj* d_trajs, int n_traj, int max_frames, int n_patches, int px, int py,
+static int check_trajs(const char* who, const FlTraj* h_trajs, int n_traj, int* max_frames) {
+    FL_REQUIRE(h_trajs, FL_E_ARG, "%s: null descriptor array", who);
+    FL_REQUIRE(n_traj > 0 && n_traj <= 65535, FL_E_ARG, "%s: n_traj=%d out of range", who, n_traj);
+    int mf = 0;
+    for (int i = 0; i < n_traj; ++i) {
+        const FlTraj& t = h_trajs[i];
+        FL_REQUIRE(t.d_velocity && t.d_pressure && t.d_idx && t.d_w && t.d_states, FL_E_ARG,
+                   "%s: trajectory %d has a null pointer", who, i);
+        FL_REQUIRE(t.n_nodes > 0 && t.n_frames > 0 && t.t0 >= 0 && t.interval > 0, FL_E_ARG,
+                   "%s: trajectory %d has bad sizes", who, i);
+        FL_REQUIRE(t.vel_stride >= 2 * t.n_nodes && t.prs_stride >= t.n_nodes, FL_E_ARG,
+                   "%s: trajectory %d: frame strides (%d, %d) smaller than the frame (%d nodes)", who, i, t.vel_stride,
+                   t.prs_stride, t.n_nodes);
+        FL_REQUIRE((uintptr_t)t.d_velocity % 8 == 0 && (uintptr_t)t.d_idx % 16 == 0 && (uintptr_t)t.d_w % 16 == 0 &&
+                       t.vel_stride % 2 == 0,
+                   FL_E_ALIGN, "%s: trajectory %d: velocity must be 8-byte aligned with an even stride, tables 16-byte aligned", who, i);
+        mf = t.n_frames > mf ? t.n_frames : mf;
+    }
+    *max_frames = mf;
+    return FL_OK;
+}
+
+extern "C" int fl_interp_patchify_dev(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int n_patches, int px, int py,
                                       const float* h_mean, const float* h_std, unsigned flags, void* stream) {
-    FL_REQUIRE(d_trajs, FL_E_ARG, "fl_interp_patchify_dev: null descriptor array");
-    FL_REQUIRE(n_traj > 0 && n_traj <= 65535 && max_frames > 0 && n_patches > 0, FL_E_ARG,
-               "fl_interp_patchify_dev: bad sizes (n_traj=%d max_frames=%d n_patches=%d)", n_traj, max_frames, n_patches);
+    FL_REQUIRE(d_trajs, FL_E_ARG, "fl_interp_patchify_dev: null device descriptor array");
+    int max_frames = 0;
+    int rc = check_trajs("fl_interp_patchify_dev", h_trajs, n_traj, &max_frames);
+    if (rc) return rc;
+    FL_REQUIRE(n_patches > 0, FL_E_ARG, "fl_interp_patchify_dev: n_patches=%d", n_patches);
     FL_REQUIRE(px > 0 && py > 0 && px * py <= 256 && (px * py) % 32 == 0, FL_E_ARG,
                "fl_interp_patchify_dev: patch of %dx%d pixels unsupported (need px*py <= 256, multiple of 32)", px, py);
     FL_REQUIRE((h_mean && h_std) || (flags & FL_NO_NORM), FL_E_ARG, "fl_interp_patchify_dev: mean/std missing");
-    return launch_interp(d_trajs, n_traj, max_frames, n_patches, px, py, h_mean, h_std, flags, (cudaStream_t)stream);
+    return launch_interp(d_trajs, h_trajs, n_traj, max_frames, n_patches, px, py, h_mean, h_std, flags, (cudaStream_t)stream);
 }
 
 extern "C" int fl_interp_patchify(const FlTraj* h_trajs, int n_traj, int n_patches, int px, int py, const float* h_mean,
                                   const float* h_std, unsigned flags, void* stream) {
-    FL_REQUIRE(h_trajs, FL_E_ARG, "fl_interp_patchify: null descriptor array");
-    FL_REQUIRE(n_traj > 0 && n_traj <= 65535, FL_E_ARG, "fl_interp_patchify: n_traj=%d out of range", n_traj);
     int max_frames = 0;
-    for (int i = 0; i < n_traj; ++i) {
-        const FlTraj& t = h_trajs[i];
-        FL_REQUIRE(t.d_velocity && t.d_pressure && t.d_idx && t.d_w && t.d_states, FL_E_ARG,
-                   "fl_interp_patchify: trajectory %d has a null pointer", i);
-        FL_REQUIRE(t.n_nodes > 0 && t.n_frames > 0 && t.t0 >= 0 && t.interval > 0, FL_E_ARG,
-                   "fl_interp_patchify: trajectory %d has bad sizes", i);
-        max_frames = t.n_frames > max_frames ? t.n_frames : max_frames;
-    }
+    int rc = check_trajs("fl_interp_patchify", h_trajs, n_traj, &max_frames);
+    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     FlTraj* d_trajs = nullptr;
     FL_CUDA(cudaMallocAsync((void**)&d_trajs, sizeof(FlTraj) * n_traj, st));
     FL_CUDA(cudaMemcpyAsync(d_trajs, h_trajs, sizeof(FlTraj) * n_traj, cudaMemcpyHostToDevice, st));
-    int rc = fl_interp_patchify_dev(d_trajs, n_traj, max_frames, n_patches, px, py, h_mean, h_std, flags, stream);
+    rc = fl_interp_patchify_dev(d_trajs, h_trajs, n_traj, n_patches, px, py, h_mean, h_std, flags, stream);
     cudaFreeAsync(d_trajs, st);
     return rc;
 }

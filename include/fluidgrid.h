@@ -32,12 +32,13 @@ extern "C" {
 #define FL_E_WORKSPACE (-3)/* workspace too small */
 #define FL_E_ALIGN (-4)    /* pointer not aligned as documented */
 
-#define FL_ABI_VERSION 1
+#define FL_ABI_VERSION 2
 
 /* personality flags of fl_plan_patch_table / fl_interp_patchify */
 #define FL_FLIP_Y 1u          /* airfoil_ds.py:80  -- y axis reversed after padding */
 #define FL_MASK_AWARE_NORM 2u /* airfoil_ds.py:236-242 -- masked pixels stay 0, others normalised */
 #define FL_NO_NORM 4u         /* normalize=False */
+#define FL_FORCE_GATHER 8u    /* testing: never pick the staged kernel */
 
 /* One grid cell of the static per-mesh table (the product's own intermediate; the reference
  * recomputes the plane coefficients of every triangle per channel per frame instead,
@@ -95,12 +96,18 @@ typedef struct FlTraj {
     float* d_states;           /* [n_frames, L, 3, px, py] */
     uint8_t* d_mask;           /* [n_frames, L, px, py] or NULL */
     int32_t n_nodes, t0, interval, n_frames;
+    int32_t vel_stride;        /* floats between consecutive frames of d_velocity (>= 2*n_nodes) */
+    int32_t prs_stride;        /* floats between consecutive frames of d_pressure (>= n_nodes)   */
 } FlTraj;
+/* Frame strides that are multiples of 4 floats on 16-byte aligned bases (pad floats readable and
+ * finite) select the staged kernel: whole frames are bulk-copied (TMA) into shared memory and
+ * gathered there.  Anything else runs the gather-from-global kernel -- same results, slower. */
 
 int fl_interp_patchify(const FlTraj* h_trajs, int n_traj, int n_patches, int px, int py,
                        const float* h_mean, const float* h_std, unsigned flags, void* stream);
-/* same, descriptors already on the device (no host->device copy of descriptors inside) */
-int fl_interp_patchify_dev(const FlTraj* d_trajs, int n_traj, int max_frames, int n_patches, int px, int py,
+/* same, with a copy of the descriptors already on the device (d_trajs; nothing is copied inside);
+ * h_trajs is the identical host copy, read for validation and kernel selection */
+int fl_interp_patchify_dev(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int n_patches, int px, int py,
                            const float* h_mean, const float* h_std, unsigned flags, void* stream);
 
 /* Plain-grid variant (no pad/patchify): replaces mesh_utils.to_grid (src/dataloader/mesh_utils.py:82-91)
