@@ -49,8 +49,15 @@ class DeviceTrajectory:
             p = p.unsqueeze(-1)
         if p.shape != (v.shape[0], plan.n_nodes, 1):
             raise ValueError(f"pressure must be ({v.shape[0]}, {plan.n_nodes}, 1), got {tuple(p.shape)}")
-        self.velocity = v.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-        self.pressure = p.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        # frame pitch padded to 16 bytes so whole frames can be bulk-copied (TMA) into shared memory
+        T, N = int(v.shape[0]), plan.n_nodes
+        self.vel_stride, self.prs_stride = (2 * N + 3) // 4 * 4, (N + 3) // 4 * 4
+        self.vel_buf = torch.zeros((T, self.vel_stride), dtype=torch.float32, device=dev)
+        self.prs_buf = torch.zeros((T, self.prs_stride), dtype=torch.float32, device=dev)
+        self.velocity = self.vel_buf[:, :2 * N].view(T, N, 2)     # reference-shaped views of the padded buffers
+        self.pressure = self.prs_buf[:, :N].view(T, N, 1)
+        self.velocity.copy_(v.to(dtype=torch.float32), non_blocking=True)
+        self.pressure.copy_(p.to(dtype=torch.float32), non_blocking=True)
         self.plan = plan
         self.n_steps = int(v.shape[0])
 
@@ -78,32 +85,34 @@ class TrajBatch:
         self.mask = torch.empty((self.n_traj, self.n_frames, L, px, py), dtype=torch.uint8, device=dev) if want_mask else None
         arr = (FlTraj * self.n_traj)()
         for i, (tr, tab, t0) in enumerate(zip(trajs, tables, t0s)):
-            arr[i] = FlTraj(tr.velocity.data_ptr(), tr.pressure.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(),
+            arr[i] = FlTraj(tr.vel_buf.data_ptr(), tr.prs_buf.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(),
                             self.states[i].data_ptr(), self.mask[i].data_ptr() if want_mask else 0,
-                            tr.plan.n_nodes, int(t0), int(interval), self.n_frames)
+                            tr.plan.n_nodes, int(t0), int(interval), self.n_frames, tr.vel_stride, tr.prs_stride)
+        self.host_desc = arr
         raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
         self.desc = torch.from_numpy(raw).to(dev)
         self._keep = (trajs, tables)   # keep the device buffers alive
 
-    def run(self, personality: Personality, normalize=True, means=None, stds=None):
+    def run(self, personality: Personality, normalize=True, means=None, stds=None, force_gather=False):
         """Enqueue the fused kernel on the current stream; returns (states, mask) device tensors."""
         flags = (FL_MASK_AWARE_NORM if personality.mask_aware_norm else 0) | (0 if normalize else FL_NO_NORM)
+        flags |= _lib.FL_FORCE_GATHER if force_gather else 0
         m = (ctypes.c_float * 3)(*(means if means is not None else personality.means))
         s = (ctypes.c_float * 3)(*(stds if stds is not None else personality.stds))
         tab = self.tab0
         with torch.cuda.device(self.device):
-            check(load().fl_interp_patchify_dev(ctypes.c_void_p(self.desc.data_ptr()), self.n_traj, self.n_frames,
+            check(load().fl_interp_patchify_dev(ctypes.c_void_p(self.desc.data_ptr()), self.host_desc, self.n_traj,
                                                 tab.n_patches, tab.px, tab.py, m, s, flags, stream_ptr()),
                   "fl_interp_patchify")
         return self.states, self.mask
 
 
 def interp_patchify(traj: DeviceTrajectory, step_num: int, seq_len: int, seq_interval: int, patch_size,
-                    personality: Personality, normalize=True, means=None, stds=None):
+                    personality: Personality, normalize=True, means=None, stds=None, force_gather=False):
     """One trajectory, frames step_num, step_num+interval, ... -> (states (T,L,3,px,py) f32,
     mask (T,L,px,py) u8, table)."""
     _lib.require_cuda()
     tab = traj.plan.patch_table(patch_size, personality.crop_patches, personality.flip_y)
     batch = TrajBatch([traj], [tab], [step_num], seq_interval, seq_len)
-    states, mask = batch.run(personality, normalize, means, stds)
+    states, mask = batch.run(personality, normalize, means, stds, force_gather)
     return states[0], mask[0], tab

@@ -114,7 +114,8 @@ def test_to_grid_nonfinite_values_are_masked():
 
 @pytest.mark.parametrize("kind", ["cylinder", "airfoil", "eagle"])
 @pytest.mark.parametrize("normalize", [True, False])
-def test_interp_patchify_matches_oracle(kind, normalize):
+@pytest.mark.parametrize("force_gather", [False, True], ids=["staged", "gather"])
+def test_interp_patchify_matches_oracle(kind, normalize, force_gather):
     """states / mask of the fused kernel == the oracle's unfold+normalise pipeline, bit for bit
     (north_star tolerance: 1e-6 relative; achieved: exact on these inputs)."""
     from fluid_llm_b200.field_path import AIRFOIL, CYLINDER, DeviceTrajectory, interp_patchify
@@ -126,7 +127,8 @@ def test_interp_patchify_matches_oracle(kind, normalize):
         nmask, _, _ = crop_airfoil_mesh(tr["mesh_pos"], tr["cells"])
         vel, prs = vel[:, nmask], prs[:, nmask]
     pers = AIRFOIL if kind == "airfoil" else CYLINDER
-    states, mask, tab = interp_patchify(DeviceTrajectory(vel, prs, plan), 1, 3, 2, PATCH, pers, normalize=normalize)
+    states, mask, tab = interp_patchify(DeviceTrajectory(vel, prs, plan), 1, 3, 2, PATCH, pers, normalize=normalize,
+                                        force_gather=force_gather)
     (_, _, _, _, _), extra = oracle_ds_get(kind, 1, 3, 2, normalize=normalize)
     assert (tab.n_bx, tab.n_by) == (extra["N_x_patch"], extra["N_y_patch"])
     assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
@@ -166,3 +168,40 @@ def test_custom_mean_std():
                                    means=means, stds=stds)
     _, extra = oracle_ds_get("eagle", 0, 2, 1, means=means, stds=stds)
     assert np.array_equal(states.cpu().numpy(), extra["states"])
+
+
+@pytest.mark.parametrize("kind", ["cylinder", "airfoil"])
+def test_nonfinite_node_values_take_the_checked_path(kind):
+    """NaN / inf node values: the staged kernel's scan sends the item down the checked path; mask and
+    zeroing follow mesh_utils.py:86-89 per channel, only the pressure mask is kept."""
+    from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
+    from fluid_llm_b200.field_path import AIRFOIL, CYLINDER, DeviceTrajectory, interp_patchify
+    import copy
+    tr = copy.deepcopy(trajectory(kind))
+    tr["pressure"][2, 50:60, 0] = np.nan
+    tr["velocity"][3, 70, 0] = np.inf
+    tr["velocity"][1, 80, 1] = -np.inf
+    plan, pos, faces = _plan(kind)
+    vel, prs = tr["velocity"], tr["pressure"]
+    if kind == "airfoil":
+        nmask, _, _ = crop_airfoil_mesh(tr["mesh_pos"], tr["cells"])
+        vel, prs = vel[:, nmask], prs[:, nmask]
+    pers = AIRFOIL if kind == "airfoil" else CYLINDER
+    with np.errstate(all="ignore"):
+        _, extra = P.ds_get(tr, 0, 5, 1, 238, PATCH, personality_of(kind), return_all=True)
+    for fg in (False, True):
+        states, mask, _ = interp_patchify(DeviceTrajectory(vel, prs, plan), 0, 5, 1, PATCH, pers, force_gather=fg)
+        assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
+        assert np.array_equal(states.cpu().numpy(), extra["states"])
+
+
+def test_long_sequence_many_items():
+    """More frames than one staged work item holds, odd node count (padded frame pitch), interval 3."""
+    from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    tr = trajectory("cylinder", 64, 3, 7)
+    plan = MeshPlan(tr["mesh_pos"], tr["cells"], 238)
+    states, mask, _ = interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 2, 20, 3, PATCH, CYLINDER)
+    _, extra = oracle_ds_get("cylinder", 2, 20, 3, T=64, mesh_seed=3, field_seed=7)
+    assert np.array_equal(states.cpu().numpy(), extra["states"])
+    assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
