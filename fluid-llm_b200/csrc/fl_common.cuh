@@ -50,6 +50,9 @@ __device__ __forceinline__ void fl_stg_stream4(float4* p, float4 v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ void fl_stg_stream2(float2* p, float2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
 __device__ __forceinline__ void fl_stg_stream1(float* p, float v) {
     asm volatile("st.global.L1::no_allocate.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
 }

@@ -11,6 +11,7 @@
 // IEEE division, i.e. the same two roundings as simple_dataloader.py:213-214.
 #include "fl_common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 
 namespace {
@@ -108,7 +109,6 @@ __global__ void k_to_grid(const FlCellIdx* __restrict__ idx, const FlCellW* __re
 // a reciprocal multiply with one Markstein correction step (bit-identical to IEEE division for
 // the ranges checked on the host and in the staging scan; anything else takes the checked path).
 // ------------------------------------------------------------------------------------------
-constexpr int ST_THREADS = 512;
 
 struct StagedConst {
     float mean[3], stdv[3], rcp[3];
@@ -137,6 +137,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         "FL_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 r;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
+    return r;
+}
 
 // (x - mean) / std, correctly rounded: q = d*r, then one Markstein step with the exact remainder
 __device__ __forceinline__ float norm_fast(float x, float mean, float stdv, float rcp) {
@@ -146,43 +156,87 @@ __device__ __forceinline__ float norm_fast(float x, float mean, float stdv, floa
     return __fmaf_rn(e, rcp, q);
 }
 
-template <bool CHECKED>
-__device__ __forceinline__ void staged_item(const FlTraj& tr, const float* __restrict__ s_vel, const float* __restrict__ s_prs,
-                                            int slot_vel, int slot_prs, int fbeg, int nf, int n_patches, int ppx,
-                                            const StagedConst& sc, unsigned flags) {
+// float -> double on the integer/FMA pipes instead of the 16-lane conversion unit (XU): exact for
+// +-0 and normal numbers (the staging scan sends items holding subnormals, inf or NaN down the
+// checked path).  {t>>3, t<<29} is one 32x32->64 multiply by 2^29; then exponent re-bias and sign.
+__device__ __forceinline__ double f2d_int(float f) {
+    const unsigned x = __float_as_uint(f);
+    const unsigned t = x & 0x7fffffffu;
+    const unsigned long long p = (unsigned long long)t * 0x20000000ull;
+    unsigned hi = (unsigned)(p >> 32);
+    hi += t ? 0x38000000u : 0u;
+    hi |= x & 0x80000000u;
+    return __hiloint2double((int)hi, (int)(unsigned)p);
+}
+template <bool INT> __device__ __forceinline__ double f2d(float f) { return INT ? f2d_int(f) : (double)f; }
+
+// two pixels at once on the packed fp32 pipe (FADD2 / FMUL2 / FFMA2): same roundings as norm_fast
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    return ((unsigned long long)__float_as_uint(b) << 32) | __float_as_uint(a);
+}
+__device__ __forceinline__ void norm_fast2(float& x0, float& x1, float neg_mean, float neg_std, float rcp) {
+    const unsigned long long x = pack2(x0, x1), nm = pack2(neg_mean, neg_mean), ns = pack2(neg_std, neg_std), rc = pack2(rcp, rcp);
+    unsigned long long d, q, e, y;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(nm));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(d), "l"(rc));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(e) : "l"(q), "l"(ns), "l"(d));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(y) : "l"(e), "l"(rc), "l"(q));
+    x0 = __uint_as_float((unsigned)y);
+    x1 = __uint_as_float((unsigned)(y >> 32));
+}
+
+// ICONV: how many of the nine float->double conversions per pixel go through f2d_int:
+// 0 none, 1 pressure (3), 2 pressure + v (6), 3 all (9).   NP: consecutive output pixels per thread (2 or 4).
+template <bool CHECKED, int ICONV, int NP>
+__device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned char* __restrict__ s_vel,
+                                            const unsigned char* __restrict__ s_prs, int slot_vel_b, int slot_prs_b,
+                                            int fbeg, int nf, int n_patches, int ppx, int ppx_shift, const StagedConst& sc,
+                                            unsigned flags) {
     const bool mask_aware = flags & FL_MASK_AWARE_NORM, no_norm = flags & FL_NO_NORM;
-    const int nquads = n_patches * ppx / 4;
+    constexpr bool IP = !CHECKED && ICONV >= 1, IV = !CHECKED && ICONV >= 2, IU = !CHECKED && ICONV >= 3;
+    // A warp owns a chunk of 32*NP consecutive output pixels; lane i handles pixels i, i+32, ... of it,
+    // so every gather instruction covers 32 ADJACENT pixels (two 16-pixel rows of a patch): many lanes
+    // hit the same node (one broadcast wavefront) instead of 32 scattered ones.
+    const int nchunks = n_patches * ppx / (32 * NP);
+    const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
     const size_t frame_out = (size_t)n_patches * 3 * ppx;
-    for (int q = threadIdx.x; q < nquads; q += ST_THREADS) {
-        int4 id[4];
-        double w0[4], w1[4], w2[4];
-        unsigned mbits = 0;
+    for (int ch = threadIdx.x >> 5; ch < nchunks; ch += warps) {
+        const int o = ch * 32 * NP + lane;          // first pixel of this lane; the others are +32*r
+        uint32_t ov[NP][3];     // byte offset of each vertex inside a velocity frame (8 * node id); pressure: half of it
+        double w0[NP], w1[NP], w2[NP];
+        unsigned mbits = 0;     // byte r = 1 if pixel r is outside the mesh
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            id[r] = __ldg((const int4*)tr.d_idx + 4 * q + r);
-            const double2 ww = __ldg((const double2*)tr.d_w + 4 * q + r);
-            const bool out = id[r].w < 0;
+        for (int r = 0; r < NP; ++r) {
+            const int4 id = __ldg((const int4*)tr.d_idx + o + 32 * r);
+            const double2 ww = __ldg((const double2*)tr.d_w + o + 32 * r);
+            const bool out = id.w < 0;
             mbits |= out ? (1u << (8 * r)) : 0u;
             w1[r] = out ? 0.0 : ww.x;
             w2[r] = out ? 0.0 : ww.y;
             w0[r] = out ? 0.0 : 1.0 - ww.x - ww.y;
-            if (out) id[r].x = id[r].y = id[r].z = 0;
+            ov[r][0] = out ? 0u : (uint32_t)id.x * 8u;
+            ov[r][1] = out ? 0u : (uint32_t)id.y * 8u;
+            ov[r][2] = out ? 0u : (uint32_t)id.z * 8u;
         }
-        const int o = 4 * q, l = o / ppx, k = o - l * ppx;
+        const int l = ppx_shift >= 0 ? (o >> ppx_shift) : o / ppx, k = o - l * ppx;   // the chunk never straddles a patch
         float* dst = tr.d_states + ((size_t)fbeg * n_patches + l) * 3 * ppx + k;
         uint8_t* mdst = tr.d_mask ? tr.d_mask + ((size_t)fbeg * n_patches + l) * ppx + k : nullptr;
         for (int f = 0; f < nf; ++f) {
-            const float2* V = (const float2*)(s_vel + (size_t)f * slot_vel);
-            const float* Pr = s_prs + (size_t)f * slot_prs;
-            float res[3][4];
+            const unsigned char* vb = s_vel + (size_t)f * slot_vel_b;     // uniform: folds into LDS [R + UR]
+            const unsigned char* pb = s_prs + (size_t)f * slot_prs_b;
+            float res[3][NP];
             unsigned fm = mbits;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float2 a0 = V[id[r].x], a1 = V[id[r].y], a2 = V[id[r].z];
-                const float p0 = Pr[id[r].x], p1 = Pr[id[r].y], p2 = Pr[id[r].z];
-                res[0][r] = (float)fma(w2[r], (double)a2.x, fma(w1[r], (double)a1.x, w0[r] * (double)a0.x));
-                res[1][r] = (float)fma(w2[r], (double)a2.y, fma(w1[r], (double)a1.y, w0[r] * (double)a0.y));
-                res[2][r] = (float)fma(w2[r], (double)p2, fma(w1[r], (double)p1, w0[r] * (double)p0));
+            for (int r = 0; r < NP; ++r) {
+                const float2 a0 = *reinterpret_cast<const float2*>(vb + ov[r][0]);
+                const float2 a1 = *reinterpret_cast<const float2*>(vb + ov[r][1]);
+                const float2 a2 = *reinterpret_cast<const float2*>(vb + ov[r][2]);
+                const float p0 = *reinterpret_cast<const float*>(pb + (ov[r][0] >> 1));
+                const float p1 = *reinterpret_cast<const float*>(pb + (ov[r][1] >> 1));
+                const float p2 = *reinterpret_cast<const float*>(pb + (ov[r][2] >> 1));
+                res[0][r] = (float)fma(w2[r], f2d<IU>(a2.x), fma(w1[r], f2d<IU>(a1.x), w0[r] * f2d<IU>(a0.x)));
+                res[1][r] = (float)fma(w2[r], f2d<IV>(a2.y), fma(w1[r], f2d<IV>(a1.y), w0[r] * f2d<IV>(a0.y)));
+                res[2][r] = (float)fma(w2[r], f2d<IP>(p2), fma(w1[r], f2d<IP>(p1), w0[r] * f2d<IP>(p0)));
                 if (CHECKED) {
                     if (!finite_f(res[2][r])) fm |= 1u << (8 * r);           // pressure mask only
 #pragma unroll
@@ -190,29 +244,46 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const float* __res
                 }
             }
             if (!no_norm) {
+                if (CHECKED) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
+                    for (int c = 0; c < 3; ++c)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const float x = res[c][r];
-                        float y = CHECKED ? __fdiv_rn(__fsub_rn(x, sc.mean[c]), sc.stdv[c])
-                                          : norm_fast(x, sc.mean[c], sc.stdv[c], sc.rcp[c]);
-                        if (mask_aware && ((fm >> (8 * r)) & 1u)) y = x;   // airfoil_ds.py:241-242
-                        res[c][r] = y;
-                    }
+                        for (int r = 0; r < NP; ++r) {
+                            const float x = res[c][r];
+                            const float y = __fdiv_rn(__fsub_rn(x, sc.mean[c]), sc.stdv[c]);
+                            res[c][r] = (mask_aware && ((fm >> (8 * r)) & 1u)) ? x : y;   // airfoil_ds.py:241-242
+                        }
+                } else if (mask_aware && fm) {      // rare: pixels on the mesh boundary / padding stay raw
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int r = 0; r < NP; ++r)
+                            if (!((fm >> (8 * r)) & 1u)) res[c][r] = norm_fast(res[c][r], sc.mean[c], sc.stdv[c], sc.rcp[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int r = 0; r < NP; r += 2) norm_fast2(res[c][r], res[c][r + 1], -sc.mean[c], -sc.stdv[c], sc.rcp[c]);
+                }
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c)
-                fl_stg_stream4((float4*)(dst + (size_t)c * ppx), make_float4(res[c][0], res[c][1], res[c][2], res[c][3]));
+#pragma unroll
+                for (int r = 0; r < NP; ++r) fl_stg_stream1(dst + (size_t)c * ppx + 32 * r, res[c][r]);   // 128 B per warp store
             dst += frame_out;
-            if (mdst) { *(unsigned*)mdst = fm; mdst += (size_t)n_patches * ppx; }
+            if (mdst) {
+#pragma unroll
+                for (int r = 0; r < NP; ++r) mdst[32 * r] = (uint8_t)((fm >> (8 * r)) & 1u);
+                mdst += (size_t)n_patches * ppx;
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(ST_THREADS, 1)
+template <int ICONV, int NP>
+__global__ void __launch_bounds__(NP == 4 ? 512 : 1024, 1)
 k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int groups_per_traj, int TF, int n_patches,
-                         int ppx, int slot_vel, int slot_prs, StagedConst sc, unsigned flags) {
+                         int ppx, int ppx_shift, int slot_vel, int slot_prs, StagedConst sc, unsigned flags) {
     extern __shared__ __align__(128) unsigned char fl_smem[];
     uint64_t* bar = (uint64_t*)fl_smem;
     float* s_vel = (float*)(fl_smem + 128);
@@ -240,25 +311,30 @@ k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int grou
         }
         mbar_wait(bar, parity);
         parity ^= 1u;
-        // staging scan: any non-finite or huge node value sends the whole item down the checked path
+        // staging scan: a non-finite, huge or subnormal node value sends the whole item down the checked path
         float nanacc = 0.f, amax = 0.f;
+        bool sub = false;
+        auto scan4 = [&](const float4 v) {
+            nanacc = fmaf(v.x, 0.f, fmaf(v.y, 0.f, fmaf(v.z, 0.f, fmaf(v.w, 0.f, nanacc))));
+            amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fmaxf(fabsf(v.z), fabsf(v.w)), amax));
+            if (ICONV) {   // subnormal <=> 0 < |bits| < 0x00800000  <=>  (|bits| - 1) < 0x007fffff (unsigned)
+                sub |= ((__float_as_uint(v.x) & 0x7fffffffu) - 1u) < 0x007fffffu;
+                sub |= ((__float_as_uint(v.y) & 0x7fffffffu) - 1u) < 0x007fffffu;
+                sub |= ((__float_as_uint(v.z) & 0x7fffffffu) - 1u) < 0x007fffffu;
+                sub |= ((__float_as_uint(v.w) & 0x7fffffffu) - 1u) < 0x007fffffu;
+            }
+        };
         for (int f = 0; f < nf; ++f) {
             const float4* v4 = (const float4*)(s_vel + (size_t)f * slot_vel);
-            for (int i = threadIdx.x; i < tr.vel_stride / 4; i += ST_THREADS) {
-                const float4 v = v4[i];
-                nanacc = fmaf(v.x, 0.f, fmaf(v.y, 0.f, fmaf(v.z, 0.f, fmaf(v.w, 0.f, nanacc))));
-                amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fmaxf(fabsf(v.z), fabsf(v.w)), amax));
-            }
+            for (int i = threadIdx.x; i < tr.vel_stride / 4; i += blockDim.x) scan4(v4[i]);
             const float4* p4 = (const float4*)(s_prs + (size_t)f * slot_prs);
-            for (int i = threadIdx.x; i < tr.prs_stride / 4; i += ST_THREADS) {
-                const float4 v = p4[i];
-                nanacc = fmaf(v.x, 0.f, fmaf(v.y, 0.f, fmaf(v.z, 0.f, fmaf(v.w, 0.f, nanacc))));
-                amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fmaxf(fabsf(v.z), fabsf(v.w)), amax));
-            }
+            for (int i = threadIdx.x; i < tr.prs_stride / 4; i += blockDim.x) scan4(p4[i]);
         }
-        const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || !sc.fast_div);
-        if (bad) staged_item<true>(tr, s_vel, s_prs, slot_vel, slot_prs, fbeg, nf, n_patches, ppx, sc, flags);
-        else staged_item<false>(tr, s_vel, s_prs, slot_vel, slot_prs, fbeg, nf, n_patches, ppx, sc, flags);
+        const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || sub || !sc.fast_div);
+        const unsigned char* svb = (const unsigned char*)s_vel;
+        const unsigned char* spb = (const unsigned char*)s_prs;
+        if (bad) staged_item<true, 0, NP>(tr, svb, spb, slot_vel * 4, slot_prs * 4, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+        else staged_item<false, ICONV, NP>(tr, svb, spb, slot_vel * 4, slot_prs * 4, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
         __syncthreads();   // every gather of this item is done before the next bulk copies land
     }
 }
@@ -282,7 +358,7 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
     for (int c = 0; c < 3; ++c) { nc.mean[c] = h_mean ? h_mean[c] : 0.f; nc.stdv[c] = h_std ? h_std[c] : 1.f; }
     const int ppx = px * py;
     // ---- staged path: needs the host copy of the descriptors to check strides / alignment ----
-    if (h_trajs && ppx % 4 == 0 && !(flags & FL_FORCE_GATHER)) {
+    if (h_trajs && ppx % 128 == 0 && !(flags & FL_FORCE_GATHER)) {
         bool ok = true;
         int slot_vel = 0, slot_prs = 0;
         for (int i = 0; i < n_traj && ok; ++i) {
@@ -294,25 +370,41 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             slot_prs = t.prs_stride > slot_prs ? t.prs_stride : slot_prs;
         }
         const size_t frame_bytes = 4 * ((size_t)slot_vel + slot_prs);
-        const size_t budget = 227 * 1024 - 128;
+        typedef void (*StagedKernel)(const FlTraj*, int, int, int, int, int, int, int, int, StagedConst, unsigned);
+        static const StagedKernel kernels[2][4] = {
+            {k_interp_patchify_staged<0, 2>, k_interp_patchify_staged<1, 2>, k_interp_patchify_staged<2, 2>, k_interp_patchify_staged<3, 2>},
+            {k_interp_patchify_staged<0, 4>, k_interp_patchify_staged<1, 4>, k_interp_patchify_staged<2, 4>, k_interp_patchify_staged<3, 4>}};
+        static int iconv = -1, ctas_per_sm = 1, np = 2;
+        if (iconv < 0) {   // tuning knobs (development): FLUIDGRID_ICONV=0..3, FLUIDGRID_CTAS=1|2, FLUIDGRID_NP=2|4
+            const char* e = getenv("FLUIDGRID_ICONV");
+            iconv = e ? atoi(e) : 1;
+            if (iconv < 0 || iconv > 3) iconv = 1;
+            e = getenv("FLUIDGRID_CTAS");
+            ctas_per_sm = (e && atoi(e) == 2) ? 2 : 1;
+            e = getenv("FLUIDGRID_NP");
+            np = (e && atoi(e) == 4) ? 4 : 2;
+            for (int a = 0; a < 2; ++a)
+                for (int b = 0; b < 4; ++b)
+                    FL_CUDA(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        }
+        const size_t budget = (227 * 1024) / ctas_per_sm - 1024 - 128;   // per CTA; 1 KB/CTA is reserved by the driver
         int TF = ok && frame_bytes ? (int)(budget / frame_bytes) : 0;
         if (TF > 16) TF = 16;
         if (TF > max_frames) TF = max_frames;
-        if (TF >= 2 && (size_t)TF * frame_bytes < (1u << 20)) {       // mbarrier tx-count limit
+        if (TF >= 1 && (size_t)TF * frame_bytes < (1u << 20)) {       // mbarrier tx-count limit
             StagedConst sc;
             for (int c = 0; c < 3; ++c) { sc.mean[c] = nc.mean[c]; sc.stdv[c] = nc.stdv[c]; sc.rcp[c] = 1.0f / nc.stdv[c]; }
             sc.fast_div = (flags & FL_NO_NORM) ? 1 : (fast_div_ok(nc.mean, nc.stdv) ? 1 : 0);
             const int gpt = (max_frames + TF - 1) / TF;
             const long n_items = (long)gpt * n_traj;
             const size_t smem = 128 + (size_t)TF * frame_bytes;
-            static bool attr_set = false;
-            if (!attr_set) {
-                FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                attr_set = true;
-            }
-            int grid = n_items < FL_SM_COUNT ? (int)n_items : FL_SM_COUNT;
-            k_interp_patchify_staged<<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, slot_vel,
-                                                                    slot_prs, sc, flags);
+            int ppx_shift = -1;
+            for (int b = 0; b < 16; ++b) if ((1 << b) == ppx) ppx_shift = b;
+            const long max_grid = (long)FL_SM_COUNT * ctas_per_sm;
+            int grid = n_items < max_grid ? (int)n_items : (int)max_grid;
+            const int threads = (np == 4 ? 512 : 1024) / ctas_per_sm;
+            kernels[np == 4][iconv]<<<grid, threads, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift,
+                                                                 slot_vel, slot_prs, sc, flags);
             FL_LAUNCH_CHECK();
             return FL_OK;
         }
