@@ -98,17 +98,25 @@ __global__ void k_to_grid(const FlCellIdx* __restrict__ idx, const FlCellW* __re
 
 
 // ------------------------------------------------------------------------------------------
-// Staged kernel (the fast path).  One persistent CTA per SM; a work item is TF consecutive
-// selected frames of one trajectory.  The frames' node arrays are bulk-copied (TMA,
-// cp.async.bulk + mbarrier) into shared memory in their global layout, every thread then walks
-// quads of 4 consecutive output pixels: the 4 table records are read once (coalesced 128-bit
-// loads, L2-resident) and reused for all TF frames, node values are gathered from shared memory,
-// results leave as 128-bit streaming stores (each warp store covers 512 contiguous bytes).
-//   HBM traffic: 12 N + 12 P bytes per frame (compulsory) ; L2 -> SM: + 32 P / TF (table).
-// Arithmetic per pixel-frame: 9 f32->f64, 3 DMUL + 6 DFMA, 3 f64->f32, then (v - mean) / std as
-// a reciprocal multiply with one Markstein correction step (bit-identical to IEEE division for
-// the ranges checked on the host and in the staging scan; anything else takes the checked path).
+// Staged kernel (the fast path).  One persistent 512-thread CTA per SM; a work item is TF
+// consecutive selected frames of one trajectory.
+//   staging   velocity frames are bulk-copied (TMA: cp.async.bulk + mbarrier) into shared memory in
+//             their global layout [node][u,v]; pressure frames are read with coalesced 128-bit loads
+//             and stored as fp64 (one conversion per NODE instead of three per PIXEL), so both
+//             arrays have an 8-byte node stride and one offset register addresses both.
+//   compute   a warp owns 128 consecutive output pixels, lane i handles pixels i, i+32, i+64, i+96,
+//             so each gather instruction covers 32 adjacent pixels.  The four table records of a
+//             thread are read once (coalesced, L2-resident) and reused for all TF frames.
+//   output    128 B per warp store (streaming, no L1 allocate); (frame, patch, channel) blocks of
+//             1 KB are written whole by two warps.
+// HBM traffic: 12 N + 12 P bytes per frame (compulsory); L2 -> SM adds 32 P / TF (table).
+// Arithmetic per pixel-frame: 6 f32->f64 (u, v), 3 DMUL + 6 DFMA, 3 f64->f32, then (v - mean) / std as
+// a reciprocal multiply with one Markstein correction step on the packed fp32 pipe (bit-identical to
+// IEEE division for the ranges checked on the host and in the staging scan; anything else takes the
+// checked path).  The conversion unit (16 lanes/clk/SM) is the binding pipe: see DESIGN.md.
 // ------------------------------------------------------------------------------------------
+constexpr int ST_THREADS = 512;
+constexpr int NP = 4;        // pixels per thread
 
 struct StagedConst {
     float mean[3], stdv[3], rcp[3];
@@ -137,16 +145,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         "FL_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
-    float2 r;
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(addr));
-    return r;
-}
-__device__ __forceinline__ float lds_f1(uint32_t addr) {
-    float r;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr));
-    return r;
-}
 
 // (x - mean) / std, correctly rounded: q = d*r, then one Markstein step with the exact remainder
 __device__ __forceinline__ float norm_fast(float x, float mean, float stdv, float rcp) {
@@ -155,27 +153,12 @@ __device__ __forceinline__ float norm_fast(float x, float mean, float stdv, floa
     float e = __fmaf_rn(-q, stdv, d);
     return __fmaf_rn(e, rcp, q);
 }
-
-// float -> double on the integer/FMA pipes instead of the 16-lane conversion unit (XU): exact for
-// +-0 and normal numbers (the staging scan sends items holding subnormals, inf or NaN down the
-// checked path).  {t>>3, t<<29} is one 32x32->64 multiply by 2^29; then exponent re-bias and sign.
-__device__ __forceinline__ double f2d_int(float f) {
-    const unsigned x = __float_as_uint(f);
-    const unsigned t = x & 0x7fffffffu;
-    const unsigned long long p = (unsigned long long)t * 0x20000000ull;
-    unsigned hi = (unsigned)(p >> 32);
-    hi += t ? 0x38000000u : 0u;
-    hi |= x & 0x80000000u;
-    return __hiloint2double((int)hi, (int)(unsigned)p);
-}
-template <bool INT> __device__ __forceinline__ double f2d(float f) { return INT ? f2d_int(f) : (double)f; }
-
 // two pixels at once on the packed fp32 pipe (FADD2 / FMUL2 / FFMA2): same roundings as norm_fast
 __device__ __forceinline__ unsigned long long pack2(float a, float b) {
     return ((unsigned long long)__float_as_uint(b) << 32) | __float_as_uint(a);
 }
-__device__ __forceinline__ void norm_fast2(float& x0, float& x1, float neg_mean, float neg_std, float rcp) {
-    const unsigned long long x = pack2(x0, x1), nm = pack2(neg_mean, neg_mean), ns = pack2(neg_std, neg_std), rc = pack2(rcp, rcp);
+__device__ __forceinline__ void norm_fast2(float& x0, float& x1, unsigned long long nm, unsigned long long ns, unsigned long long rc) {
+    const unsigned long long x = pack2(x0, x1);
     unsigned long long d, q, e, y;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(nm));
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(d), "l"(rc));
@@ -185,24 +168,20 @@ __device__ __forceinline__ void norm_fast2(float& x0, float& x1, float neg_mean,
     x1 = __uint_as_float((unsigned)(y >> 32));
 }
 
-// ICONV: how many of the nine float->double conversions per pixel go through f2d_int:
-// 0 none, 1 pressure (3), 2 pressure + v (6), 3 all (9).   NP: consecutive output pixels per thread (2 or 4).
-template <bool CHECKED, int ICONV, int NP>
-__device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned char* __restrict__ s_vel,
-                                            const unsigned char* __restrict__ s_prs, int slot_vel_b, int slot_prs_b,
+template <bool CHECKED>
+__device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned char* __restrict__ s_nodes, int slot_b,
                                             int fbeg, int nf, int n_patches, int ppx, int ppx_shift, const StagedConst& sc,
                                             unsigned flags) {
     const bool mask_aware = flags & FL_MASK_AWARE_NORM, no_norm = flags & FL_NO_NORM;
-    constexpr bool IP = !CHECKED && ICONV >= 1, IV = !CHECKED && ICONV >= 2, IU = !CHECKED && ICONV >= 3;
-    // A warp owns a chunk of 32*NP consecutive output pixels; lane i handles pixels i, i+32, ... of it,
-    // so every gather instruction covers 32 ADJACENT pixels (two 16-pixel rows of a patch): many lanes
-    // hit the same node (one broadcast wavefront) instead of 32 scattered ones.
     const int nchunks = n_patches * ppx / (32 * NP);
     const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
     const size_t frame_out = (size_t)n_patches * 3 * ppx;
+    unsigned long long nm[3], ns[3], rc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { nm[c] = pack2(-sc.mean[c], -sc.mean[c]); ns[c] = pack2(-sc.stdv[c], -sc.stdv[c]); rc[c] = pack2(sc.rcp[c], sc.rcp[c]); }
     for (int ch = threadIdx.x >> 5; ch < nchunks; ch += warps) {
         const int o = ch * 32 * NP + lane;          // first pixel of this lane; the others are +32*r
-        uint32_t ov[NP][3];     // byte offset of each vertex inside a velocity frame (8 * node id); pressure: half of it
+        uint32_t ov[NP][3];     // byte offset of each vertex's 16-byte node record {u f32, v f32, p f64} in a frame slot
         double w0[NP], w1[NP], w2[NP];
         unsigned mbits = 0;     // byte r = 1 if pixel r is outside the mesh
 #pragma unroll
@@ -214,29 +193,29 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
             w1[r] = out ? 0.0 : ww.x;
             w2[r] = out ? 0.0 : ww.y;
             w0[r] = out ? 0.0 : 1.0 - ww.x - ww.y;
-            ov[r][0] = out ? 0u : (uint32_t)id.x * 8u;
-            ov[r][1] = out ? 0u : (uint32_t)id.y * 8u;
-            ov[r][2] = out ? 0u : (uint32_t)id.z * 8u;
+            ov[r][0] = out ? 0u : (uint32_t)id.x * 16u;
+            ov[r][1] = out ? 0u : (uint32_t)id.y * 16u;
+            ov[r][2] = out ? 0u : (uint32_t)id.z * 16u;
         }
         const int l = ppx_shift >= 0 ? (o >> ppx_shift) : o / ppx, k = o - l * ppx;   // the chunk never straddles a patch
         float* dst = tr.d_states + ((size_t)fbeg * n_patches + l) * 3 * ppx + k;
         uint8_t* mdst = tr.d_mask ? tr.d_mask + ((size_t)fbeg * n_patches + l) * ppx + k : nullptr;
-        for (int f = 0; f < nf; ++f) {
-            const unsigned char* vb = s_vel + (size_t)f * slot_vel_b;     // uniform: folds into LDS [R + UR]
-            const unsigned char* pb = s_prs + (size_t)f * slot_prs_b;
+        const unsigned char* nb = s_nodes;    // loop-carried uniform base: folds into LDS.128 [R + UR]
+#pragma unroll 1
+        for (int f = 0; f < nf; ++f, nb += slot_b) {
             float res[3][NP];
             unsigned fm = mbits;
 #pragma unroll
             for (int r = 0; r < NP; ++r) {
-                const float2 a0 = *reinterpret_cast<const float2*>(vb + ov[r][0]);
-                const float2 a1 = *reinterpret_cast<const float2*>(vb + ov[r][1]);
-                const float2 a2 = *reinterpret_cast<const float2*>(vb + ov[r][2]);
-                const float p0 = *reinterpret_cast<const float*>(pb + (ov[r][0] >> 1));
-                const float p1 = *reinterpret_cast<const float*>(pb + (ov[r][1] >> 1));
-                const float p2 = *reinterpret_cast<const float*>(pb + (ov[r][2] >> 1));
-                res[0][r] = (float)fma(w2[r], f2d<IU>(a2.x), fma(w1[r], f2d<IU>(a1.x), w0[r] * f2d<IU>(a0.x)));
-                res[1][r] = (float)fma(w2[r], f2d<IV>(a2.y), fma(w1[r], f2d<IV>(a1.y), w0[r] * f2d<IV>(a0.y)));
-                res[2][r] = (float)fma(w2[r], f2d<IP>(p2), fma(w1[r], f2d<IP>(p1), w0[r] * f2d<IP>(p0)));
+                const float4 a0 = *reinterpret_cast<const float4*>(nb + ov[r][0]);   // one 128-bit gather per vertex
+                const float4 a1 = *reinterpret_cast<const float4*>(nb + ov[r][1]);
+                const float4 a2 = *reinterpret_cast<const float4*>(nb + ov[r][2]);
+                const double p0 = __hiloint2double(__float_as_int(a0.w), __float_as_int(a0.z));
+                const double p1 = __hiloint2double(__float_as_int(a1.w), __float_as_int(a1.z));
+                const double p2 = __hiloint2double(__float_as_int(a2.w), __float_as_int(a2.z));
+                res[0][r] = (float)fma(w2[r], (double)a2.x, fma(w1[r], (double)a1.x, w0[r] * (double)a0.x));
+                res[1][r] = (float)fma(w2[r], (double)a2.y, fma(w1[r], (double)a1.y, w0[r] * (double)a0.y));
+                res[2][r] = (float)fma(w2[r], p2, fma(w1[r], p1, w0[r] * p0));
                 if (CHECKED) {
                     if (!finite_f(res[2][r])) fm |= 1u << (8 * r);           // pressure mask only
 #pragma unroll
@@ -263,7 +242,7 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
 #pragma unroll
                     for (int c = 0; c < 3; ++c)
 #pragma unroll
-                        for (int r = 0; r < NP; r += 2) norm_fast2(res[c][r], res[c][r + 1], -sc.mean[c], -sc.stdv[c], sc.rcp[c]);
+                        for (int r = 0; r < NP; r += 2) norm_fast2(res[c][r], res[c][r + 1], nm[c], ns[c], rc[c]);
                 }
             }
 #pragma unroll
@@ -280,62 +259,44 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
     }
 }
 
-template <int ICONV, int NP>
-__global__ void __launch_bounds__(NP == 4 ? 512 : 1024, 1)
+__global__ void __launch_bounds__(ST_THREADS, 1)
 k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int groups_per_traj, int TF, int n_patches,
-                         int ppx, int ppx_shift, int slot_vel, int slot_prs, StagedConst sc, unsigned flags) {
+                         int ppx, int ppx_shift, int slot_nodes, StagedConst sc, unsigned flags) {
     extern __shared__ __align__(128) unsigned char fl_smem[];
-    uint64_t* bar = (uint64_t*)fl_smem;
-    float* s_vel = (float*)(fl_smem + 128);
-    float* s_prs = s_vel + (size_t)TF * slot_vel;
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    unsigned parity = 0;
+    float4* s_nodes = (float4*)fl_smem;          // [TF][slot_nodes] records {u, v, p as fp64}
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int j = item / groups_per_traj, g = item - j * groups_per_traj;
         const FlTraj tr = trajs[j];
         const int fbeg = g * TF;
         if (fbeg >= tr.n_frames) continue;                     // uniform across the CTA
         const int nf = min(TF, tr.n_frames - fbeg);
-        const unsigned vb = (unsigned)tr.vel_stride * 4u, pb = (unsigned)tr.prs_stride * 4u;
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, (unsigned)nf * (vb + pb));
-            for (int f = 0; f < nf; ++f) {
-                const size_t t = (size_t)tr.t0 + (size_t)(fbeg + f) * tr.interval;
-                bulk_g2s(s_vel + (size_t)f * slot_vel, tr.d_velocity + t * tr.vel_stride, vb, bar);
-                bulk_g2s(s_prs + (size_t)f * slot_prs, tr.d_pressure + t * tr.prs_stride, pb, bar);
-            }
-        }
-        mbar_wait(bar, parity);
-        parity ^= 1u;
-        // staging scan: a non-finite, huge or subnormal node value sends the whole item down the checked path
+        // staging: coalesced 128-bit loads of 4 nodes' (u,v) pairs and pressures -> four 16-byte node
+        // records, pressure converted to fp64 once per node; scanned on the way
         float nanacc = 0.f, amax = 0.f;
-        bool sub = false;
-        auto scan4 = [&](const float4 v) {
+        auto scan4 = [&](const float4 v) {     // a non-finite or huge value sends the whole item down the checked path
             nanacc = fmaf(v.x, 0.f, fmaf(v.y, 0.f, fmaf(v.z, 0.f, fmaf(v.w, 0.f, nanacc))));
             amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fmaxf(fabsf(v.z), fabsf(v.w)), amax));
-            if (ICONV) {   // subnormal <=> 0 < |bits| < 0x00800000  <=>  (|bits| - 1) < 0x007fffff (unsigned)
-                sub |= ((__float_as_uint(v.x) & 0x7fffffffu) - 1u) < 0x007fffffu;
-                sub |= ((__float_as_uint(v.y) & 0x7fffffffu) - 1u) < 0x007fffffu;
-                sub |= ((__float_as_uint(v.z) & 0x7fffffffu) - 1u) < 0x007fffffu;
-                sub |= ((__float_as_uint(v.w) & 0x7fffffffu) - 1u) < 0x007fffffu;
-            }
         };
-        for (int f = 0; f < nf; ++f) {
-            const float4* v4 = (const float4*)(s_vel + (size_t)f * slot_vel);
-            for (int i = threadIdx.x; i < tr.vel_stride / 4; i += blockDim.x) scan4(v4[i]);
-            const float4* p4 = (const float4*)(s_prs + (size_t)f * slot_prs);
-            for (int i = threadIdx.x; i < tr.prs_stride / 4; i += blockDim.x) scan4(p4[i]);
+        const int nq = tr.prs_stride / 4;      // groups of 4 nodes per frame (pad nodes are zero-filled)
+        for (int i = threadIdx.x; i < nf * nq; i += blockDim.x) {
+            const int f = i / nq, k4 = i - f * nq;
+            const size_t t = (size_t)tr.t0 + (size_t)(fbeg + f) * tr.interval;
+            const float4* vsrc = (const float4*)(tr.d_velocity + t * tr.vel_stride) + 2 * k4;
+            const float4 va = fl_ldg_stream4(vsrc), vb = fl_ldg_stream4(vsrc + 1);
+            const float4 pp = fl_ldg_stream4((const float4*)(tr.d_pressure + t * tr.prs_stride) + k4);
+            scan4(va); scan4(vb); scan4(pp);
+            float4* d = s_nodes + (size_t)f * slot_nodes + 4 * k4;
+            const double p0 = (double)pp.x, p1 = (double)pp.y, p2 = (double)pp.z, p3 = (double)pp.w;
+            d[0] = make_float4(va.x, va.y, __int_as_float(__double2loint(p0)), __int_as_float(__double2hiint(p0)));
+            d[1] = make_float4(va.z, va.w, __int_as_float(__double2loint(p1)), __int_as_float(__double2hiint(p1)));
+            d[2] = make_float4(vb.x, vb.y, __int_as_float(__double2loint(p2)), __int_as_float(__double2hiint(p2)));
+            d[3] = make_float4(vb.z, vb.w, __int_as_float(__double2loint(p3)), __int_as_float(__double2hiint(p3)));
         }
-        const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || sub || !sc.fast_div);
-        const unsigned char* svb = (const unsigned char*)s_vel;
-        const unsigned char* spb = (const unsigned char*)s_prs;
-        if (bad) staged_item<true, 0, NP>(tr, svb, spb, slot_vel * 4, slot_prs * 4, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
-        else staged_item<false, ICONV, NP>(tr, svb, spb, slot_vel * 4, slot_prs * 4, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
-        __syncthreads();   // every gather of this item is done before the next bulk copies land
+        const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || !sc.fast_div);
+        const unsigned char* snb = (const unsigned char*)s_nodes;
+        if (bad) staged_item<true>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+        else staged_item<false>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+        __syncthreads();   // every gather of this item is done before the next item's staging lands
     }
 }
 
@@ -363,48 +324,34 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
         int slot_vel = 0, slot_prs = 0;
         for (int i = 0; i < n_traj && ok; ++i) {
             const FlTraj& t = h_trajs[i];
-            ok = t.vel_stride % 4 == 0 && t.prs_stride % 4 == 0 && t.vel_stride >= 2 * t.n_nodes && t.prs_stride >= t.n_nodes &&
+            ok = t.vel_stride % 4 == 0 && t.prs_stride % 4 == 0 && t.vel_stride >= 2 * t.prs_stride && t.prs_stride >= t.n_nodes &&
                  ((uintptr_t)t.d_velocity % 16 == 0) && ((uintptr_t)t.d_pressure % 16 == 0) && ((uintptr_t)t.d_states % 16 == 0) &&
                  (t.d_mask == nullptr || (uintptr_t)t.d_mask % 4 == 0);
             slot_vel = t.vel_stride > slot_vel ? t.vel_stride : slot_vel;
             slot_prs = t.prs_stride > slot_prs ? t.prs_stride : slot_prs;
         }
-        const size_t frame_bytes = 4 * ((size_t)slot_vel + slot_prs);
-        typedef void (*StagedKernel)(const FlTraj*, int, int, int, int, int, int, int, int, StagedConst, unsigned);
-        static const StagedKernel kernels[2][4] = {
-            {k_interp_patchify_staged<0, 2>, k_interp_patchify_staged<1, 2>, k_interp_patchify_staged<2, 2>, k_interp_patchify_staged<3, 2>},
-            {k_interp_patchify_staged<0, 4>, k_interp_patchify_staged<1, 4>, k_interp_patchify_staged<2, 4>, k_interp_patchify_staged<3, 4>}};
-        static int iconv = -1, ctas_per_sm = 1, np = 2;
-        if (iconv < 0) {   // tuning knobs (development): FLUIDGRID_ICONV=0..3, FLUIDGRID_CTAS=1|2, FLUIDGRID_NP=2|4
-            const char* e = getenv("FLUIDGRID_ICONV");
-            iconv = e ? atoi(e) : 1;
-            if (iconv < 0 || iconv > 3) iconv = 1;
-            e = getenv("FLUIDGRID_CTAS");
-            ctas_per_sm = (e && atoi(e) == 2) ? 2 : 1;
-            e = getenv("FLUIDGRID_NP");
-            np = (e && atoi(e) == 4) ? 4 : 2;
-            for (int a = 0; a < 2; ++a)
-                for (int b = 0; b < 4; ++b)
-                    FL_CUDA(cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        }
-        const size_t budget = (227 * 1024) / ctas_per_sm - 1024 - 128;   // per CTA; 1 KB/CTA is reserved by the driver
+        const size_t frame_bytes = 16 * (size_t)slot_prs;           // one 16-byte record per node (incl. pad nodes)
+        const size_t budget = 227 * 1024;
         int TF = ok && frame_bytes ? (int)(budget / frame_bytes) : 0;
         if (TF > 16) TF = 16;
         if (TF > max_frames) TF = max_frames;
-        if (TF >= 1 && (size_t)TF * frame_bytes < (1u << 20)) {       // mbarrier tx-count limit
+        if (TF >= 1) {
             StagedConst sc;
             for (int c = 0; c < 3; ++c) { sc.mean[c] = nc.mean[c]; sc.stdv[c] = nc.stdv[c]; sc.rcp[c] = 1.0f / nc.stdv[c]; }
             sc.fast_div = (flags & FL_NO_NORM) ? 1 : (fast_div_ok(nc.mean, nc.stdv) ? 1 : 0);
             const int gpt = (max_frames + TF - 1) / TF;
             const long n_items = (long)gpt * n_traj;
-            const size_t smem = 128 + (size_t)TF * frame_bytes;
+            const size_t smem = (size_t)TF * frame_bytes;
+            static bool attr_set = false;
+            if (!attr_set) {
+                FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                attr_set = true;
+            }
             int ppx_shift = -1;
             for (int b = 0; b < 16; ++b) if ((1 << b) == ppx) ppx_shift = b;
-            const long max_grid = (long)FL_SM_COUNT * ctas_per_sm;
-            int grid = n_items < max_grid ? (int)n_items : (int)max_grid;
-            const int threads = (np == 4 ? 512 : 1024) / ctas_per_sm;
-            kernels[np == 4][iconv]<<<grid, threads, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift,
-                                                                 slot_vel, slot_prs, sc, flags);
+            int grid = n_items < FL_SM_COUNT ? (int)n_items : FL_SM_COUNT;
+            k_interp_patchify_staged<<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift,
+                                                                    slot_prs, sc, flags);
             FL_LAUNCH_CHECK();
             return FL_OK;
         }

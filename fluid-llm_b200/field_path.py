@@ -51,7 +51,8 @@ class DeviceTrajectory:
             raise ValueError(f"pressure must be ({v.shape[0]}, {plan.n_nodes}, 1), got {tuple(p.shape)}")
         # frame pitch padded to 16 bytes so whole frames can be bulk-copied (TMA) into shared memory
         T, N = int(v.shape[0]), plan.n_nodes
-        self.vel_stride, self.prs_stride = (2 * N + 3) // 4 * 4, (N + 3) // 4 * 4
+        self.prs_stride = (N + 3) // 4 * 4          # nodes padded to a multiple of 4 (pad values are zero)
+        self.vel_stride = 2 * self.prs_stride
         self.vel_buf = torch.zeros((T, self.vel_stride), dtype=torch.float32, device=dev)
         self.prs_buf = torch.zeros((T, self.prs_stride), dtype=torch.float32, device=dev)
         self.velocity = self.vel_buf[:, :2 * N].view(T, N, 2)     # reference-shaped views of the padded buffers

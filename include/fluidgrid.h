@@ -99,9 +99,10 @@ typedef struct FlTraj {
     int32_t vel_stride;        /* floats between consecutive frames of d_velocity (>= 2*n_nodes) */
     int32_t prs_stride;        /* floats between consecutive frames of d_pressure (>= n_nodes)   */
 } FlTraj;
-/* Frame strides that are multiples of 4 floats on 16-byte aligned bases (pad floats readable and
- * finite) select the staged kernel: whole frames are bulk-copied (TMA) into shared memory and
- * gathered there.  Anything else runs the gather-from-global kernel -- same results, slower. */
+/* prs_stride a multiple of 4, vel_stride >= 2 * prs_stride, 16-byte aligned bases and pad floats
+ * that are readable and finite select the staged kernel: whole frames are staged in shared memory
+ * as 16-byte node records and gathered there.  Anything else runs the gather-from-global kernel --
+ * same results, slower. */
 
 int fl_interp_patchify(const FlTraj* h_trajs, int n_traj, int n_patches, int px, int py,
                        const float* h_mean, const float* h_std, unsigned flags, void* stream);
