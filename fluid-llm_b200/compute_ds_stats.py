@@ -64,16 +64,24 @@ def merge_stats(parts):
     return out
 
 
+def gather_stats(agg, group=None):
+    """All-gather the (6, 3) aggregates of every rank -> (world, 6, 3) in rank order (works on any backend)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return agg.unsqueeze(0)
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(agg) for _ in range(world)]
+    dist.all_gather(parts, agg.contiguous(), group=group)
+    return torch.stack(parts)
+
+
 def all_reduce_stats(agg, group=None):
     """The path's only collective: all-gather the 144-byte aggregates of every rank (NCCL over
     NVLink; latency-bound) and merge them in rank order on every rank -> identical results."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return agg
-    world = dist.get_world_size(group)
-    gathered = torch.empty((world,) + tuple(agg.shape), dtype=agg.dtype, device=agg.device)
-    dist.all_gather_into_tensor(gathered, agg.contiguous(), group=group)
-    return merge_stats(gathered)
+    return merge_stats(gather_stats(agg, group))
 
 
 def mean_std(agg):

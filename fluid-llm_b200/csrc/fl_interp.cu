@@ -331,7 +331,12 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             slot_prs = t.prs_stride > slot_prs ? t.prs_stride : slot_prs;
         }
         const size_t frame_bytes = 16 * (size_t)slot_prs;           // one 16-byte record per node (incl. pad nodes)
-        const size_t budget = 227 * 1024;
+        static int ctas_per_sm = 0;
+        if (!ctas_per_sm) {   // tuning knob (development): FLUIDGRID_CTAS=1|2
+            const char* e = getenv("FLUIDGRID_CTAS");
+            ctas_per_sm = (e && atoi(e) == 2) ? 2 : 1;
+        }
+        const size_t budget = ctas_per_sm == 1 ? 227 * 1024 : (227 * 1024) / 2 - 1024;
         int TF = ok && frame_bytes ? (int)(budget / frame_bytes) : 0;
         if (TF > 16) TF = 16;
         if (TF > max_frames) TF = max_frames;
@@ -349,8 +354,9 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             }
             int ppx_shift = -1;
             for (int b = 0; b < 16; ++b) if ((1 << b) == ppx) ppx_shift = b;
-            int grid = n_items < FL_SM_COUNT ? (int)n_items : FL_SM_COUNT;
-            k_interp_patchify_staged<<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift,
+            const long max_grid = (long)FL_SM_COUNT * ctas_per_sm;
+            int grid = n_items < max_grid ? (int)n_items : (int)max_grid;
+            k_interp_patchify_staged<<<grid, ST_THREADS / ctas_per_sm, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift,
                                                                     slot_prs, sc, flags);
             FL_LAUNCH_CHECK();
             return FL_OK;

@@ -35,6 +35,14 @@ CYLINDER = Personality("cylinder", False, 0, False, (0.823, 0.0005865, 0.04763),
 AIRFOIL = Personality("airfoil", True, 1, True, (170.1, -1.183, 9.935e+04), (50.0, 50.0, 6197.0))
 
 
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous block of trajectories owned by `rank` (sizes differ by at most one).  Trajectories are
+    independent, so this is the whole multi-GPU story of the per-frame path: no data-path collective."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
 class DeviceTrajectory:
     """Node fields of one trajectory resident in HBM, in the pickle's own layout
     (velocity f32[T,N,2], pressure f32[T,N,1]; max/ds_download/torch_MGN.py:68-95)."""

@@ -27,6 +27,18 @@ def num_patches(dim_size, kern_size, stride, padding=0):
     return (dim_size + 2 * padding - kern_size) // stride + 1
 
 
+def position_ids(seq_len, n_x_patch, n_y_patch):
+    """simple_dataloader.py:218-226 -> int64 (seq_len-1, N_patch, 3).  Labels patch l as (l % N_x, l // N_x)
+    although F.unfold orders patches l = bx * N_y + by; reproduced as is (model weights depend on it)."""
+    n_patch = n_x_patch * n_y_patch
+    arange = np.arange((seq_len - 1) * n_patch)
+    x_idx = arange % n_x_patch
+    y_idx = (arange // n_x_patch) % n_y_patch
+    t_idx = arange // n_patch
+    ids = np.stack([x_idx, y_idx, t_idx], axis=1).reshape(seq_len - 1, n_patch, 3)
+    return torch.from_numpy(ids.astype(np.int64))
+
+
 class _GpuFieldDataset(Dataset):
     """Shared machinery of MGNDataset / AirfoilDataset."""
 
@@ -124,13 +136,7 @@ class _GpuFieldDataset(Dataset):
     def _get_pos_id(self):
         """simple_dataloader.py:218-226 (the labelling quirk is reproduced as is)."""
         if self._pos_ids is None:
-            seq_dim = (self.seq_len - 1) * self.N_patch
-            arange = np.arange(seq_dim)
-            x_idx = arange % self.N_x_patch
-            y_idx = (arange // self.N_x_patch) % self.N_y_patch
-            t_idx = arange // self.N_patch
-            ids = np.stack([x_idx, y_idx, t_idx], axis=1).reshape(self.seq_len - 1, self.N_patch, 3)
-            self._pos_ids = torch.from_numpy(ids.astype(np.int64))
+            self._pos_ids = position_ids(self.seq_len, self.N_x_patch, self.N_y_patch)
         return self._pos_ids
 
     def __len__(self):

@@ -1,0 +1,69 @@
+"""CPU: host-side logic of the product (grid axes, crops, patch geometry, position ids, sharding)
+against the oracle's restatement of the reference."""
+import numpy as np
+import pytest
+
+from oracle import pipeline as P
+
+from helpers import trajectory
+
+
+@pytest.mark.parametrize("sem", ["1.26", "2.x"])
+@pytest.mark.parametrize("box", [(0, 1.6, 0, 0.41), (-0.49, 1.99, -0.74, 0.73), (-2.5, 2.5, -1.7, 1.5), (0, 1, 0, 3.3)])
+def test_grid_pos_matches_oracle(sem, box):
+    from fluid_llm_b200.mesh_utils import grid_pos
+    b = [np.float32(v) for v in box]
+    gx, gy = grid_pos(b[0], b[1], b[2], b[3], 238, sem)
+    ox, oy = P.grid_pos(b[0], b[1], b[2], b[3], 238, sem)
+    assert gx.dtype == np.float32 and np.array_equal(gx, ox) and np.array_equal(gy, oy)
+
+
+def test_default_semantics_is_the_pinned_numpy(monkeypatch):
+    from fluid_llm_b200 import mesh_utils
+    monkeypatch.delenv("FLUIDGRID_NUMPY_SEMANTICS", raising=False)
+    assert mesh_utils.default_numpy_semantics() == "1.26"
+    monkeypatch.setenv("FLUIDGRID_NUMPY_SEMANTICS", "2.x")
+    assert mesh_utils.default_numpy_semantics() == "2.x"
+
+
+def test_airfoil_crop_matches_oracle():
+    from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
+    tr = trajectory("airfoil")
+    m, pos, faces = crop_airfoil_mesh(tr["mesh_pos"], tr["cells"])
+    mo, poso, faceso = P.airfoil_crop(tr["mesh_pos"], tr["cells"])
+    assert np.array_equal(m, mo) and np.array_equal(pos, poso) and np.array_equal(faces, faceso)
+    assert faces.max() < len(pos) and 0 < len(pos) < len(tr["mesh_pos"])
+
+
+def test_position_ids_and_patch_counts():
+    from fluid_llm_b200.simple_dataloader import num_patches, position_ids
+    from fluid_llm_b200.ds_props import DSProps
+    assert np.array_equal(position_ids(10, 15, 4).numpy(), P.get_pos_id(10, 15, 4))
+    assert position_ids(4, 13, 7).dtype.is_floating_point is False and position_ids(4, 13, 7).shape == (3, 91, 3)
+    assert num_patches(240, 16, 16) == 15 and num_patches(64, 16, 16) == 4
+    p = DSProps(15, 4, (16, 16), 10)
+    assert (p.input_tot_size, p.N_patch, p.out_patch_size, p.channel) == ((240, 64), 60, (16, 16), 3)
+
+
+def test_shard_assignment_covers_everything_once():
+    from fluid_llm_b200.field_path import shard_range
+    for n in (1, 7, 32, 256):
+        for world in (1, 2, 3, 8):
+            got = []
+            for r in range(world):
+                lo, hi = shard_range(n, r, world)
+                got += list(range(lo, hi))
+            assert got == list(range(n))
+            sizes = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synthetic_meshes_are_deterministic_and_valid():
+    from fluid_llm_b200 import synth
+    for kind in ("cylinder", "airfoil", "eagle"):
+        p1, c1 = synth.make_mesh(kind, 3)
+        p2, c2 = synth.make_mesh(kind, 3)
+        assert np.array_equal(p1, p2) and np.array_equal(c1, c2)
+        assert p1.dtype == np.float32 and c1.dtype == np.int32 and c1.min() == 0 and c1.max() == len(p1) - 1
+    with pytest.raises(ValueError):
+        synth.make_mesh("torus")
