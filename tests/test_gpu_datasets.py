@@ -1,0 +1,140 @@
+"""-m gpu: the drop-in datasets (MGNDataset / AirfoilDataset) and the frozen reference outputs."""
+import copy
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pipeline as P
+
+from helpers import PATCH, trajectory
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _write(tmp_path, trajs):
+    for i, tr in enumerate(trajs):
+        with open(tmp_path / f"{i}.pkl", "wb") as f:
+            pickle.dump(tr, f)
+    return str(tmp_path)
+
+
+@pytest.mark.parametrize("kind", ["cylinder", "airfoil"])
+def test_dataset_five_tuple_matches_oracle(kind, tmp_path):
+    from fluid_llm_b200.airfoil_ds import AirfoilDataset
+    from fluid_llm_b200.simple_dataloader import MGNDataset
+    trajs = [trajectory(kind, 140, s, 10 + s) for s in (0, 1)]
+    d = _write(tmp_path, copy.deepcopy(trajs))
+    DS = MGNDataset if kind == "cylinder" else AirfoilDataset
+    ds = DS(load_dir=d, resolution=238, patch_size=PATCH, stride=PATCH, seq_len=4, seq_interval=2, mode="valid")
+    pers = "airfoil" if kind == "airfoil" else "cylinder"
+    assert len(ds) == 2 and ds.save_files == ["0.pkl", "1.pkl"]
+    want, extra = P.ds_get(trajs[1], 100, 4, 2, 238, PATCH, pers, return_all=True)     # valid mode: step 100
+    assert (ds.N_x_patch, ds.N_y_patch, ds.N_patch) == (extra["N_x_patch"], extra["N_y_patch"], extra["N_x_patch"] * extra["N_y_patch"])
+    got = ds[1]
+    assert len(got) == 5
+    for a, b in zip(got, want):
+        assert a.is_cuda and tuple(a.shape) == b.shape
+        assert str(a.dtype).replace("torch.", "") == str(b.dtype)
+        assert np.array_equal(a.cpu().numpy(), b)
+    # ds_get with explicit arguments, int index, clamped step (simple_dataloader.py:177-179)
+    ds.max_step_num = 120                      # the synthetic trajectories are shorter than the datasets' 600 steps
+    got = ds.ds_get(0, 10 ** 6)
+    want = P.ds_get(trajs[0], 120, 4, 2, 238, PATCH, pers)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.cpu().numpy(), b)
+    # ds_min_max probes file [1], step 20, raw values (simple_dataloader.py:45-50)
+    raw = P.full_seq(trajs[1], 20, 1, 1, 238, PATCH, pers)[0][0, :3]
+    if kind == "airfoil":
+        raw = raw[:, 16:-16, 16:-16]
+    for c in range(3):
+        assert np.isclose(ds.ds_min_max[c][0], raw[c].min()) and np.isclose(ds.ds_min_max[c][1], raw[c].max())
+    # normalize=False and host output
+    ds2 = DS(load_dir=d, resolution=238, patch_size=PATCH, stride=PATCH, seq_len=3, seq_interval=1, mode="test",
+             normalize=False, output_device="cpu")
+    got = ds2[0]
+    want = P.ds_get(trajs[0], 100, 3, 1, 238, PATCH, pers, normalize_ds=False)
+    for a, b in zip(got, want):
+        assert not a.is_cuda and np.array_equal(a.numpy(), b)
+
+
+def test_dataset_train_mode_and_dataloader(tmp_path):
+    from fluid_llm_b200.simple_dataloader import MGNDataset
+    from torch.utils.data import DataLoader
+    trajs = [trajectory("cylinder", 620, s, 10 + s) for s in (0, 1)]
+    d = _write(tmp_path, copy.deepcopy(trajs))
+    ds = MGNDataset(load_dir=d, resolution=238, patch_size=PATCH, stride=PATCH, seq_len=10, seq_interval=1, mode="train")
+    assert ds.max_step_num == 590
+    import random
+    random.seed(3)
+    step = random.randint(0, 590)
+    random.seed(3)
+    got = ds[0]
+    want = P.ds_get(trajs[0], step, 10, 1, 238, PATCH, "cylinder")
+    assert np.array_equal(got[0].cpu().numpy(), want[0])
+    dl = DataLoader(ds, batch_size=2, shuffle=False, num_workers=0)
+    batch = next(iter(dl))
+    assert tuple(batch[0].shape) == (2, 9, 60, 3, 16, 16) and batch[3].dtype == torch.bool and batch[4].dtype == torch.int64
+
+
+@pytest.mark.parametrize("kind", ["cylinder", "airfoil"])
+def test_cuda_path_reproduces_frozen_reference(kind):
+    """tests/golden/ref_*.npz = the reference's own datasets run under NumPy 2.x (oracle/make_golden.py);
+    the CUDA path in "2.x" grid semantics must reproduce them (tri ids bit-exact, values <= 1e-6 rel)."""
+    from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
+    from fluid_llm_b200.field_path import AIRFOIL, CYLINDER, DeviceTrajectory, interp_patchify
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    g = np.load(os.path.join(GOLDEN, f"ref_{kind}.npz"))
+    pos, faces, vel, prs = g["mesh_pos"], g["cells"], g["velocity"], g["pressure"]
+    if kind == "airfoil":
+        m, pos, faces = crop_airfoil_mesh(pos, faces)
+        vel, prs = vel[:, m], prs[:, m]
+    plan = MeshPlan(pos, faces, 238, "2.x")
+    assert np.array_equal(plan.tri_index, g["tri_index"])
+    states, mask, tab = interp_patchify(DeviceTrajectory(vel, prs, plan), int(g["step_num"]), int(g["seq_len"]),
+                                        int(g["seq_interval"]), PATCH, AIRFOIL if kind == "airfoil" else CYLINDER)
+    assert (tab.n_bx, tab.n_by) == (int(g["N_x_patch"]), int(g["N_y_patch"]))
+    s = states.cpu().numpy()
+    np.testing.assert_allclose(s[:-1], g["input_states"], rtol=1e-6, atol=0)
+    assert np.array_equal(s[:-1], g["input_states"]) and np.array_equal(s[1:], g["next_state"])
+    masks = np.unpackbits(g["masks"])[:np.prod(g["masks_shape"])].reshape(g["masks_shape"]).astype(bool)
+    assert np.array_equal(np.repeat(mask.cpu().numpy()[1:, :, None], 3, axis=2).astype(bool), masks)
+
+
+def test_full_size_properties_cylinder():
+    """BASELINE config 1 at full size (T = 600): properties that need no oracle pass."""
+    from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    tr = trajectory("cylinder", 600)
+    plan = MeshPlan(tr["mesh_pos"], tr["cells"], 238)
+    dt = DeviceTrajectory(tr["velocity"], tr["pressure"], plan)
+    raw, mask, tab = interp_patchify(dt, 0, 600, 1, PATCH, CYLINDER, normalize=False)
+    assert tuple(raw.shape) == (600, 60, 3, 16, 16)
+    # mask <=> tri == -1 (incl. padding) and is the same for every frame; masked pixels are exactly 0
+    m0 = mask[0]
+    assert bool((mask == m0).all())
+    tri = tab.idx[:, 3].reshape(60, 16, 16)
+    assert torch.equal(m0.bool(), tri < 0)
+    assert float(raw.abs().amax(dim=(0, 2))[m0.bool()].max()) == 0.0
+    # interpolation is a convex combination: values stay inside the per-frame node range
+    vmin = torch.from_numpy(np.stack([tr["velocity"][..., 0].min(1), tr["velocity"][..., 1].min(1), tr["pressure"][..., 0].min(1)], 1)).cuda()
+    vmax = torch.from_numpy(np.stack([tr["velocity"][..., 0].max(1), tr["velocity"][..., 1].max(1), tr["pressure"][..., 0].max(1)], 1)).cuda()
+    inside = ~m0.bool()
+    sel = raw.permute(0, 2, 1, 3, 4)[:, :, inside]            # (T, 3, n_inside)
+    assert bool((sel >= vmin[:, :, None] - 1e-6).all()) and bool((sel <= vmax[:, :, None] + 1e-6).all())
+    # linearity: interp(a*f + g) == a*interp(f) + interp(g) up to fp32 rounding, via a constant field: exact
+    const = DeviceTrajectory(np.full((2, plan.n_nodes, 2), 0.75, np.float32), np.full((2, plan.n_nodes, 1), -3.5, np.float32), plan)
+    c, _, _ = interp_patchify(const, 0, 2, 1, PATCH, CYLINDER, normalize=False)
+    cs = c.permute(0, 2, 1, 3, 4)[:, :, inside]
+    assert bool((cs[:, :2] == 0.75).all()) and bool((cs[:, 2] == -3.5).all())
+    # normalised output == (raw - mean) / std computed by torch in fp32, bit for bit
+    norm, _, _ = interp_patchify(dt, 0, 600, 1, PATCH, CYLINDER)
+    mean = torch.tensor(CYLINDER.means, device="cuda").view(1, 1, 3, 1, 1)
+    std = torch.tensor(CYLINDER.stds, device="cuda").view(1, 1, 3, 1, 1)
+    assert torch.equal(norm, (raw - mean) / std)
+    # staged and gather kernels agree bit for bit at full size
+    norm2, _, _ = interp_patchify(dt, 0, 600, 1, PATCH, CYLINDER, force_gather=True)
+    assert torch.equal(norm, norm2)
