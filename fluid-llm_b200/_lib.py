@@ -17,7 +17,7 @@ FL_FORCE_GATHER = 8
 
 class FlTraj(ctypes.Structure):
     _fields_ = [("d_velocity", c_void_p), ("d_pressure", c_void_p), ("d_idx", c_void_p), ("d_w", c_void_p),
-                ("d_states", c_void_p), ("d_mask", c_void_p),
+                ("d_idx_slot", c_void_p), ("d_node_slot", c_void_p), ("d_states", c_void_p), ("d_mask", c_void_p),
                 ("n_nodes", c_int32), ("t0", c_int32), ("interval", c_int32), ("n_frames", c_int32),
                 ("vel_stride", c_int32), ("prs_stride", c_int32)]
 

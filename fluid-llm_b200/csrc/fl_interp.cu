@@ -168,13 +168,30 @@ __device__ __forceinline__ void norm_fast2(float& x0, float& x1, unsigned long l
     x1 = __uint_as_float((unsigned)(y >> 32));
 }
 
-template <bool CHECKED>
+// float -> double on the integer/FMA pipes instead of the 16-lane conversion unit (XU): exact for
+// +-0 and normal numbers (the staging scan sends items holding subnormals, inf or NaN down the
+// checked path).  {t>>3, t<<29} is one 32x32->64 multiply by 2^29; then exponent re-bias and sign.
+__device__ __forceinline__ double f2d_int(float f) {
+    const unsigned x = __float_as_uint(f);
+    const unsigned t = x & 0x7fffffffu;
+    const unsigned long long p = (unsigned long long)t * 0x20000000ull;
+    unsigned hi = (unsigned)(p >> 32);
+    hi += t ? 0x38000000u : 0u;
+    hi |= x & 0x80000000u;
+    return __hiloint2double((int)hi, (int)(unsigned)p);
+}
+template <bool INT> __device__ __forceinline__ double f2d(float f) { return INT ? f2d_int(f) : (double)f; }
+
+// ICONV: 0 = every float->double conversion on the XU, 1 = v on the integer pipes, 2 = u and v
+template <bool CHECKED, int ICONV>
 __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned char* __restrict__ s_nodes, int slot_b,
                                             int fbeg, int nf, int n_patches, int ppx, int ppx_shift, const StagedConst& sc,
                                             unsigned flags) {
     const bool mask_aware = flags & FL_MASK_AWARE_NORM, no_norm = flags & FL_NO_NORM;
+    constexpr bool IV = !CHECKED && ICONV >= 1, IU = !CHECKED && ICONV >= 2;
     const int nchunks = n_patches * ppx / (32 * NP);
     const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    const FlCellIdx* idx_tab = tr.d_idx_slot ? tr.d_idx_slot : tr.d_idx;   // node ids as shared-memory slots
     const size_t frame_out = (size_t)n_patches * 3 * ppx;
     unsigned long long nm[3], ns[3], rc[3];
 #pragma unroll
@@ -186,7 +203,7 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
         unsigned mbits = 0;     // byte r = 1 if pixel r is outside the mesh
 #pragma unroll
         for (int r = 0; r < NP; ++r) {
-            const int4 id = __ldg((const int4*)tr.d_idx + o + 32 * r);
+            const int4 id = __ldg((const int4*)idx_tab + o + 32 * r);
             const double2 ww = __ldg((const double2*)tr.d_w + o + 32 * r);
             const bool out = id.w < 0;
             mbits |= out ? (1u << (8 * r)) : 0u;
@@ -213,8 +230,8 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
                 const double p0 = __hiloint2double(__float_as_int(a0.w), __float_as_int(a0.z));
                 const double p1 = __hiloint2double(__float_as_int(a1.w), __float_as_int(a1.z));
                 const double p2 = __hiloint2double(__float_as_int(a2.w), __float_as_int(a2.z));
-                res[0][r] = (float)fma(w2[r], (double)a2.x, fma(w1[r], (double)a1.x, w0[r] * (double)a0.x));
-                res[1][r] = (float)fma(w2[r], (double)a2.y, fma(w1[r], (double)a1.y, w0[r] * (double)a0.y));
+                res[0][r] = (float)fma(w2[r], f2d<IU>(a2.x), fma(w1[r], f2d<IU>(a1.x), w0[r] * f2d<IU>(a0.x)));
+                res[1][r] = (float)fma(w2[r], f2d<IV>(a2.y), fma(w1[r], f2d<IV>(a1.y), w0[r] * f2d<IV>(a0.y)));
                 res[2][r] = (float)fma(w2[r], p2, fma(w1[r], p1, w0[r] * p0));
                 if (CHECKED) {
                     if (!finite_f(res[2][r])) fm |= 1u << (8 * r);           // pressure mask only
@@ -259,6 +276,7 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
     }
 }
 
+template <int ICONV>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int groups_per_traj, int TF, int n_patches,
                          int ppx, int ppx_shift, int slot_nodes, StagedConst sc, unsigned flags) {
@@ -273,9 +291,16 @@ k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int grou
         // staging: coalesced 128-bit loads of 4 nodes' (u,v) pairs and pressures -> four 16-byte node
         // records, pressure converted to fp64 once per node; scanned on the way
         float nanacc = 0.f, amax = 0.f;
-        auto scan4 = [&](const float4 v) {     // a non-finite or huge value sends the whole item down the checked path
+        bool sub = false;
+        auto scan4 = [&](const float4 v, bool vel) {     // a non-finite or huge value sends the whole item down the checked path
             nanacc = fmaf(v.x, 0.f, fmaf(v.y, 0.f, fmaf(v.z, 0.f, fmaf(v.w, 0.f, nanacc))));
             amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fmaxf(fabsf(v.z), fabsf(v.w)), amax));
+            if (ICONV && vel) {   // subnormal <=> 0 < |bits| < 0x00800000  <=>  (|bits| - 1) < 0x007fffff (unsigned)
+                sub |= ((__float_as_uint(v.x) & 0x7fffffffu) - 1u) < 0x007fffffu;
+                sub |= ((__float_as_uint(v.y) & 0x7fffffffu) - 1u) < 0x007fffffu;
+                sub |= ((__float_as_uint(v.z) & 0x7fffffffu) - 1u) < 0x007fffffu;
+                sub |= ((__float_as_uint(v.w) & 0x7fffffffu) - 1u) < 0x007fffffu;
+            }
         };
         const int nq = tr.prs_stride / 4;      // groups of 4 nodes per frame (pad nodes are zero-filled)
         for (int i = threadIdx.x; i < nf * nq; i += blockDim.x) {
@@ -284,18 +309,20 @@ k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int grou
             const float4* vsrc = (const float4*)(tr.d_velocity + t * tr.vel_stride) + 2 * k4;
             const float4 va = fl_ldg_stream4(vsrc), vb = fl_ldg_stream4(vsrc + 1);
             const float4 pp = fl_ldg_stream4((const float4*)(tr.d_pressure + t * tr.prs_stride) + k4);
-            scan4(va); scan4(vb); scan4(pp);
-            float4* d = s_nodes + (size_t)f * slot_nodes + 4 * k4;
+            scan4(va, true); scan4(vb, true); scan4(pp, false);
+            float4* d = s_nodes + (size_t)f * slot_nodes;
+            int4 sl = make_int4(4 * k4, 4 * k4 + 1, 4 * k4 + 2, 4 * k4 + 3);
+            if (tr.d_node_slot) sl = __ldg((const int4*)tr.d_node_slot + k4);      // spatially sorted slots
             const double p0 = (double)pp.x, p1 = (double)pp.y, p2 = (double)pp.z, p3 = (double)pp.w;
-            d[0] = make_float4(va.x, va.y, __int_as_float(__double2loint(p0)), __int_as_float(__double2hiint(p0)));
-            d[1] = make_float4(va.z, va.w, __int_as_float(__double2loint(p1)), __int_as_float(__double2hiint(p1)));
-            d[2] = make_float4(vb.x, vb.y, __int_as_float(__double2loint(p2)), __int_as_float(__double2hiint(p2)));
-            d[3] = make_float4(vb.z, vb.w, __int_as_float(__double2loint(p3)), __int_as_float(__double2hiint(p3)));
+            d[sl.x] = make_float4(va.x, va.y, __int_as_float(__double2loint(p0)), __int_as_float(__double2hiint(p0)));
+            d[sl.y] = make_float4(va.z, va.w, __int_as_float(__double2loint(p1)), __int_as_float(__double2hiint(p1)));
+            d[sl.z] = make_float4(vb.x, vb.y, __int_as_float(__double2loint(p2)), __int_as_float(__double2hiint(p2)));
+            d[sl.w] = make_float4(vb.z, vb.w, __int_as_float(__double2loint(p3)), __int_as_float(__double2hiint(p3)));
         }
-        const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || !sc.fast_div);
+        const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || sub || !sc.fast_div);
         const unsigned char* snb = (const unsigned char*)s_nodes;
-        if (bad) staged_item<true>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
-        else staged_item<false>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+        if (bad) staged_item<true, 0>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+        else staged_item<false, ICONV>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
         __syncthreads();   // every gather of this item is done before the next item's staging lands
     }
 }
@@ -326,7 +353,8 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             const FlTraj& t = h_trajs[i];
             ok = t.vel_stride % 4 == 0 && t.prs_stride % 4 == 0 && t.vel_stride >= 2 * t.prs_stride && t.prs_stride >= t.n_nodes &&
                  ((uintptr_t)t.d_velocity % 16 == 0) && ((uintptr_t)t.d_pressure % 16 == 0) && ((uintptr_t)t.d_states % 16 == 0) &&
-                 (t.d_mask == nullptr || (uintptr_t)t.d_mask % 4 == 0);
+                 (t.d_mask == nullptr || (uintptr_t)t.d_mask % 4 == 0) && ((uintptr_t)t.d_node_slot % 16 == 0) &&
+                 ((uintptr_t)t.d_idx_slot % 16 == 0);
             slot_vel = t.vel_stride > slot_vel ? t.vel_stride : slot_vel;
             slot_prs = t.prs_stride > slot_prs ? t.prs_stride : slot_prs;
         }
@@ -347,16 +375,21 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             const int gpt = (max_frames + TF - 1) / TF;
             const long n_items = (long)gpt * n_traj;
             const size_t smem = (size_t)TF * frame_bytes;
-            static bool attr_set = false;
-            if (!attr_set) {
-                FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                attr_set = true;
+            typedef void (*StagedKernel)(const FlTraj*, int, int, int, int, int, int, int, StagedConst, unsigned);
+            static const StagedKernel kernels[3] = {k_interp_patchify_staged<0>, k_interp_patchify_staged<1>, k_interp_patchify_staged<2>};
+            static int iconv = -1;
+            if (iconv < 0) {   // tuning knob (development): FLUIDGRID_ICONV=0|1|2
+                const char* e = getenv("FLUIDGRID_ICONV");
+                iconv = e ? atoi(e) : 0;
+                if (iconv < 0 || iconv > 2) iconv = 0;
+                for (int a = 0; a < 3; ++a)
+                    FL_CUDA(cudaFuncSetAttribute(kernels[a], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             }
             int ppx_shift = -1;
             for (int b = 0; b < 16; ++b) if ((1 << b) == ppx) ppx_shift = b;
             const long max_grid = (long)FL_SM_COUNT * ctas_per_sm;
             int grid = n_items < max_grid ? (int)n_items : (int)max_grid;
-            k_interp_patchify_staged<<<grid, ST_THREADS / ctas_per_sm, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift,
+            kernels[iconv]<<<grid, ST_THREADS / ctas_per_sm, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift,
                                                                     slot_prs, sc, flags);
             FL_LAUNCH_CHECK();
             return FL_OK;

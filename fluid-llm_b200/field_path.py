@@ -75,7 +75,7 @@ class TrajBatch:
     """Pre-built launch descriptors for a fixed batch (descriptor array already on the device), so
     the steady-state call is exactly one kernel launch and no host->device traffic."""
 
-    def __init__(self, trajs, tables, t0s, interval, n_frames, want_mask=True):
+    def __init__(self, trajs, tables, t0s, interval, n_frames, want_mask=True, use_slots=True):
         if not (len(trajs) == len(tables) == len(t0s)) or not trajs:
             raise ValueError("trajs, tables and t0s must be non-empty and of equal length")
         tab0 = tables[0]
@@ -95,6 +95,8 @@ class TrajBatch:
         arr = (FlTraj * self.n_traj)()
         for i, (tr, tab, t0) in enumerate(zip(trajs, tables, t0s)):
             arr[i] = FlTraj(tr.vel_buf.data_ptr(), tr.prs_buf.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(),
+                            tab.idx_slot.data_ptr() if use_slots and tab.idx_slot is not None else 0,
+                            tr.plan.node_slot_d.data_ptr() if use_slots and tab.idx_slot is not None else 0,
                             self.states[i].data_ptr(), self.mask[i].data_ptr() if want_mask else 0,
                             tr.plan.n_nodes, int(t0), int(interval), self.n_frames, tr.vel_stride, tr.prs_stride)
         self.host_desc = arr

@@ -67,11 +67,34 @@ def grid_pos(x_min, x_max, y_min, y_max, grid_res, numpy_semantics=None):
 
 
 class PatchTable:
-    """The static table re-ordered into output-pixel order for one dataset personality."""
+    """The static table re-ordered into output-pixel order for one dataset personality.
+    `idx_slot` is the same table with node ids replaced by the plan's shared-memory slots."""
 
-    def __init__(self, idx, w, n_bx, n_by, px, py):
+    def __init__(self, idx, w, n_bx, n_by, px, py, idx_slot=None):
         self.idx, self.w, self.n_bx, self.n_by, self.px, self.py = idx, w, n_bx, n_by, px, py
+        self.idx_slot = idx_slot
         self.n_patches = n_bx * n_by
+
+
+def morton_slots(pos32, n_padded):
+    """Slot of every node in a Z-order (Morton) sort of the positions: spatial neighbours get neighbouring
+    slots, so the 32 adjacent pixels one gather instruction serves read neighbouring 16-byte records
+    (distinct bank groups) instead of colliding at random.  Pad nodes keep their own index."""
+    n = len(pos32)
+    lo, hi = pos32.min(axis=0).astype(np.float64), pos32.max(axis=0).astype(np.float64)
+    q = ((pos32.astype(np.float64) - lo) / np.maximum(hi - lo, 1e-300) * 65535.0).astype(np.uint64)
+
+    def spread(v):
+        v = (v | (v << 8)) & np.uint64(0x00FF00FF)
+        v = (v | (v << 4)) & np.uint64(0x0F0F0F0F)
+        v = (v | (v << 2)) & np.uint64(0x33333333)
+        v = (v | (v << 1)) & np.uint64(0x55555555)
+        return v
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1))
+    order = np.argsort(code, kind="stable")
+    slot = np.arange(n_padded, dtype=np.int32)
+    slot[order] = np.arange(n, dtype=np.int32)
+    return slot
 
 
 class MeshPlan:
@@ -119,6 +142,8 @@ class MeshPlan:
             self.cells_d = torch.from_numpy(tri).to(dev)
             self.ax_d = torch.from_numpy(self.ax).to(dev)
             self.ay_d = torch.from_numpy(self.ay).to(dev)
+            self.n_padded = (self.n_nodes + 3) // 4 * 4
+            self.node_slot_d = torch.from_numpy(morton_slots(pos32, self.n_padded)).to(dev)
             n = self.nx * self.ny
             self.tri_index_d = torch.empty((self.nx, self.ny), dtype=torch.int32, device=dev)
             self.cell_idx_d = torch.empty((n, 4), dtype=torch.int32, device=dev)
@@ -172,7 +197,10 @@ class MeshPlan:
                 check(lib.fl_plan_patch_table(ptr(self.cell_idx_d), ptr(self.cell_w_d), self.nx, self.ny, px, py, key[2],
                                               flags, ptr(idx), ptr(w), ctypes.byref(nbx), ctypes.byref(nby),
                                               stream_ptr()), "fl_plan_patch_table")
-            tab = PatchTable(idx, w, nbx.value, nby.value, px, py)
+                idx_slot = idx.clone()
+                inside = idx[:, 3] >= 0
+                idx_slot[inside, :3] = self.node_slot_d[idx[inside, :3].long()]
+            tab = PatchTable(idx, w, nbx.value, nby.value, px, py, idx_slot)
             self._tables[key] = tab
         return tab
 

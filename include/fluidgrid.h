@@ -32,7 +32,7 @@ extern "C" {
 #define FL_E_WORKSPACE (-3)/* workspace too small */
 #define FL_E_ALIGN (-4)    /* pointer not aligned as documented */
 
-#define FL_ABI_VERSION 2
+#define FL_ABI_VERSION 3
 
 /* personality flags of fl_plan_patch_table / fl_interp_patchify */
 #define FL_FLIP_Y 1u          /* airfoil_ds.py:80  -- y axis reversed after padding */
@@ -93,6 +93,9 @@ typedef struct FlTraj {
     const float* d_pressure;   /* [T, n_nodes, 1] */
     const FlCellIdx* d_idx;    /* patch-ordered table of this trajectory's mesh */
     const FlCellW* d_w;
+    const FlCellIdx* d_idx_slot; /* optional (NULL = d_idx): same table with node ids replaced by shared-memory slots */
+    const int32_t* d_node_slot;  /* optional (NULL = identity): slot of every node, [prs_stride]; a spatially sorted
+                                    (Morton) order keeps the gathers of neighbouring pixels in neighbouring banks */
     float* d_states;           /* [n_frames, L, 3, px, py] */
     uint8_t* d_mask;           /* [n_frames, L, px, py] or NULL */
     int32_t n_nodes, t0, interval, n_frames;
