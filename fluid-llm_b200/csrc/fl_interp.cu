@@ -190,7 +190,11 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
     const bool mask_aware = flags & FL_MASK_AWARE_NORM, no_norm = flags & FL_NO_NORM;
     constexpr bool IV = !CHECKED && ICONV >= 1, IU = !CHECKED && ICONV >= 2;
     const int nchunks = n_patches * ppx / (32 * NP);
-    const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    const int lane_id = threadIdx.x & 31, warps = blockDim.x >> 5;
+    // pixel of this lane inside a group of 32 adjacent pixels (2 patch rows x 16): the 8 lanes of a quarter-warp
+    // (one LDS.128 wavefront) take a compact 2 x 4 block, which touches fewer distinct nodes than a 1 x 8 strip;
+    // any permutation inside the group keeps every warp store one contiguous 128-byte line
+    const int lane = ppx_shift >= 0 && (ppx & 15) == 0 ? ((lane_id >> 2) & 1) * 16 + (lane_id >> 3) * 4 + (lane_id & 3) : lane_id;
     const FlCellIdx* idx_tab = tr.d_idx_slot ? tr.d_idx_slot : tr.d_idx;   // node ids as shared-memory slots
     const size_t frame_out = (size_t)n_patches * 3 * ppx;
     unsigned long long nm[3], ns[3], rc[3];
