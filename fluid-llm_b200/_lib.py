@@ -50,6 +50,9 @@ SIGNATURES = {
     "fl_stats_workspace_bytes": (c_size_t, []),
     "fl_ds_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fl_stats_merge": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "fl_cast_bf16": (c_int, [c_void_p, c_void_p, ctypes.c_long, c_void_p]),
+    "fl_patch_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,278 @@
+// fl_embed.cu -- the path's only dense contraction: the patch-embedding projection on the 5th-gen
+// tensor cores (tcgen05.mma, accumulators in TMEM, operands staged by TMA).
+//
+// Replaces PatchEmbeddings.forward + MLP.forward + the positional-embedding add of InputEmbeddings.forward
+// (src/models/layers/patch_encoder.py:23-30, MLP.py:48-54, input_embeddings.py:36-52,
+// positional_encodings/positional_embeddings.py:32-37) as the reference runs them under bf16 autocast:
+//   h   = LeakyReLU_0.01( bf16( x_bf16 @ W1^T + b1 ) )                 tokens x 768 -> 512
+//   out = bf16( h @ W2^T + b2 ) + (x_emb[p0] + y_emb[p1] + t_emb[p2])  512 -> llm_dim, fp32 result
+// One kernel, C[M,N] = epilogue(A[M,K] . B[N,K]^T), used twice; nn.Linear weights are [N,K] K-major already.
+//
+// Kernel anatomy (one 128 x BLOCK_N output tile per CTA, 192 threads):
+//   warp 0     TMA producer: cp.async.bulk.tensor.2d of the A (128 x 64) and B (BLOCK_N x 64) bf16 tiles,
+//              128-byte swizzle, into a 4-stage shared-memory ring (full/empty mbarriers)
+//   warp 1     MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BLOCK_N,
+//              K = 16) four times per stage, tcgen05.commit releases the stage / signals the epilogue
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per call) -> bias, bf16 rounding, LeakyReLU or
+//              positional-embedding add -> global
+#include "fl_common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int BM = 128, BK = 64, STAGES = 4, GEMM_THREADS = 192;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* b, unsigned n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(n) : "memory"); }
+__device__ __forceinline__ void mb_expect_tx(uint64_t* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* b, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nFLG_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FLG_DONE;\nbra FLG_WAIT;\nFLG_DONE:\n}\n" ::"r"(s_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(s_u32(smem)), "l"(map), "r"(s_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
+}
+// shared-memory matrix descriptor (sm_100): K-major tile of 64 bf16 (= one 128-byte swizzle atom) per row,
+// rows densely packed, 8-row groups 1024 bytes apart (SBO), version 1, SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc(const void* smem) {
+    uint64_t d = 0;
+    d |= (uint64_t)((s_u32(smem) & 0x3ffff) >> 4);           // start address  [0,14)
+    d |= (uint64_t)0 << 16;                                    // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                          // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                                    // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                                    // layout type: SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+        "%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct Epilogue {
+    const float* bias;        // [N] fp32 (already rounded to bf16 values, as autocast casts the bias)
+    int leaky;                // 1: LeakyReLU(0.01) on the bf16-rounded value, store bf16
+    void* out;                // leaky ? bf16 [M,N] : fp32 [M,N]
+    const float* x_emb;       // optional positional tables [*, N] fp32 (NULL: none)
+    const float* y_emb;
+    const float* t_emb;
+    const long long* pos_ids; // [M,3] int64
+    int max_x, max_y, max_t;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K, Epilogue ep) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    unsigned char* sa = smem;                                   // [STAGES][128 x 64 bf16], 1024-byte aligned tiles
+    unsigned char* sb = smem + STAGES * A_BYTES;                // [STAGES][BN x 64 bf16]
+    uint64_t* full = (uint64_t*)(smem + STAGES * (A_BYTES + B_BYTES));
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, kblocks = K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
+        mb_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 2) {   // TMEM allocation: BN fp32 accumulator columns (power of two >= 32), by one warp
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                        // ===== TMA producer =====
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES, round = kb / STAGES;
+                mb_wait(&empty[s], (round & 1) ^ 1);            // slot free (first round passes immediately)
+                mb_expect_tx(&full[s], A_BYTES + B_BYTES);
+                tma_load_2d(sa + s * A_BYTES, &map_a, &full[s], kb * BK, m0);
+                tma_load_2d(sb + s * B_BYTES, &map_b, &full[s], kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                        // ===== MMA issuer =====
+            const uint32_t idesc = umma_idesc(BN);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES, round = kb / STAGES;
+                mb_wait(&full[s], round & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t da = umma_desc(sa + s * A_BYTES), db = umma_desc(sb + s * B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)               // 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the address field
+                    umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                umma_commit(&empty[s]);                         // frees the stage once these MMAs have read it
+            }
+            umma_commit(tmem_full);                             // accumulator complete
+        }
+    } else {                                                    // ===== epilogue warps 2..5 =====
+        mb_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        const int row = m0 + q * 32 + lane;
+        long long p0 = 0, p1 = 0, p2 = 0;
+        if (ep.pos_ids && row < M) {
+            p0 = ep.pos_ids[3 * (size_t)row]; p1 = ep.pos_ids[3 * (size_t)row + 1]; p2 = ep.pos_ids[3 * (size_t)row + 2];
+            p0 = p0 < 0 ? 0 : (p0 >= ep.max_x ? ep.max_x - 1 : p0);
+            p1 = p1 < 0 ? 0 : (p1 >= ep.max_y ? ep.max_y - 1 : p1);
+            p2 = p2 < 0 ? 0 : (p2 >= ep.max_t ? ep.max_t - 1 : p2);
+        }
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (row < M) {
+                const int col = n0 + c;
+                if (ep.leaky) {
+                    __nv_bfloat16* o = (__nv_bfloat16*)ep.out + (size_t)row * N + col;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        __align__(16) __nv_bfloat16 t[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float x = __bfloat162float(__float2bfloat16_rn(v[i + j] + __ldg(ep.bias + col + i + j)));
+                            t[j] = __float2bfloat16_rn(x > 0.f ? x : 0.01f * x);
+                        }
+                        *(uint4*)(o + i) = *(const uint4*)t;
+                    }
+                } else {
+                    float* o = (float*)ep.out + (size_t)row * N + col;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float r4[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float x = __bfloat162float(__float2bfloat16_rn(v[i + j] + __ldg(ep.bias + col + i + j)));
+                            if (ep.pos_ids) {
+                                const int cc = col + i + j;
+                                x += (__ldg(ep.x_emb + (size_t)p0 * N + cc) + __ldg(ep.y_emb + (size_t)p1 * N + cc)) +
+                                     __ldg(ep.t_emb + (size_t)p2 * N + cc);
+                            }
+                            r4[j] = x;
+                        }
+                        *(float4*)(o + i) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+}
+
+__global__ void k_cast_bf16(const float4* __restrict__ in, uint2* __restrict__ out, long n4) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = fl_ldg_stream4(in + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    out[i] = make_uint2(*(unsigned*)&a, *(unsigned*)&b);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_map(CUtensorMap* map, const void* base, int rows, int cols, int box_rows) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        FL_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        FL_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, FL_E_ARG, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = (EncodeTiledFn)fn;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};          // innermost first
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};                       // bytes between rows
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FL_REQUIRE(r == CUDA_SUCCESS, FL_E_ARG, "cuTensorMapEncodeTiled failed (%d) for a %d x %d bf16 matrix", (int)r, rows, cols);
+    return FL_OK;
+}
+
+template <int BN>
+int launch_gemm(const void* A, const void* B, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
+    CUtensorMap ma, mb;
+    int rc = make_map(&ma, A, M, K, BM);
+    if (rc) return rc;
+    rc = make_map(&mb, B, N, K, BN);
+    if (rc) return rc;
+    const size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16;
+    static bool attr = false;
+    if (!attr) {
+        FL_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid((M + BM - 1) / BM, N / BN);
+    k_gemm_tcgen05<BN><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, M, N, K, ep);
+    FL_LAUNCH_CHECK();
+    return FL_OK;
+}
+
+}  // namespace
+
+extern "C" int fl_cast_bf16(const float* d_in, void* d_out_bf16, long n, void* stream) {
+    FL_REQUIRE(d_in && d_out_bf16 && n > 0 && n % 4 == 0, FL_E_ARG, "fl_cast_bf16: need non-null buffers and n %% 4 == 0");
+    FL_REQUIRE(((uintptr_t)d_in % 16 == 0) && ((uintptr_t)d_out_bf16 % 8 == 0), FL_E_ALIGN, "fl_cast_bf16: unaligned buffer");
+    long n4 = n / 4;
+    k_cast_bf16<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_in, (uint2*)d_out_bf16, n4);
+    FL_LAUNCH_CHECK();
+    return FL_OK;
+}
+
+extern "C" int fl_patch_embed(const void* d_x_bf16, const void* d_w1_bf16, const float* d_b1, const void* d_w2_bf16,
+                              const float* d_b2, const float* d_x_emb, const float* d_y_emb, const float* d_t_emb,
+                              const long long* d_pos_ids, int max_x, int max_y, int max_t, void* d_hidden_bf16, float* d_out,
+                              int n_tokens, int in_dim, int hid_dim, int out_dim, void* stream) {
+    FL_REQUIRE(d_x_bf16 && d_w1_bf16 && d_b1 && d_w2_bf16 && d_b2 && d_hidden_bf16 && d_out, FL_E_ARG, "fl_patch_embed: null pointer");
+    FL_REQUIRE(n_tokens > 0 && in_dim % BK == 0 && hid_dim % BK == 0 && hid_dim % 256 == 0 && out_dim % 256 == 0, FL_E_ARG,
+               "fl_patch_embed: dims (%d -> %d -> %d) must be multiples of 64 (K) and 256 (N)", in_dim, hid_dim, out_dim);
+    FL_REQUIRE((d_pos_ids == nullptr) || (d_x_emb && d_y_emb && d_t_emb && max_x > 0 && max_y > 0 && max_t > 0), FL_E_ARG,
+               "fl_patch_embed: position ids given without embedding tables");
+    FL_REQUIRE(((uintptr_t)d_x_bf16 | (uintptr_t)d_w1_bf16 | (uintptr_t)d_w2_bf16 | (uintptr_t)d_hidden_bf16 | (uintptr_t)d_out) % 16 == 0,
+               FL_E_ALIGN, "fl_patch_embed: buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    Epilogue e1{d_b1, 1, d_hidden_bf16, nullptr, nullptr, nullptr, nullptr, 0, 0, 0};
+    int rc = launch_gemm<256>(d_x_bf16, d_w1_bf16, n_tokens, hid_dim, in_dim, e1, st);
+    if (rc) return rc;
+    Epilogue e2{d_b2, 0, d_out, d_x_emb, d_y_emb, d_t_emb, d_pos_ids, max_x, max_y, max_t};
+    return launch_gemm<256>(d_hidden_bf16, d_w2_bf16, n_tokens, out_dim, hid_dim, e2, st);
+}

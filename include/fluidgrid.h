@@ -151,6 +151,20 @@ int fl_ds_stats(const float* d_states, const uint8_t* d_mask, int T, int L, int 
 /* fixed-order Chan merge of n_parts aggregates (each f64[18]) -> d_out f64[18] */
 int fl_stats_merge(const double* d_parts, int n_parts, double* d_out, void* stream);
 
+/* ---- patch embedding on the tensor cores (tcgen05) ------------------------------------------------
+ * src/models/layers/patch_encoder.py:23-30 + MLP.py:48-54 + input_embeddings.py:36-52 as run under bf16 autocast:
+ *   h = LeakyReLU_0.01(bf16(x @ W1^T + b1));  out = bf16(h @ W2^T + b2) + x_emb[p0] + y_emb[p1] + t_emb[p2]  (fp32)
+ * d_x_bf16 [n_tokens, in_dim] bf16 (fl_cast_bf16 of the patchified states: a token is one patch, c*256+i*16+j),
+ * d_w1_bf16 [hid_dim, in_dim], d_w2_bf16 [out_dim, hid_dim] bf16 (nn.Linear layout), biases fp32,
+ * embedding tables fp32 [max_*, out_dim], d_pos_ids int64 [n_tokens, 3] (NULL: no positional add),
+ * d_hidden_bf16 [n_tokens, hid_dim] workspace, d_out fp32 [n_tokens, out_dim].
+ * in_dim, hid_dim multiples of 64; hid_dim, out_dim multiples of 256. */
+int fl_cast_bf16(const float* d_in, void* d_out_bf16, long n, void* stream);
+int fl_patch_embed(const void* d_x_bf16, const void* d_w1_bf16, const float* d_b1, const void* d_w2_bf16, const float* d_b2,
+                   const float* d_x_emb, const float* d_y_emb, const float* d_t_emb, const long long* d_pos_ids,
+                   int max_x, int max_y, int max_t, void* d_hidden_bf16, float* d_out,
+                   int n_tokens, int in_dim, int hid_dim, int out_dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,60 @@
+"""-m gpu: the tcgen05 patch-embedding GEMMs against PyTorch's own bf16-autocast evaluation of the reference
+layers (src/models/layers/patch_encoder.py, MLP.py, input_embeddings.py, positional_embeddings.py)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _reference(x, w1, b1, w2, b2, tabs, ids):
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        h = F.leaky_relu(F.linear(x, w1, b1), 0.01)          # MLP.py:48-54, nn.LeakyReLU() default slope
+        y = F.linear(h, w2, b2)
+    if tabs is None:
+        return y.float()
+    xe, ye, te = tabs
+    return y + (xe[ids[..., 0]] + ye[ids[..., 1]] + te[ids[..., 2]])   # positional_embeddings.py:32-37
+
+
+@pytest.mark.parametrize("n_tokens", [128, 4800, 1000])
+def test_patch_embed_matches_autocast_reference(n_tokens):
+    from fluid_llm_b200.patch_embed import PatchEmbedder
+    g = torch.Generator(device="cuda").manual_seed(n_tokens)
+    x = torch.randn(n_tokens, 3, 16, 16, device="cuda", generator=g)
+    w1 = torch.randn(512, 768, device="cuda", generator=g) * 768 ** -0.5
+    b1 = torch.randn(512, device="cuda", generator=g) * 0.1
+    w2 = torch.randn(768, 512, device="cuda", generator=g) * 512 ** -0.5
+    b2 = torch.randn(768, device="cuda", generator=g) * 0.1
+    tabs = [torch.randn(m, 768, device="cuda", generator=g) * 768 ** -0.5 for m in (20, 10, 30)]
+    ids = torch.stack([torch.randint(0, m, (n_tokens,), device="cuda", generator=g) for m in (20, 10, 30)], dim=1)
+    emb = PatchEmbedder(w1, b1, w2, b2, *tabs)
+    out = emb(x, ids)
+    ref = _reference(x.reshape(n_tokens, -1), w1, b1, w2, b2, tabs, ids)
+    assert out.shape == (n_tokens, 768) and out.dtype == torch.float32
+    # both sides round h and y to bf16 (8 mantissa bits); fp32 accumulation order differs -> at most a few bf16 ulps
+    torch.testing.assert_close(out, ref, rtol=2e-2, atol=2e-2)
+    assert float((out - ref).abs().mean()) < 2e-3
+    # exact-arithmetic check of the same bf16-rounded operands (catches layout / swizzle bugs a loose tolerance hides)
+    xb, w1b, w2b = x.reshape(n_tokens, -1).bfloat16().double(), w1.bfloat16().double(), w2.bfloat16().double()
+    h = (xb @ w1b.T + b1.bfloat16().double()).float().bfloat16().float()
+    h = torch.where(h > 0, h, 0.01 * h).bfloat16().double()
+    y = (h @ w2b.T + b2.bfloat16().double()).float().bfloat16().float()
+    exact = y + (tabs[0][ids[:, 0]] + tabs[1][ids[:, 1]] + tabs[2][ids[:, 2]])
+    assert float((out - exact).abs().max()) < 6e-2 and float(((out - exact).abs() > 1e-6).float().mean()) < 0.05
+
+
+def test_patch_embed_shapes_and_errors():
+    from fluid_llm_b200.patch_embed import PatchEmbedder
+    w1, b1, w2, b2 = torch.randn(512, 768), torch.zeros(512), torch.randn(768, 512), torch.zeros(768)
+    emb = PatchEmbedder(w1, b1, w2, b2)
+    x = torch.randn(2, 3, 60, 3, 16, 16, device="cuda")
+    out = emb(x)
+    assert out.shape == (2, 3, 60, 768)
+    ref = _reference(x.reshape(-1, 768), w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), None, None).view(2, 3, 60, 768)
+    torch.testing.assert_close(out, ref, rtol=2e-2, atol=2e-2)
+    with pytest.raises(ValueError):
+        emb(x, torch.zeros(2, 3, 60, 3, dtype=torch.int64, device="cuda"))      # no tables
+    with pytest.raises(ValueError):
+        PatchEmbedder(w1, b1, torch.randn(768, 256), b2)
