@@ -10,7 +10,7 @@
 //
 // Kernel anatomy (one 128 x BLOCK_N output tile per CTA, 192 threads):
 //   warp 0     TMA producer: cp.async.bulk.tensor.2d of the A (128 x 64) and B (BLOCK_N x 64) bf16 tiles,
-//              128-byte swizzle, into a 4-stage shared-memory ring (full/empty mbarriers)
+//              128-byte swizzle, into a 2-stage shared-memory ring (two CTAs per SM) (full/empty mbarriers)
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BLOCK_N,
 //              K = 16) four times per stage, tcgen05.commit releases the stage / signals the epilogue
 //   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per call) -> bias, bf16 rounding, LeakyReLU or
@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 4, GEMM_THREADS = 192;
+constexpr int BM = 128, BK = 64, STAGES = 2, GEMM_THREADS = 192;   // 2 stages = 96 KB: two CTAs per SM, one runs its epilogue while the other feeds the tensor core
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(uint64_t* b, unsigned n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(n) : "memory"); }
@@ -88,7 +88,7 @@ struct Epilogue {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K, Epilogue ep) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
@@ -146,48 +146,54 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mb_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-        const int row = m0 + q * 32 + lane;
-        long long p0 = 0, p1 = 0, p2 = 0;
-        if (ep.pos_ids && row < M) {
-            p0 = ep.pos_ids[3 * (size_t)row]; p1 = ep.pos_ids[3 * (size_t)row + 1]; p2 = ep.pos_ids[3 * (size_t)row + 2];
-            p0 = p0 < 0 ? 0 : (p0 >= ep.max_x ? ep.max_x - 1 : p0);
-            p1 = p1 < 0 ? 0 : (p1 >= ep.max_y ? ep.max_y - 1 : p1);
-            p2 = p2 < 0 ? 0 : (p2 >= ep.max_t ? ep.max_t - 1 : p2);
+        // The accumulator arrives one ROW per lane (32 columns per tcgen05.ld).  Written out like that, every
+        // store instruction would touch 32 different rows; instead each 32 x 32 block goes through a per-warp,
+        // XOR-swizzled shared tile (the operand ring is free once tmem_full has fired) and leaves with 8 lanes
+        // per row: 128-bit accesses, 4 full rows per instruction, bias / activation / positional add applied there.
+        float4* tile = (float4*)(smem + q * 4096);              // [32 rows][8 float4], index r*8 + (c4 ^ (r & 7))
+        long long* s_pos = (long long*)(smem + 16384 + q * 768);   // [32 rows][3] clamped position ids
+        if (ep.pos_ids) {
+            const int row = m0 + q * 32 + lane;
+            long long p0 = 0, p1 = 0, p2 = 0;
+            if (row < M) {
+                p0 = ep.pos_ids[3 * (size_t)row]; p1 = ep.pos_ids[3 * (size_t)row + 1]; p2 = ep.pos_ids[3 * (size_t)row + 2];
+                p0 = p0 < 0 ? 0 : (p0 >= ep.max_x ? ep.max_x - 1 : p0);
+                p1 = p1 < 0 ? 0 : (p1 >= ep.max_y ? ep.max_y - 1 : p1);
+                p2 = p2 < 0 ? 0 : (p2 >= ep.max_t ? ep.max_t - 1 : p2);
+            }
+            s_pos[3 * lane] = p0; s_pos[3 * lane + 1] = p1; s_pos[3 * lane + 2] = p2;
         }
+        const int c4 = lane & 7, rsub = lane >> 3;              // after the transpose: this lane's float4 column and row phase
         for (int c = 0; c < BN; c += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            if (row < M) {
-                const int col = n0 + c;
+            __syncwarp();                                       // the previous block has been read out of the tile
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tile[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+            const int col = n0 + c + 4 * c4;
+            const float4 b4 = __ldg((const float4*)(ep.bias + col));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + rsub, row = m0 + q * 32 + r;
+                const float4 a = tile[r * 8 + (c4 ^ (r & 7))];
+                if (row >= M) continue;
+                float x[4] = {a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = __bfloat162float(__float2bfloat16_rn(x[j]));      // the Linear's bf16 output
                 if (ep.leaky) {
-                    __nv_bfloat16* o = (__nv_bfloat16*)ep.out + (size_t)row * N + col;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
-                        __align__(16) __nv_bfloat16 t[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float x = __bfloat162float(__float2bfloat16_rn(v[i + j] + __ldg(ep.bias + col + i + j)));
-                            t[j] = __float2bfloat16_rn(x > 0.f ? x : 0.01f * x);
-                        }
-                        *(uint4*)(o + i) = *(const uint4*)t;
-                    }
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(x[0] > 0.f ? x[0] : 0.01f * x[0], x[1] > 0.f ? x[1] : 0.01f * x[1]);
+                    __nv_bfloat162 hi = __floats2bfloat162_rn(x[2] > 0.f ? x[2] : 0.01f * x[2], x[3] > 0.f ? x[3] : 0.01f * x[3]);
+                    *(uint2*)((__nv_bfloat16*)ep.out + (size_t)row * N + col) = make_uint2(*(unsigned*)&lo, *(unsigned*)&hi);
                 } else {
-                    float* o = (float*)ep.out + (size_t)row * N + col;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        float r4[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float x = __bfloat162float(__float2bfloat16_rn(v[i + j] + __ldg(ep.bias + col + i + j)));
-                            if (ep.pos_ids) {
-                                const int cc = col + i + j;
-                                x += (__ldg(ep.x_emb + (size_t)p0 * N + cc) + __ldg(ep.y_emb + (size_t)p1 * N + cc)) +
-                                     __ldg(ep.t_emb + (size_t)p2 * N + cc);
-                            }
-                            r4[j] = x;
-                        }
-                        *(float4*)(o + i) = make_float4(r4[0], r4[1], r4[2], r4[3]);
+                    if (ep.pos_ids) {
+                        const float4 e0 = __ldg((const float4*)(ep.x_emb + (size_t)s_pos[3 * r] * N + col));
+                        const float4 e1 = __ldg((const float4*)(ep.y_emb + (size_t)s_pos[3 * r + 1] * N + col));
+                        const float4 e2 = __ldg((const float4*)(ep.t_emb + (size_t)s_pos[3 * r + 2] * N + col));
+                        x[0] += (e0.x + e1.x) + e2.x; x[1] += (e0.y + e1.y) + e2.y;
+                        x[2] += (e0.z + e1.z) + e2.z; x[3] += (e0.w + e1.w) + e2.w;
                     }
+                    fl_stg_stream4((float4*)((float*)ep.out + (size_t)row * N + col), make_float4(x[0], x[1], x[2], x[3]));
                 }
             }
         }

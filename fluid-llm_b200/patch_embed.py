@@ -50,7 +50,7 @@ class PatchEmbedder:
         """x (..., N_patch, 3, H, W) fp32 CUDA, position_ids (..., N_patch, 3) int64 -> (..., N_patch, llm_dim) fp32."""
         if not x.is_cuda:
             raise _lib.FluidGridError("PatchEmbedder: x must be a CUDA tensor")
-        lead = x.shape[:-3]
+        lead = x.shape[:-1] if x.shape[-1] == self.in_dim else x.shape[:-3]     # already-flattened patches are accepted too
         xf = x.reshape(-1, self.in_dim)                 # patch_encoder.py:25: flatten (C, H, W) -> c*H*W + i*W + j
         if xf.shape[1] != self.in_dim:
             raise ValueError(f"PatchEmbedder: patches flatten to {xf.shape[1]} values, weights expect {self.in_dim}")
