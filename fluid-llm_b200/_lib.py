@@ -41,6 +41,8 @@ SIGNATURES = {
     "fl_interp_patchify_dev": (c_int, [c_void_p, POINTER(FlTraj), c_int, c_int, c_int, c_int, POINTER(c_float),
                                        POINTER(c_float), c_uint, c_void_p]),
     "fl_to_grid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "fl_interp_frames": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_int, POINTER(c_float), POINTER(c_float), c_uint, c_void_p, c_void_p, c_void_p]),
     "fl_patch_to_img": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fl_img_to_patch": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fl_rollout_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -462,6 +462,57 @@ extern "C" int fl_interp_patchify(const FlTraj* h_trajs, int n_traj, int n_patch
     return rc;
 }
 
+// eagle/Dataloader/IMG_MGN.py:78-157 (DilResNet image loader): per frame three to_grid calls, optional crop of
+// `crop` pixels per side, (v - mean) / std on EVERY pixel, frames stored channel-last [T][H][W][3].
+__global__ void k_interp_frames(const FlCellIdx* __restrict__ idx, const FlCellW* __restrict__ wt, int nx, int ny, int crop,
+                                const float* __restrict__ vel, const float* __restrict__ prs, int vel_stride, int prs_stride,
+                                int t0, int interval, int n_frames, NormConst nc, int no_norm, float* __restrict__ states,
+                                uint8_t* __restrict__ mask) {
+    const int H = nx - 2 * crop, W = ny - 2 * crop;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= H * W) return;
+    const int ix = p / W + crop, iy = p % W + crop;
+    const FlCellIdx id = idx[ix * ny + iy];
+    const FlCellW w = wt[ix * ny + iy];
+    const double w0 = 1.0 - w.w1 - w.w2;
+    for (int f = blockIdx.y; f < n_frames; f += gridDim.y) {
+        const size_t t = (size_t)t0 + (size_t)f * interval;
+        float v[3] = {0.f, 0.f, 0.f};
+        bool masked = id.tri < 0;
+        if (!masked) {
+            interp3(vel + t * vel_stride, prs + t * prs_stride, id, w0, w.w1, w.w2, v);
+            masked = !finite_f(v[2]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) if (!finite_f(v[c])) v[c] = 0.f;
+        }
+        float* dst = states + ((size_t)f * H * W + p) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dst[c] = no_norm ? v[c] : __fdiv_rn(__fsub_rn(v[c], nc.mean[c]), nc.stdv[c]);
+        if (mask) mask[(size_t)f * H * W + p] = masked ? 1 : 0;
+    }
+}
+
+extern "C" int fl_interp_frames(const FlCellIdx* d_cell_idx, const FlCellW* d_cell_w, int nx, int ny, int crop,
+                                const float* d_velocity, const float* d_pressure, int n_nodes, int vel_stride, int prs_stride,
+                                int t0, int interval, int n_frames, const float* h_mean, const float* h_std, unsigned flags,
+                                float* d_states, uint8_t* d_mask, void* stream) {
+    FL_REQUIRE(d_cell_idx && d_cell_w && d_velocity && d_pressure && d_states, FL_E_ARG, "fl_interp_frames: null pointer");
+    FL_REQUIRE(nx > 0 && ny > 0 && crop >= 0 && nx > 2 * crop && ny > 2 * crop && n_frames > 0 && t0 >= 0 && interval > 0 && n_nodes > 0,
+               FL_E_ARG, "fl_interp_frames: bad sizes");
+    FL_REQUIRE(vel_stride >= 2 * n_nodes && prs_stride >= n_nodes && vel_stride % 2 == 0 && (uintptr_t)d_velocity % 8 == 0, FL_E_ARG,
+               "fl_interp_frames: bad frame strides / alignment");
+    FL_REQUIRE((h_mean && h_std) || (flags & FL_NO_NORM), FL_E_ARG, "fl_interp_frames: mean/std missing");
+    NormConst nc;
+    for (int c = 0; c < 3; ++c) { nc.mean[c] = h_mean ? h_mean[c] : 0.f; nc.stdv[c] = h_std ? h_std[c] : 1.f; }
+    const int HW = (nx - 2 * crop) * (ny - 2 * crop);
+    dim3 grid((HW + 255) / 256, n_frames < 64 ? n_frames : 64);
+    k_interp_frames<<<grid, 256, 0, (cudaStream_t)stream>>>(d_cell_idx, d_cell_w, nx, ny, crop, d_velocity, d_pressure, vel_stride,
+                                                          prs_stride, t0, interval, n_frames, nc, (flags & FL_NO_NORM) ? 1 : 0, d_states,
+                                                          d_mask);
+    FL_LAUNCH_CHECK();
+    return FL_OK;
+}
+
 extern "C" int fl_to_grid(const FlCellIdx* d_cell_idx, const FlCellW* d_cell_w, int nx, int ny, const float* d_val,
                           int n_fields, int n_nodes, float* d_data, uint8_t* d_mask, void* stream) {
     FL_REQUIRE(d_cell_idx && d_cell_w && d_val && d_data, FL_E_ARG, "fl_to_grid: null pointer");

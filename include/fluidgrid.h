@@ -120,6 +120,15 @@ int fl_interp_patchify_dev(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_t
 int fl_to_grid(const FlCellIdx* d_cell_idx, const FlCellW* d_cell_w, int nx, int ny,
                const float* d_val, int n_fields, int n_nodes, float* d_data, uint8_t* d_mask, void* stream);
 
+/* Channel-last frame variant without pad/patchify: replaces eagle/Dataloader/IMG_MGN.py:78-157 (_get_step x T +
+ * normalize + permute).  Frames t0, t0+interval, ...; `crop` pixels removed per side (IMG_MGN.py:91-95);
+ * every pixel normalised (masked ones become (0 - mean) / std).  d_states f32 [n_frames, nx-2c, ny-2c, 3],
+ * d_mask u8 [n_frames, nx-2c, ny-2c] (NULL to skip). */
+int fl_interp_frames(const FlCellIdx* d_cell_idx, const FlCellW* d_cell_w, int nx, int ny, int crop,
+                     const float* d_velocity, const float* d_pressure, int n_nodes, int vel_stride, int prs_stride,
+                     int t0, int interval, int n_frames, const float* h_mean, const float* h_std, unsigned flags,
+                     float* d_states, uint8_t* d_mask, void* stream);
+
 /* ---- inverse path --------------------------------------------------------------------------- */
 /* src/utils_model.py:77-92 patch_to_img: patches [B, L, C, px, py] -> img [B, C, n_bx*px, n_by*py].
  * elem_size 2 or 4 (bf16/fp16 or fp32; pure permutation). */

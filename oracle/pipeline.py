@@ -5,7 +5,7 @@ Every function cites the reference lines it follows.  The matplotlib C++ arithme
 restated in oracle/tri_oracle.cpp (front: oracle/mpl_tri.py).
 
 PARITY STATUS.  The reference holds no golden vectors for this path (it has no tests).  This
-restatement is pinned the only way available here: tests/test_oracle_vs_reference.py imports
+restatement is pinned the only way available here: tests/test_oracle.py (test_oracle_vs_reference_*_live) imports
 the reference's UNMODIFIED Python from /root/reference behind stub modules for the three
 packages that are not installed (oracle/stubs: matplotlib -> oracle/mpl_tri.py, cprint,
 natsort) and compares every stage bit-for-bit; oracle/make_golden.py freezes those outputs in
@@ -235,6 +235,31 @@ def ds_get(traj, step_num, seq_len, seq_interval=1, resolution=238, patch_size=(
     if return_all:
         return out, dict(states=states, masks=masks, tri_index=tri_index, N_x_patch=nxp, N_y_patch=nyp)
     return out
+
+
+def img_mgn_item(traj, t, window_length, kind, numpy_semantics="1.26"):
+    """eagle/Dataloader/IMG_MGN.py:46-128,141-157 -> states float32 (T, H, W, 3) normalised, mask bool (T, H, W)."""
+    pos, faces, vel, prs = traj["mesh_pos"], traj["cells"], traj["velocity"], traj["pressure"]
+    if kind == "airfoil":
+        nmask, pos, faces = airfoil_crop(pos, faces)
+        vel, prs = vel[:, nmask], prs[:, nmask]
+    triang, tri_index, gx, gy = get_mesh_interpolation(pos, faces, 238, numpy_semantics)
+    states, masks = [], []
+    for i in range(t, t + window_length):
+        st, m = get_step(triang, tri_index, gx, gy, vel, prs, i, None, pad=False)
+        if kind == "airfoil":
+            st, m = st[:, 16:-16, 16:-16], m[16:-16, 16:-16]
+        states.append(st)
+        masks.append(m)
+    states = np.stack(states).astype(F32)
+    if kind == "airfoil":
+        means, stds = (170.1, -1.183, 9.935e+04), (71.06, 46.73, 8964)
+    else:
+        means, stds = (0.823, 0.0005865, 0.04763), (0.275, 0.275, 0.275)
+    m = np.asarray(means, dtype=F32).reshape(1, 3, 1, 1)
+    s = np.asarray(stds, dtype=F32).reshape(1, 3, 1, 1)
+    states = ((states - m).astype(F32) / s).astype(F32)
+    return np.ascontiguousarray(states.transpose(0, 2, 3, 1)), np.stack(masks)
 
 
 # --------------------------------------------------------------------------------------------

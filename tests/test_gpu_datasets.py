@@ -138,3 +138,23 @@ def test_full_size_properties_cylinder():
     # staged and gather kernels agree bit for bit at full size
     norm2, _, _ = interp_patchify(dt, 0, 600, 1, PATCH, CYLINDER, force_gather=True)
     assert torch.equal(norm, norm2)
+
+
+@pytest.mark.parametrize("kind", ["cylinder", "airfoil"])
+def test_img_mgn_dataset_matches_oracle(kind, tmp_path):
+    """The DilResNet image loader (eagle/Dataloader/IMG_MGN.py): channel-last frames, all-pixel normalise, airfoil crop."""
+    from fluid_llm_b200.img_mgn import EagleDataset
+    root = tmp_path / f"{kind}_dataset" / "test"
+    root.mkdir(parents=True)
+    trajs = [trajectory(kind, 140, s, 10 + s) for s in (0, 1)]
+    _write(root, copy.deepcopy(trajs))
+    ds = EagleDataset(str(tmp_path / f"{kind}_dataset"), mode="test", window_length=6)
+    assert len(ds) == 2
+    item = ds[1]
+    want_s, want_m = P.img_mgn_item(trajs[1], 100, 6, kind)
+    assert item["states"].dtype == torch.float32 and item["mask"].dtype == bool
+    assert np.array_equal(item["mask"], want_m)
+    np.testing.assert_allclose(item["states"].numpy(), want_s, rtol=1e-6, atol=0)
+    assert np.array_equal(item["states"].numpy(), want_s)
+    back = ds.denormalize(item["states"])
+    assert back.shape == item["states"].shape
