@@ -37,6 +37,8 @@ WORKLOADS = {
     "airfoil": dict(kind="airfoil", personality="airfoil", n_traj=16, T=600),
     "cylinder": dict(kind="cylinder", personality="cylinder", n_traj=24, T=600),
     "eagle": dict(kind="eagle", personality="cylinder", n_traj=12, T=990),
+    # BASELINE config 5: ~1M-triangle mesh, grid_res 2048 (2048 x 1024 cells, 8192 patches), T = 64
+    "big": dict(kind="big", personality="cylinder", n_traj=4, T=64, res=2048, n_meshes=1),
 }
 N_MESHES = 4   # distinct meshes per GPU (trajectories cycle through them)
 
@@ -98,7 +100,7 @@ def make_inputs(w, rank):
     from fluid_llm_b200 import synth
     from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
     meshes = []
-    for m in range(N_MESHES):
+    for m in range(w.get("n_meshes", N_MESHES)):
         pos, cells = synth.make_mesh(w["kind"], seed=100 * rank + m)
         sel = None
         if w["personality"] == "airfoil":
@@ -106,7 +108,7 @@ def make_inputs(w, rank):
         meshes.append((pos, cells, sel))
     trajs = []
     for i in range(w["n_traj"]):
-        pos, cells, sel = meshes[i % N_MESHES]
+        pos, cells, sel = meshes[i % len(meshes)]
         n_full = len(sel) if sel is not None else len(pos)
         full_pos = np.zeros((n_full, 2), np.float32)
         if sel is not None:
@@ -116,7 +118,7 @@ def make_inputs(w, rank):
         vel, prs = synth.make_fields(w["kind"], full_pos, w["T"], seed=1000 * rank + i)
         if sel is not None:
             vel, prs = np.ascontiguousarray(vel[:, sel]), np.ascontiguousarray(prs[:, sel])
-        trajs.append((i % N_MESHES, vel, prs))
+        trajs.append((i % len(meshes), vel, prs))
     return meshes, trajs
 
 
@@ -126,7 +128,7 @@ def cpu_frames_per_s(w, meshes, trajs, budget_s, n_frames_cap=None):
     from oracle import pipeline as P
     mi, vel, prs = trajs[0]
     pos, cells, _ = meshes[mi]
-    triang, tri_index, gx, gy = P.get_mesh_interpolation(pos, cells, RES)
+    triang, tri_index, gx, gy = P.get_mesh_interpolation(pos, cells, w.get("res", RES))
     done, t0 = 0, time.perf_counter()
     cap = n_frames_cap or w["T"]
     while done < cap:
@@ -209,7 +211,7 @@ def run_ours(args, w):
     pers = AIRFOIL if w["personality"] == "airfoil" else CYLINDER
 
     meshes, trajs = make_inputs(w, rank)
-    plans = [MeshPlan(pos, cells, RES, device=dev) for (pos, cells, _) in meshes]
+    plans = [MeshPlan(pos, cells, w.get("res", RES), device=dev) for (pos, cells, _) in meshes]
     tables = [p.patch_table(PATCH, pers.crop_patches, pers.flip_y) for p in plans]
     dtrajs = [DeviceTrajectory(vel, prs, plans[mi]) for (mi, vel, prs) in trajs]
     batch = TrajBatch(dtrajs, [tables[mi] for (mi, _, _) in trajs], [0] * len(trajs), 1, w["T"], want_mask=True)
@@ -220,7 +222,7 @@ def run_ours(args, w):
     # algorithmic bytes: read u,v,p once (12 N), write 3-channel fp32 patches once (12 P)
     # [+ the u8 mask this run also writes is NOT counted]; static table 32 B per output pixel per mesh
     bytes_frames = sum(w["T"] * (12 * n + 12 * P_px) for n in n_nodes)
-    bytes_static = N_MESHES * 32 * P_px
+    bytes_static = len(meshes) * 32 * P_px
     algo_bytes = bytes_frames + bytes_static
 
     def step():
@@ -305,7 +307,7 @@ def run_ours(args, w):
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64->f32", "data": "synthetic",
                 "config": {"workload": f"{args.workload}-shaped: {len(trajs)} trajectories/GPU x T={w['T']} frames, "
-                                       f"{N_MESHES} meshes/GPU of ~{int(np.mean(n_nodes))} nodes (after the dataset's crop), "
+                                       f"{len(meshes)} meshes/GPU of ~{int(np.mean(n_nodes))} nodes (after the dataset's crop), "
                                        f"grid {plans[0].nx}x{plans[0].ny}, {tab.n_bx}x{tab.n_by} patches of 16x16",
                            "frames_per_step_per_gpu": n_frames_step, "parallelism": f"trajectory-sharded x{world}",
                            "l2_policy": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (algo_bytes / 1e6),

@@ -205,3 +205,24 @@ def test_long_sequence_many_items():
     _, extra = oracle_ds_get("cylinder", 2, 20, 3, T=64, mesh_seed=3, field_seed=7)
     assert np.array_equal(states.cpu().numpy(), extra["states"])
     assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
+
+
+def test_big_mesh_gather_path_matches_oracle():
+    """BASELINE config 5 in miniature: a structured ~80k-triangle mesh on a 512-point grid.  The node arrays do
+    not fit the staged kernel's shared memory, so this exercises the gather-from-global kernel end to end."""
+    from fluid_llm_b200 import synth
+    from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    pos, cells = synth.make_mesh("big", 0, nx=281, ny=141)
+    vel, prs = synth.make_fields("big", pos, 3, 1)
+    plan = MeshPlan(pos, cells, 512)
+    triang, tri_o, gx, gy = P.get_mesh_interpolation(pos, cells, 512)
+    assert (plan.nx, plan.ny) == tri_o.shape == (512, 256)
+    assert np.array_equal(plan.tri_index, tri_o)
+    assert np.array_equal(tri_o, mpl_tri.rule_find_many(triang, gx, gy, bucketed=True))
+    states, mask, tab = interp_patchify(DeviceTrajectory(vel, prs, plan), 0, 3, 1, PATCH, CYLINDER)
+    tr = {"mesh_pos": pos, "cells": cells, "velocity": vel, "pressure": prs}
+    _, extra = P.ds_get(tr, 0, 3, 1, 512, PATCH, "cylinder", return_all=True)
+    assert (tab.n_bx, tab.n_by) == (32, 16)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
+    assert np.array_equal(states.cpu().numpy(), extra["states"])
