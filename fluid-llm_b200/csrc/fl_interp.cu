@@ -100,20 +100,23 @@ __global__ void k_to_grid(const FlCellIdx* __restrict__ idx, const FlCellW* __re
 // ------------------------------------------------------------------------------------------
 // Staged kernel (the fast path).  One persistent 512-thread CTA per SM; a work item is TF
 // consecutive selected frames of one trajectory.
-//   staging   velocity frames are bulk-copied (TMA: cp.async.bulk + mbarrier) into shared memory in
-//             their global layout [node][u,v]; pressure frames are read with coalesced 128-bit loads
-//             and stored as fp64 (one conversion per NODE instead of three per PIXEL), so both
-//             arrays have an 8-byte node stride and one offset register addresses both.
-//   compute   a warp owns 128 consecutive output pixels, lane i handles pixels i, i+32, i+64, i+96,
-//             so each gather instruction covers 32 adjacent pixels.  The four table records of a
-//             thread are read once (coalesced, L2-resident) and reused for all TF frames.
-//   output    128 B per warp store (streaming, no L1 allocate); (frame, patch, channel) blocks of
-//             1 KB are written whole by two warps.
+//   staging   coalesced 128-bit streaming loads of 4 nodes' (u,v) pairs and pressures are written to
+//             shared memory as four 16-byte node records {u f32, v f32, p f64}: pressure is converted
+//             once per NODE instead of three times per PIXEL, and one 128-bit gather fetches a vertex.
+//             Records sit at Morton-ordered slots (d_node_slot); the same pass scans for non-finite /
+//             huge values.  (A TMA bulk-copy staging of the frames in their global layout was measured
+//             slower: twice the gather instructions and three more conversions per pixel.)
+//   compute   a warp owns 128 consecutive output pixels, lane i handles pixels p(i), p(i)+32, +64, +96
+//             (p = a 2 x 4-block permutation inside each 32-pixel group), so every gather instruction
+//             covers 32 adjacent pixels.  The four table records of a thread are read once (coalesced,
+//             L2-resident) and reused for all TF frames.
+//   output    128 B per warp store (streaming, no L1 allocate); each (frame, patch, channel) block of
+//             1 KB is written whole by two warps.
 // HBM traffic: 12 N + 12 P bytes per frame (compulsory); L2 -> SM adds 32 P / TF (table).
 // Arithmetic per pixel-frame: 6 f32->f64 (u, v), 3 DMUL + 6 DFMA, 3 f64->f32, then (v - mean) / std as
 // a reciprocal multiply with one Markstein correction step on the packed fp32 pipe (bit-identical to
 // IEEE division for the ranges checked on the host and in the staging scan; anything else takes the
-// checked path).  The conversion unit (16 lanes/clk/SM) is the binding pipe: see DESIGN.md.
+// checked path).  What bounds it today (profiles/README.md): the L1/shared LSU data pipe at ~80 %.
 // ------------------------------------------------------------------------------------------
 constexpr int ST_THREADS = 512;
 constexpr int NP = 4;        // pixels per thread
@@ -122,29 +125,6 @@ struct StagedConst {
     float mean[3], stdv[3], rcp[3];
     int fast_div;        // 1: Markstein division valid for these constants
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "FL_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra FL_DONE;\n"
-        "bra FL_WAIT;\n"
-        "FL_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 
 // (x - mean) / std, correctly rounded: q = d*r, then one Markstein step with the exact remainder
 __device__ __forceinline__ float norm_fast(float x, float mean, float stdv, float rcp) {
