@@ -174,7 +174,8 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
     // pixel of this lane inside a group of 32 adjacent pixels (2 patch rows x 16): the 8 lanes of a quarter-warp
     // (one LDS.128 wavefront) take a compact 2 x 4 block, which touches fewer distinct nodes than a 1 x 8 strip;
     // any permutation inside the group keeps every warp store one contiguous 128-byte line
-    const int lane = ppx_shift >= 0 && (ppx & 15) == 0 ? ((lane_id >> 2) & 1) * 16 + (lane_id >> 3) * 4 + (lane_id & 3) : lane_id;
+    const bool permuted = ppx_shift >= 0 && (ppx & 15) == 0;
+    const int lane = permuted ? ((lane_id >> 2) & 1) * 16 + (lane_id >> 3) * 4 + (lane_id & 3) : lane_id;
     const FlCellIdx* idx_tab = tr.d_idx_slot ? tr.d_idx_slot : tr.d_idx;   // node ids as shared-memory slots
     const size_t frame_out = (size_t)n_patches * 3 * ppx;
     unsigned long long nm[3], ns[3], rc[3];
@@ -198,9 +199,22 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
             ov[r][1] = out ? 0u : (uint32_t)id.y * 16u;
             ov[r][2] = out ? 0u : (uint32_t)id.z * 16u;
         }
+        // mask bytes of the chunk in pixel order: lane j will store the four bytes of pixels 4j..4j+3 with one 32-bit
+        // store per frame (the mask is static on the unchecked path); pixel 32r+q lives in byte r of lane inv(q)'s mbits
+        unsigned mword = 0;
+        if (!CHECKED && NP == 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int q = 4 * (lane_id & 7) + i;                                  // position inside the 32-pixel group
+                const int src = !permuted ? q : (((q >> 2) & 3) << 3) | (((q >> 4) & 1) << 2) | (q & 3);   // inverse of the lane permutation
+                const unsigned m = __shfl_sync(0xffffffffu, mbits, src);
+                mword |= ((m >> (8 * (lane_id >> 3))) & 1u) << (8 * i);
+            }
+        }
         const int l = ppx_shift >= 0 ? (o >> ppx_shift) : o / ppx, k = o - l * ppx;   // the chunk never straddles a patch
         float* dst = tr.d_states + ((size_t)fbeg * n_patches + l) * 3 * ppx + k;
         uint8_t* mdst = tr.d_mask ? tr.d_mask + ((size_t)fbeg * n_patches + l) * ppx + k : nullptr;
+        unsigned* mdst4 = tr.d_mask ? (unsigned*)(tr.d_mask + ((size_t)fbeg * n_patches + l) * ppx + (k - lane)) + lane_id : nullptr;
         const unsigned char* nb = s_nodes;    // loop-carried uniform base: folds into LDS.128 [R + UR]
 #pragma unroll 1
         for (int f = 0; f < nf; ++f, nb += slot_b) {
@@ -252,9 +266,14 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
                 for (int r = 0; r < NP; ++r) fl_stg_stream1(dst + (size_t)c * ppx + 32 * r, res[c][r]);   // 128 B per warp store
             dst += frame_out;
             if (mdst) {
+                if (!CHECKED && NP == 4) {
+                    *mdst4 = mword;                                   // 128 contiguous bytes per warp
+                    mdst4 += (size_t)n_patches * ppx / 4;
+                } else {
 #pragma unroll
-                for (int r = 0; r < NP; ++r) mdst[32 * r] = (uint8_t)((fm >> (8 * r)) & 1u);
-                mdst += (size_t)n_patches * ppx;
+                    for (int r = 0; r < NP; ++r) mdst[32 * r] = (uint8_t)((fm >> (8 * r)) & 1u);
+                    mdst += (size_t)n_patches * ppx;
+                }
             }
         }
     }
