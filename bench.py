@@ -122,6 +122,13 @@ def make_inputs(w, rank):
     return meshes, trajs
 
 
+def workload_text(name, w, meshes):
+    """Same text for both arms: what one step of the full workload is."""
+    n = int(np.mean([len(m[0]) for m in meshes]))
+    return (f"{name}-shaped (BASELINE.json configs): {WORKLOADS[name]['n_traj']} trajectories/GPU x T={WORKLOADS[name]['T']} frames per step, "
+            f"meshes of ~{n} nodes (after the dataset's crop), grid_res {w.get('res', RES)}, patch 16x16")
+
+
 def cpu_frames_per_s(w, meshes, trajs, budget_s, n_frames_cap=None):
     """The oracle's per-frame path (3x to_grid + pad + unfold + normalise), one thread, trifinder
     built outside the timed loop (the most favourable reading of the reference's CPU path)."""
@@ -181,8 +188,9 @@ def run_reference(args, w):
     value = frames / dt
     line = {"impl": "reference", "metric": "grid-frames/sec (interp+normalise+patchify)", "value": value, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64->f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}-shaped, res {RES}, patch 16x16", "frames_per_step": frames // args.steps},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_text(args.workload, w, meshes),
+                       "sample": f"each step = {per_worker} frames x {cores} worker processes of that workload", "frames_per_step": frames // args.steps},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"{per_worker} frames x {cores} processes per step; trifinder build outside the timed loop"},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -252,7 +260,15 @@ def run_ours(args, w):
     sec = ms / 1e3
     value = world * n_frames_step * args.steps / sec
     peak, peak_src = measured_peak()
-    achieved = algo_bytes * args.steps / sec / 1e9 if world == 1 else None
+    achieved = algo_bytes * args.steps / sec / 1e9       # per GPU: every rank launches the same kernel on its own shard
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("workload") == args.workload:
+            traffic = tj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
 
     # ---- e2e: host buffers in, host buffers out, through the same public API ----------------
     e2e_traj = min(4, len(trajs))
@@ -305,16 +321,15 @@ def run_ours(args, w):
     if rank == 0:
         line = {"metric": "grid-frames/sec (interp+normalise+patchify)", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64->f32", "data": "synthetic",
-                "config": {"workload": f"{args.workload}-shaped: {len(trajs)} trajectories/GPU x T={w['T']} frames, "
-                                       f"{len(meshes)} meshes/GPU of ~{int(np.mean(n_nodes))} nodes (after the dataset's crop), "
-                                       f"grid {plans[0].nx}x{plans[0].ny}, {tab.n_bx}x{tab.n_by} patches of 16x16",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_text(args.workload, w, meshes),
+                           "grid": f"{plans[0].nx}x{plans[0].ny} cells, {tab.n_bx}x{tab.n_by} patches of 16x16",
                            "frames_per_step_per_gpu": n_frames_step, "parallelism": f"trajectory-sharded x{world}",
                            "l2_policy": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (algo_bytes / 1e6),
                            "mesh_seed": "100*rank+m", "field_seed": "1000*rank+i", "stats_check_n": float(agg[0, 0].item())},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": algo_bytes, "kernel": "k_interp_patchify"},
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": algo_bytes, "kernel": "k_interp_patchify_staged", "traffic_source": "ncu --set full, profiles/r1_final_traffic.json" if traffic else None},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": f"{e2e_traj} trajectories/step/GPU, pinned host buffers both ways"},

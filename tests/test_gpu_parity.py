@@ -226,3 +226,24 @@ def test_big_mesh_gather_path_matches_oracle():
     assert (tab.n_bx, tab.n_by) == (32, 16)
     assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
     assert np.array_equal(states.cpu().numpy(), extra["states"])
+
+
+@pytest.mark.parametrize("patch", [(8, 8), (16, 8), (8, 16), (4, 8)])
+def test_other_patch_sizes(patch):
+    """Patch sizes other than the reference's 16 x 16: (16,8)/(8,16) run the staged kernel, (8,8)/(4,8) the gather kernel."""
+    from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
+    tr = trajectory("cylinder")
+    plan, _, _ = _plan("cylinder")
+    states, mask, tab = interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 0, 3, 1, patch, CYLINDER)
+    _, extra = P.ds_get(tr, 0, 3, 1, 238, patch, "cylinder", return_all=True)
+    assert (tab.n_bx, tab.n_by) == (extra["N_x_patch"], extra["N_y_patch"])
+    assert np.array_equal(states.cpu().numpy(), extra["states"])
+    assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
+
+
+def test_unsupported_patch_size_is_an_error():
+    from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
+    tr = trajectory("cylinder")
+    plan, _, _ = _plan("cylinder")
+    with pytest.raises(ValueError):
+        interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 0, 2, 1, (5, 5), CYLINDER)
