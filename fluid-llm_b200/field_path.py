@@ -10,6 +10,7 @@ grid (which the reference's DataLoader collation requires anyway).
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -75,7 +76,9 @@ class TrajBatch:
     """Pre-built launch descriptors for a fixed batch (descriptor array already on the device), so
     the steady-state call is exactly one kernel launch and no host->device traffic."""
 
-    def __init__(self, trajs, tables, t0s, interval, n_frames, want_mask=True, use_slots=True):
+    def __init__(self, trajs, tables, t0s, interval, n_frames, want_mask=True, use_slots=None):
+        if use_slots is None:
+            use_slots = os.environ.get("FLUIDGRID_SLOTS", "1") != "0"
         if not (len(trajs) == len(tables) == len(t0s)) or not trajs:
             raise ValueError("trajs, tables and t0s must be non-empty and of equal length")
         tab0 = tables[0]
