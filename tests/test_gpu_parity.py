@@ -247,3 +247,25 @@ def test_unsupported_patch_size_is_an_error():
     plan, _, _ = _plan("cylinder")
     with pytest.raises(ValueError):
         interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 0, 2, 1, (5, 5), CYLINDER)
+
+
+@pytest.mark.parametrize("kind", ["cylinder", "airfoil", "eagle"])
+def test_experimental_block_path_matches_oracle(kind, monkeypatch):
+    """FLUIDGRID_BLOCKS=1: the 2 x 2 pixel-block form of the staged kernel (dense sums over <= 6 shared nodes)."""
+    monkeypatch.setenv("FLUIDGRID_BLOCKS", "1")
+    from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
+    from fluid_llm_b200.field_path import AIRFOIL, CYLINDER, DeviceTrajectory, interp_patchify
+    tr = trajectory(kind)
+    plan, pos, faces = _plan(kind)
+    vel, prs = tr["velocity"], tr["pressure"]
+    if kind == "airfoil":
+        nmask, _, _ = crop_airfoil_mesh(tr["mesh_pos"], tr["cells"])
+        vel, prs = vel[:, nmask], prs[:, nmask]
+    pers = AIRFOIL if kind == "airfoil" else CYLINDER
+    states, mask, tab = interp_patchify(DeviceTrajectory(vel, prs, plan), 0, 7, 1, PATCH, pers)
+    assert tab.blk_ids is not None
+    _, extra = oracle_ds_get(kind, 0, 7, 1)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
+    s, so = states.cpu().numpy(), extra["states"]
+    np.testing.assert_allclose(s, so, rtol=1e-6, atol=0)
+    assert np.array_equal(s, so)
