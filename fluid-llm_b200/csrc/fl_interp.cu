@@ -148,27 +148,11 @@ __device__ __forceinline__ void norm_fast2(float& x0, float& x1, unsigned long l
     x1 = __uint_as_float((unsigned)(y >> 32));
 }
 
-// float -> double on the integer/FMA pipes instead of the 16-lane conversion unit (XU): exact for
-// +-0 and normal numbers (the staging scan sends items holding subnormals, inf or NaN down the
-// checked path).  {t>>3, t<<29} is one 32x32->64 multiply by 2^29; then exponent re-bias and sign.
-__device__ __forceinline__ double f2d_int(float f) {
-    const unsigned x = __float_as_uint(f);
-    const unsigned t = x & 0x7fffffffu;
-    const unsigned long long p = (unsigned long long)t * 0x20000000ull;
-    unsigned hi = (unsigned)(p >> 32);
-    hi += t ? 0x38000000u : 0u;
-    hi |= x & 0x80000000u;
-    return __hiloint2double((int)hi, (int)(unsigned)p);
-}
-template <bool INT> __device__ __forceinline__ double f2d(float f) { return INT ? f2d_int(f) : (double)f; }
-
-// ICONV: 0 = every float->double conversion on the XU, 1 = v on the integer pipes, 2 = u and v
-template <bool CHECKED, int ICONV>
+template <bool CHECKED>
 __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned char* __restrict__ s_nodes, int slot_b,
                                             int fbeg, int nf, int n_patches, int ppx, int ppx_shift, const StagedConst& sc,
                                             unsigned flags) {
     const bool mask_aware = flags & FL_MASK_AWARE_NORM, no_norm = flags & FL_NO_NORM;
-    constexpr bool IV = !CHECKED && ICONV >= 1, IU = !CHECKED && ICONV >= 2;
     const int nchunks = n_patches * ppx / (32 * NP);
     const int lane_id = threadIdx.x & 31, warps = blockDim.x >> 5;
     // pixel of this lane inside a group of 32 adjacent pixels (2 patch rows x 16): the 8 lanes of a quarter-warp
@@ -228,8 +212,8 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
                 const double p0 = __hiloint2double(__float_as_int(a0.w), __float_as_int(a0.z));
                 const double p1 = __hiloint2double(__float_as_int(a1.w), __float_as_int(a1.z));
                 const double p2 = __hiloint2double(__float_as_int(a2.w), __float_as_int(a2.z));
-                res[0][r] = (float)fma(w2[r], f2d<IU>(a2.x), fma(w1[r], f2d<IU>(a1.x), w0[r] * f2d<IU>(a0.x)));
-                res[1][r] = (float)fma(w2[r], f2d<IV>(a2.y), fma(w1[r], f2d<IV>(a1.y), w0[r] * f2d<IV>(a0.y)));
+                res[0][r] = (float)fma(w2[r], (double)a2.x, fma(w1[r], (double)a1.x, w0[r] * (double)a0.x));
+                res[1][r] = (float)fma(w2[r], (double)a2.y, fma(w1[r], (double)a1.y, w0[r] * (double)a0.y));
                 res[2][r] = (float)fma(w2[r], p2, fma(w1[r], p1, w0[r] * p0));
                 if (CHECKED) {
                     if (!finite_f(res[2][r])) fm |= 1u << (8 * r);           // pressure mask only
@@ -418,8 +402,8 @@ __device__ __forceinline__ void staged_item_blocks(const FlTraj& tr, const unsig
     }
 }
 
-// ICONV 0..2: per-pixel form with 0 / v / u,v converted on the integer pipes; ICONV 3: the 2 x 2 block form
-template <int ICONV>
+// BLOCKS: the experimental 2 x 2 pixel-block form instead of the per-pixel form
+template <bool BLOCKS>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int groups_per_traj, int TF, int n_patches,
                          int ppx, int ppx_shift, int slot_nodes, StagedConst sc, unsigned flags) {
@@ -434,16 +418,9 @@ k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int grou
         // staging: coalesced 128-bit loads of 4 nodes' (u,v) pairs and pressures -> four 16-byte node
         // records, pressure converted to fp64 once per node; scanned on the way
         float nanacc = 0.f, amax = 0.f;
-        bool sub = false;
-        auto scan4 = [&](const float4 v, bool vel) {     // a non-finite or huge value sends the whole item down the checked path
+        auto scan4 = [&](const float4 v) {     // a non-finite or huge value sends the whole item down the checked path
             nanacc = fmaf(v.x, 0.f, fmaf(v.y, 0.f, fmaf(v.z, 0.f, fmaf(v.w, 0.f, nanacc))));
             amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fmaxf(fabsf(v.z), fabsf(v.w)), amax));
-            if (ICONV && vel) {   // subnormal <=> 0 < |bits| < 0x00800000  <=>  (|bits| - 1) < 0x007fffff (unsigned)
-                sub |= ((__float_as_uint(v.x) & 0x7fffffffu) - 1u) < 0x007fffffu;
-                sub |= ((__float_as_uint(v.y) & 0x7fffffffu) - 1u) < 0x007fffffu;
-                sub |= ((__float_as_uint(v.z) & 0x7fffffffu) - 1u) < 0x007fffffu;
-                sub |= ((__float_as_uint(v.w) & 0x7fffffffu) - 1u) < 0x007fffffu;
-            }
         };
         const int nq = tr.prs_stride / 4;      // groups of 4 nodes per frame (pad nodes are zero-filled)
         for (int i = threadIdx.x; i < nf * nq; i += blockDim.x) {
@@ -452,7 +429,7 @@ k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int grou
             const float4* vsrc = (const float4*)(tr.d_velocity + t * tr.vel_stride) + 2 * k4;
             const float4 va = fl_ldg_stream4(vsrc), vb = fl_ldg_stream4(vsrc + 1);
             const float4 pp = fl_ldg_stream4((const float4*)(tr.d_pressure + t * tr.prs_stride) + k4);
-            scan4(va, true); scan4(vb, true); scan4(pp, false);
+            scan4(va); scan4(vb); scan4(pp);
             float4* d = s_nodes + (size_t)f * slot_nodes;
             int4 sl = make_int4(4 * k4, 4 * k4 + 1, 4 * k4 + 2, 4 * k4 + 3);
             if (tr.d_node_slot) sl = __ldg((const int4*)tr.d_node_slot + k4);      // spatially sorted slots
@@ -462,11 +439,11 @@ k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int grou
             d[sl.z] = make_float4(vb.x, vb.y, __int_as_float(__double2loint(p2)), __int_as_float(__double2hiint(p2)));
             d[sl.w] = make_float4(vb.z, vb.w, __int_as_float(__double2loint(p3)), __int_as_float(__double2hiint(p3)));
         }
-        const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || sub || !sc.fast_div);
+        const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || !sc.fast_div);
         const unsigned char* snb = (const unsigned char*)s_nodes;
-        if (bad) staged_item<true, 0>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
-        else if (ICONV == 3) staged_item_blocks(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, sc, flags);
-        else staged_item<false, ICONV == 3 ? 0 : ICONV>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+        if (bad) staged_item<true>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+        else if (BLOCKS) staged_item_blocks(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, sc, flags);
+        else staged_item<false>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
         __syncthreads();   // every gather of this item is done before the next item's staging lands
     }
 }
@@ -504,12 +481,7 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             slot_prs = t.prs_stride > slot_prs ? t.prs_stride : slot_prs;
         }
         const size_t frame_bytes = 16 * (size_t)slot_prs;           // one 16-byte record per node (incl. pad nodes)
-        static int ctas_per_sm = 0;
-        if (!ctas_per_sm) {   // tuning knob (development): FLUIDGRID_CTAS=1|2
-            const char* e = getenv("FLUIDGRID_CTAS");
-            ctas_per_sm = (e && atoi(e) == 2) ? 2 : 1;
-        }
-        const size_t budget = ctas_per_sm == 1 ? 227 * 1024 : (227 * 1024) / 2 - 1024;
+        const size_t budget = 227 * 1024;
         int TF = ok && frame_bytes ? (int)(budget / frame_bytes) : 0;
         if (TF > 16) TF = 16;
         if (TF > max_frames) TF = max_frames;
@@ -520,25 +492,23 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             const int gpt = (max_frames + TF - 1) / TF;
             const long n_items = (long)gpt * n_traj;
             const size_t smem = (size_t)TF * frame_bytes;
-            typedef void (*StagedKernel)(const FlTraj*, int, int, int, int, int, int, int, StagedConst, unsigned);
-            static const StagedKernel kernels[4] = {k_interp_patchify_staged<0>, k_interp_patchify_staged<1>, k_interp_patchify_staged<2>,
-                                                    k_interp_patchify_staged<3>};
-            static int iconv = -1;
-            if (iconv < 0) {   // tuning knob (development): FLUIDGRID_ICONV=0|1|2
-                const char* e = getenv("FLUIDGRID_ICONV");
-                iconv = e ? atoi(e) : 0;
-                if (iconv < 0 || iconv > 2) iconv = 0;
-                for (int a = 0; a < 4; ++a)
-                    FL_CUDA(cudaFuncSetAttribute(kernels[a], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            static bool attr_set = false;
+            if (!attr_set) {
+                FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                attr_set = true;
             }
             int ppx_shift = -1;
             for (int b = 0; b < 16; ++b) if ((1 << b) == ppx) ppx_shift = b;
-            const long max_grid = (long)FL_SM_COUNT * ctas_per_sm;
-            int grid = n_items < max_grid ? (int)n_items : (int)max_grid;
+            const int grid = n_items < FL_SM_COUNT ? (int)n_items : FL_SM_COUNT;      // one persistent CTA per SM
             bool blocks = ppx == 256;                 // the block form needs its tables on every trajectory
             for (int i = 0; i < n_traj; ++i) blocks = blocks && h_trajs[i].d_blk_ids != nullptr;
-            kernels[blocks ? 3 : iconv]<<<grid, ST_THREADS / ctas_per_sm, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift,
-                                                                    slot_prs, sc, flags);
+            if (blocks)
+                k_interp_patchify_staged<true><<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift,
+                                                                              slot_prs, sc, flags);
+            else
+                k_interp_patchify_staged<false><<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift,
+                                                                               slot_prs, sc, flags);
             FL_LAUNCH_CHECK();
             return FL_OK;
         }
