@@ -71,6 +71,36 @@ class DeviceTrajectory:
         self.plan = plan
         self.n_steps = int(v.shape[0])
 
+    @classmethod
+    def from_padded(cls, vel_padded, prs_padded, plan: MeshPlan, stream=None, pinned=None):
+        """Node fields already in the device pitch (traj_store .fgt files): host [T, vel_stride] / [T, prs_stride]
+        -> pinned staging -> HBM, asynchronously on `stream` (default: the current stream)."""
+        self = cls.__new__(cls)
+        dev = plan.device
+        T, N = int(vel_padded.shape[0]), plan.n_nodes
+        self.prs_stride = (N + 3) // 4 * 4
+        self.vel_stride = 2 * self.prs_stride
+        if tuple(vel_padded.shape) != (T, self.vel_stride) or tuple(prs_padded.shape) != (T, self.prs_stride):
+            raise ValueError(f"padded node fields must be ({T}, {self.vel_stride}) and ({T}, {self.prs_stride})")
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev), torch.cuda.stream(st):
+            self.vel_buf = torch.empty((T, self.vel_stride), dtype=torch.float32, device=dev)
+            self.prs_buf = torch.empty((T, self.prs_stride), dtype=torch.float32, device=dev)
+            for name, src, dst in (("vel", vel_padded, self.vel_buf), ("prs", prs_padded, self.prs_buf)):
+                if pinned is not None:
+                    h = pinned.get(name, src.shape)
+                    h.numpy()[...] = src                      # page cache / disk -> pinned memory
+                else:
+                    h = torch.from_numpy(np.ascontiguousarray(src)).pin_memory()
+                dst.copy_(h, non_blocking=True)
+            if pinned is not None:
+                st.synchronize()                               # the staging buffers are reused by the next load
+        self.velocity = self.vel_buf[:, :2 * N].view(T, N, 2)
+        self.pressure = self.prs_buf[:, :N].view(T, N, 1)
+        self.plan = plan
+        self.n_steps = T
+        return self
+
 
 class TrajBatch:
     """Pre-built launch descriptors for a fixed batch (descriptor array already on the device), so

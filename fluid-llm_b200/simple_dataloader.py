@@ -20,6 +20,7 @@ from torch.utils.data import Dataset
 
 from .field_path import CYLINDER, DeviceTrajectory, Personality, interp_patchify
 from .mesh_utils import MeshPlan
+from .traj_store import PinnedStage, TrajectoryFile
 
 
 def num_patches(dim_size, kern_size, stride, padding=0):
@@ -70,6 +71,7 @@ class _GpuFieldDataset(Dataset):
         self.numpy_semantics = numpy_semantics
         self._cache = OrderedDict()
         self._pos_ids = None
+        self._pinned = PinnedStage()
 
         self.save_files = self._list_files()
         # simple_dataloader.py:45-56: probe file [1], step 20, for value ranges and the patch grid
@@ -82,7 +84,8 @@ class _GpuFieldDataset(Dataset):
 
     # -- file handling ----------------------------------------------------------------------
     def _list_files(self):
-        return sorted([f for f in os.listdir(f"{self.load_dir}/") if f.endswith('.pkl')])
+        # the reference's pickles, or the flat .fgt files of traj_store.py (same stems, converted once)
+        return sorted([f for f in os.listdir(f"{self.load_dir}/") if f.endswith(('.pkl', '.fgt'))])
 
     def _prepare_mesh(self, save_data):
         """-> (pos, faces, velocity, pressure) as the locate step should see them."""
@@ -96,11 +99,27 @@ class _GpuFieldDataset(Dataset):
         if traj is not None:
             self._cache.move_to_end(key)
             return traj
-        with open(path, 'rb') as f:
-            save_data = pickle.load(f)
-        pos, faces, vel, prs = self._prepare_mesh(save_data)
-        plan = MeshPlan(pos, faces, self.resolution, self.numpy_semantics, self.device)
-        traj = DeviceTrajectory(vel, prs, plan)
+        if path.endswith('.fgt'):
+            # flat format: crop (if any) was applied at conversion time, node fields are already in the device pitch
+            tf = TrajectoryFile(path)
+            if self.personality.crop_patches and not tf.header["meta"].get("airfoil_crop"):
+                # converted without the airfoil node crop: apply it now, like the pickle route does
+                n = tf.n_nodes
+                raw = {"mesh_pos": tf.mesh_pos, "cells": tf.cells,
+                       "velocity": np.asarray(tf.array("velocity"))[:, :2 * n].reshape(tf.n_steps, n, 2),
+                       "pressure": np.asarray(tf.array("pressure"))[:, :n, None]}
+                pos, faces, vel, prs = self._prepare_mesh(raw)
+                plan = MeshPlan(pos, faces, self.resolution, self.numpy_semantics, self.device)
+                traj = DeviceTrajectory(vel, prs, plan)
+            else:
+                plan = MeshPlan(tf.mesh_pos, tf.cells, self.resolution, self.numpy_semantics, self.device)
+                traj = tf.to_device(plan, pinned=self._pinned)
+        else:
+            with open(path, 'rb') as f:
+                save_data = pickle.load(f)
+            pos, faces, vel, prs = self._prepare_mesh(save_data)
+            plan = MeshPlan(pos, faces, self.resolution, self.numpy_semantics, self.device)
+            traj = DeviceTrajectory(vel, prs, plan)
         self._cache[key] = traj
         while len(self._cache) > self.cache_size:
             self._cache.popitem(last=False)

@@ -158,3 +158,28 @@ def test_img_mgn_dataset_matches_oracle(kind, tmp_path):
     assert np.array_equal(item["states"].numpy(), want_s)
     back = ds.denormalize(item["states"])
     assert back.shape == item["states"].shape
+
+
+@pytest.mark.parametrize("kind", ["cylinder", "airfoil"])
+def test_datasets_on_flat_fgt_files(kind, tmp_path):
+    """The flat on-disk format (traj_store.py) feeds the same datasets: identical 5-tuples to the pickle route."""
+    from fluid_llm_b200.airfoil_ds import AirfoilDataset
+    from fluid_llm_b200.simple_dataloader import MGNDataset
+    from fluid_llm_b200.traj_store import convert_pickle
+    trajs = [trajectory(kind, 140, s, 10 + s) for s in (0, 1)]
+    pk = tmp_path / "pkl"
+    fg = tmp_path / "fgt"
+    pk.mkdir()
+    fg.mkdir()
+    _write(pk, copy.deepcopy(trajs))
+    for i in range(2):
+        convert_pickle(str(pk / f"{i}.pkl"), str(fg / f"{i}.fgt"), airfoil_crop=(kind == "airfoil"))
+    DS = MGNDataset if kind == "cylinder" else AirfoilDataset
+    kw = dict(resolution=238, patch_size=PATCH, stride=PATCH, seq_len=4, seq_interval=2, mode="valid")
+    a, b = DS(load_dir=str(pk), **kw), DS(load_dir=str(fg), **kw)
+    assert b.save_files == ["0.fgt", "1.fgt"] and (a.N_x_patch, a.N_y_patch) == (b.N_x_patch, b.N_y_patch)
+    for x, y in zip(a[1], b[1]):
+        assert torch.equal(x, y)
+    want = P.ds_get(trajs[0], 100, 4, 2, 238, PATCH, "airfoil" if kind == "airfoil" else "cylinder")
+    for x, w in zip(b[0], want):
+        assert np.array_equal(x.cpu().numpy(), w)

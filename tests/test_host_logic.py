@@ -67,3 +67,27 @@ def test_synthetic_meshes_are_deterministic_and_valid():
         assert p1.dtype == np.float32 and c1.dtype == np.int32 and c1.min() == 0 and c1.max() == len(p1) - 1
     with pytest.raises(ValueError):
         synth.make_mesh("torus")
+
+
+def test_fgt_file_roundtrip(tmp_path):
+    import pickle
+    from fluid_llm_b200.traj_store import TrajectoryFile, convert_pickle, write_fgt
+    tr = trajectory("airfoil", 5)
+    pkl = tmp_path / "0.pkl"
+    with open(pkl, "wb") as f:
+        pickle.dump(tr, f)
+    hdr = convert_pickle(str(pkl), str(tmp_path / "0.fgt"), airfoil_crop=True)
+    tf = TrajectoryFile(str(tmp_path / "0.fgt"))
+    m, pos, faces = P.airfoil_crop(tr["mesh_pos"], tr["cells"])
+    assert tf.n_nodes == len(pos) and tf.n_steps == 5 and tf.prs_stride % 4 == 0 and tf.vel_stride == 2 * tf.prs_stride
+    assert np.array_equal(tf.mesh_pos, pos) and np.array_equal(tf.cells, faces.astype(np.int32))
+    vel, prs = tf.array("velocity"), tf.array("pressure")
+    assert np.array_equal(vel[:, :2 * tf.n_nodes].reshape(5, -1, 2), tr["velocity"][:, m])
+    assert np.array_equal(prs[:, :tf.n_nodes], tr["pressure"][:, m, 0])
+    assert not vel[:, 2 * tf.n_nodes:].any() and not prs[:, tf.n_nodes:].any()          # pad nodes are zero
+    assert all(a["offset"] % 4096 == 0 for a in hdr["arrays"].values())
+    with pytest.raises(ValueError):
+        write_fgt(str(tmp_path / "bad.fgt"), pos, faces, tr["velocity"], tr["pressure"])   # uncropped fields, cropped mesh
+    (tmp_path / "junk.fgt").write_bytes(b"not a trajectory")
+    with pytest.raises(ValueError):
+        TrajectoryFile(str(tmp_path / "junk.fgt"))
