@@ -332,6 +332,29 @@ def grid2mesh(velocity_grid, pressure_grid, mesh_pos, numpy_semantics="1.26"):
     return np.stack(vm), np.stack(pm)
 
 
+def get_nrmse(true_states, pred_states, mesh_pos, faces, numpy_semantics="1.26"):
+    """eagle/eagle_utils.py:60-130 -> float32 (1, seq_len): velocity + pressure N-RMSE on the grid."""
+    seq_len = true_states.shape[1]
+    triang, tri_index, gx, gy = get_mesh_interpolation(mesh_pos[0, 0], faces[0, 0], 238, numpy_semantics)
+    t_img, p_img = [], []
+    for i in range(seq_len):
+        ts, ps = [], []
+        for j in range(3):
+            a, mask = to_grid(true_states[0, i][:, j], gx, gy, triang, tri_index)
+            b, _ = to_grid(pred_states[0, i][:, j], gx, gy, triang, tri_index)
+            ts.append(a)
+            ps.append(b)
+        t_img.append(np.stack(ts))
+        p_img.append(np.stack(ps))
+    t_img, p_img = np.stack(t_img)[None], np.stack(p_img)[None]
+    m = np.broadcast_to(mask[None, None, None], t_img.shape)
+
+    def aux(p, t, mm):
+        err = ((p - t) * (~mm)).astype(F32)
+        return np.sqrt((err * err).mean(axis=(-1, -2, -3), dtype=F32))
+    return aux(p_img[:, :, :2], t_img[:, :, :2], m[:, :, :2]) + aux(p_img[:, :, 2:], t_img[:, :, 2:], m[:, :, 2:])
+
+
 # --------------------------------------------------------------------------------------------
 # dataset statistics  (max/compute_ds_stats.py)
 # --------------------------------------------------------------------------------------------

@@ -149,3 +149,19 @@ def test_ds_stats_matches_oracle(kind):
     assert torch.equal(ds_stats(states, mask), ds_stats(states, mask))
     means, stds = mean_std(torch.from_numpy(agg))
     assert means.shape == (6,) and (stds >= 0).all()
+
+
+def test_get_nrmse_matches_oracle():
+    """eagle/eagle_utils.py:89-130: true and predicted node states gridded and compared (second caller of to_grid)."""
+    from fluid_llm_b200.eagle_utils import get_nrmse
+    from helpers import trajectory
+    tr = trajectory("cylinder", 8)
+    T, N = 5, len(tr["mesh_pos"])
+    true = np.concatenate([tr["velocity"][:T], tr["pressure"][:T]], axis=2)[None]            # (1, T, N, 3)
+    pred = (true + np.random.default_rng(0).standard_normal(true.shape).astype(np.float32) * 0.05).astype(np.float32)
+    pos = np.broadcast_to(tr["mesh_pos"], (1, T, N, 2)).copy()
+    faces = np.broadcast_to(tr["cells"], (1, T) + tr["cells"].shape).copy()
+    got = get_nrmse(torch.from_numpy(true), torch.from_numpy(pred), torch.from_numpy(pos), torch.from_numpy(faces))
+    want = P.get_nrmse(true, pred, pos, faces)
+    assert got.shape == (1, T)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5)
