@@ -41,6 +41,8 @@ WORKLOADS = {
     "big": dict(kind="big", personality="cylinder", n_traj=4, T=64, res=2048, n_meshes=1),
 }
 N_MESHES = 4   # distinct meshes per GPU (trajectories cycle through them)
+# padded grid in patches every rank must agree on (so per-GPU work is identical at every N)
+WORKLOAD_GRIDS = {"airfoil": (15, 9), "cylinder": (15, 4), "eagle": (15, 10), "big": (128, 64)}
 
 
 def measured_peak():
@@ -99,12 +101,23 @@ def make_inputs(w, rank):
     """Seeded synthetic trajectories of the workload (host arrays), cropped as the dataset would."""
     from fluid_llm_b200 import synth
     from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
-    meshes = []
-    for m in range(w.get("n_meshes", N_MESHES)):
-        pos, cells = synth.make_mesh(w["kind"], seed=100 * rank + m)
+    from fluid_llm_b200.mesh_utils import _grid_shape
+    meshes, want, seed = [], None, 100 * rank
+    while len(meshes) < w.get("n_meshes", N_MESHES):
+        pos, cells = synth.make_mesh(w["kind"], seed=seed)
+        seed += 1
         sel = None
         if w["personality"] == "airfoil":
             sel, pos, cells = crop_airfoil_mesh(pos, cells)
+        # one batch = one patch grid (the reference's DataLoader collation needs that too): skip the rare synthetic mesh
+        # whose cropped bounding box lands on the other side of a multiple of the patch size
+        lo, hi = pos.min(axis=0), pos.max(axis=0)
+        nx, ny = _grid_shape(lo[0], hi[0], lo[1], hi[1], w.get("res", RES), "1.26")
+        grid = (-(-nx // PATCH[0]), -(-ny // PATCH[1]))
+        if want is None:
+            want = WORKLOAD_GRIDS.get(w["kind"], grid)
+        if grid != want:
+            continue
         meshes.append((pos, cells, sel))
     trajs = []
     for i in range(w["n_traj"]):
@@ -328,7 +341,7 @@ def run_ours(args, w):
                            "grid": f"{plans[0].nx}x{plans[0].ny} cells, {tab.n_bx}x{tab.n_by} patches of 16x16",
                            "frames_per_step_per_gpu": n_frames_step, "parallelism": f"trajectory-sharded x{world}",
                            "l2_policy": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2" % (algo_bytes / 1e6),
-                           "mesh_seed": "100*rank+m", "field_seed": "1000*rank+i", "stats_check_n": float(agg[0, 0].item())},
+                           "mesh_seed": "100*rank + 0,1,2,.. (meshes with another patch grid skipped)", "field_seed": "1000*rank+i", "stats_check_n": float(agg[0, 0].item())},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": algo_bytes, "kernel": "k_interp_patchify_staged", "traffic_source": "ncu --set full, profiles/r1_final_traffic.json" if traffic else None},
