@@ -321,6 +321,18 @@ def run_ours(args, w):
         e2e_sec = float(t.item())
     e2e_value = world * e2e_traj * e2e_T * e2e_steps / e2e_sec
 
+    # ---- the one-off per-mesh step, reported separately (cells located per second) ----
+    plans[0].locate()
+    torch.cuda.synchronize()
+    reps = []
+    for _ in range(10):
+        t0 = time.perf_counter()
+        plans[0].locate()            # four kernels + its own stream sync (the bin-item count is read back)
+        reps.append((time.perf_counter() - t0) * 1e3)
+    loc_ms = float(np.median(reps))
+    locate = {"ms_per_mesh": loc_ms, "cells_per_s": plans[0].nx * plans[0].ny / (loc_ms / 1e3),
+              "mesh": f"{plans[0].n_nodes} nodes / {plans[0].n_cells} triangles -> {plans[0].nx}x{plans[0].ny} cells"}
+
     # ---- the path's only collective: dataset statistics merged over ranks (functional check) ----
     agg = compute_ds_stats.ds_stats(batch.states[0], batch.mask[0])
     agg = compute_ds_stats.all_reduce_stats(agg)
@@ -349,6 +361,7 @@ def run_ours(args, w):
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "note": f"{e2e_traj} trajectories/step/GPU, pinned host buffers both ways"},
                 "gpu_launches": args.steps,
+                "locate_one_off": locate,
                 "clocks": sampler.result()}
         print(json.dumps(line), flush=True)
     if world > 1:

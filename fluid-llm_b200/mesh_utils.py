@@ -208,19 +208,25 @@ class MeshPlan:
             self.tri_index_d = torch.empty((self.nx, self.ny), dtype=torch.int32, device=dev)
             self.cell_idx_d = torch.empty((n, 4), dtype=torch.int32, device=dev)
             self.cell_w_d = torch.empty((n, 2), dtype=torch.float64, device=dev)
-            lib = load()
-            ws_bytes = int(lib.fl_locate_workspace_bytes(self.n_nodes, self.n_cells))
-            for _ in range(2):
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                rc = lib.fl_locate(ptr(self.pos_d), ptr(self.cells_d), self.n_nodes, self.n_cells, ptr(self.ax_d),
-                                   ptr(self.ay_d), self.nx, self.ny, ptr(self.tri_index_d), ptr(self.cell_idx_d),
-                                   ptr(self.cell_w_d), ptr(ws), ws_bytes, stream_ptr())
-                if rc != -3:
-                    break
-                ws_bytes *= 8          # very uneven meshes: retry once with a larger bin-item store
-            check(rc, "fl_locate")
+            self._ws_bytes = int(load().fl_locate_workspace_bytes(self.n_nodes, self.n_cells))
+            self.locate()
         self._tables = {}
         self._tri_index_host = None
+
+    def locate(self):
+        """(Re)run the point-location kernels (fl_locate) on the resident mesh: fills tri_index and the static table.
+        Called once by the constructor; bench.py calls it again to time the one-off step."""
+        lib = load()
+        with torch.cuda.device(self.device):
+            for _ in range(2):
+                ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+                rc = lib.fl_locate(ptr(self.pos_d), ptr(self.cells_d), self.n_nodes, self.n_cells, ptr(self.ax_d),
+                                   ptr(self.ay_d), self.nx, self.ny, ptr(self.tri_index_d), ptr(self.cell_idx_d),
+                                   ptr(self.cell_w_d), ptr(ws), self._ws_bytes, stream_ptr())
+                if rc != -3:
+                    break
+                self._ws_bytes *= 8          # very uneven meshes: retry once with a larger bin-item store
+            check(rc, "fl_locate")
 
     # -- reference-shaped views -------------------------------------------------------------
     @property
