@@ -209,6 +209,7 @@ class MeshPlan:
             self.cell_idx_d = torch.empty((n, 4), dtype=torch.int32, device=dev)
             self.cell_w_d = torch.empty((n, 2), dtype=torch.float64, device=dev)
             self._ws_bytes = int(load().fl_locate_workspace_bytes(self.n_nodes, self.n_cells))
+            self._tri_index_host = None
             self.locate()
         self._tables = {}
         self._tri_index_host = None
@@ -227,6 +228,7 @@ class MeshPlan:
                     break
                 self._ws_bytes *= 8          # very uneven meshes: retry once with a larger bin-item store
             check(rc, "fl_locate")
+        self._tri_index_host = None
 
     # -- reference-shaped views -------------------------------------------------------------
     @property

@@ -269,3 +269,49 @@ def test_experimental_block_path_matches_oracle(kind, monkeypatch):
     s, so = states.cpu().numpy(), extra["states"]
     np.testing.assert_allclose(s, so, rtol=1e-6, atol=0)
     assert np.array_equal(s, so)
+
+
+def test_c_abi_called_directly_as_integration_md_shows():
+    """fl_interp_patchify with host-side descriptors, bound with plain ctypes exactly like INTEGRATION.md section 5
+    (unpadded node arrays straight from the pickle layout -> the gather kernel)."""
+    import ctypes
+    from fluid_llm_b200._lib import LIB_PATH
+    tr = trajectory("cylinder")
+    plan, _, _ = _plan("cylinder")
+    tab = plan.patch_table(PATCH)
+    lib = ctypes.CDLL(LIB_PATH)
+
+    class FlTraj(ctypes.Structure):
+        _fields_ = [("d_velocity", ctypes.c_void_p), ("d_pressure", ctypes.c_void_p),
+                    ("d_idx", ctypes.c_void_p), ("d_w", ctypes.c_void_p),
+                    ("d_idx_slot", ctypes.c_void_p), ("d_node_slot", ctypes.c_void_p),
+                    ("d_blk_ids", ctypes.c_void_p), ("d_blk_idx", ctypes.c_void_p),
+                    ("d_blk_w", ctypes.c_void_p), ("d_b_list", ctypes.c_void_p),
+                    ("d_states", ctypes.c_void_p), ("d_mask", ctypes.c_void_p),
+                    ("n_nodes", ctypes.c_int32), ("t0", ctypes.c_int32), ("interval", ctypes.c_int32), ("n_frames", ctypes.c_int32),
+                    ("n_b", ctypes.c_int32), ("pad0", ctypes.c_int32), ("vel_stride", ctypes.c_int32), ("prs_stride", ctypes.c_int32)]
+
+    lib.fl_interp_patchify.restype = ctypes.c_int
+    lib.fl_interp_patchify.argtypes = [ctypes.POINTER(FlTraj), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.c_uint, ctypes.c_void_p]
+    lib.fl_last_error.restype = ctypes.c_char_p
+    vel = torch.from_numpy(tr["velocity"]).cuda()           # [T, N, 2], unpadded: N = 1855 is odd
+    prs = torch.from_numpy(tr["pressure"]).cuda()           # [T, N, 1]
+    N, seq_len, step, interval = vel.shape[1], 3, 1, 2
+    states = torch.empty((seq_len, tab.n_patches, 3, 16, 16), dtype=torch.float32, device="cuda")
+    mask = torch.empty((seq_len, tab.n_patches, 16, 16), dtype=torch.uint8, device="cuda")
+    traj = FlTraj(vel.data_ptr(), prs.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(), None, None, None, None, None, None,
+                  states.data_ptr(), mask.data_ptr(), N, step, interval, seq_len, 0, 0, vel.stride(0), prs.stride(0))
+    mean = (ctypes.c_float * 3)(0.823, 0.0005865, 0.04763)
+    std = (ctypes.c_float * 3)(0.275, 0.275, 0.275)
+    rc = lib.fl_interp_patchify(ctypes.byref(traj), 1, tab.n_patches, 16, 16, mean, std, 0,
+                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.fl_last_error().decode()
+    torch.cuda.synchronize()
+    _, extra = oracle_ds_get("cylinder", step, seq_len, interval)
+    assert np.array_equal(states.cpu().numpy(), extra["states"])
+    assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
+    # argument errors come back as negative codes with a message
+    traj.vel_stride = N          # too small for [N, 2]
+    assert lib.fl_interp_patchify(ctypes.byref(traj), 1, tab.n_patches, 16, 16, mean, std, 0, None) == -1
+    assert b"stride" in lib.fl_last_error()
