@@ -106,7 +106,7 @@ class TrajBatch:
     """Pre-built launch descriptors for a fixed batch (descriptor array already on the device), so
     the steady-state call is exactly one kernel launch and no host->device traffic."""
 
-    def __init__(self, trajs, tables, t0s, interval, n_frames, want_mask=True, use_slots=None):
+    def __init__(self, trajs, tables, t0s, interval, n_frames, want_mask=True, use_slots=None, out=None):
         if use_slots is None:
             use_slots = os.environ.get("FLUIDGRID_SLOTS", "1") != "0"
         # experimental 2 x 2 block path of the staged kernel (slower today, see profiles/README.md): opt-in
@@ -125,8 +125,17 @@ class TrajBatch:
             last = int(t0) + (self.n_frames - 1) * int(interval)
             if t0 < 0 or last >= tr.n_steps or interval < 1 or n_frames < 1:
                 raise ValueError(f"frames {t0}..{last} step {interval} outside trajectory of {tr.n_steps} steps")
-        self.states = torch.empty((self.n_traj, self.n_frames, L, 3, px, py), dtype=torch.float32, device=dev)
-        self.mask = torch.empty((self.n_traj, self.n_frames, L, px, py), dtype=torch.uint8, device=dev) if want_mask else None
+        if out is not None:           # caller-owned output buffers (HostPipeline's device slots)
+            self.states, self.mask = out
+            if tuple(self.states.shape) != (self.n_traj, self.n_frames, L, 3, px, py) or self.states.dtype != torch.float32 \
+                    or not self.states.is_contiguous() or self.states.device != dev:
+                raise ValueError("out[0] must be a contiguous float32 (n_traj, n_frames, L, 3, px, py) tensor on the plan's device")
+            if want_mask and (self.mask is None or tuple(self.mask.shape) != (self.n_traj, self.n_frames, L, px, py)
+                              or self.mask.dtype != torch.uint8 or not self.mask.is_contiguous()):
+                raise ValueError("out[1] must be a contiguous uint8 (n_traj, n_frames, L, px, py) tensor")
+        else:
+            self.states = torch.empty((self.n_traj, self.n_frames, L, 3, px, py), dtype=torch.float32, device=dev)
+            self.mask = torch.empty((self.n_traj, self.n_frames, L, px, py), dtype=torch.uint8, device=dev) if want_mask else None
         arr = (FlTraj * self.n_traj)()
         for i, (tr, tab, t0) in enumerate(zip(trajs, tables, t0s)):
             arr[i] = FlTraj(tr.vel_buf.data_ptr(), tr.prs_buf.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(),
@@ -165,3 +174,89 @@ def interp_patchify(traj: DeviceTrajectory, step_num: int, seq_len: int, seq_int
     batch = TrajBatch([traj], [tab], [step_num], seq_interval, seq_len)
     states, mask = batch.run(personality, normalize, means, stds, force_gather)
     return states[0], mask[0], tab
+
+
+class HostPipeline:
+    """Host buffers in, host buffers out: the call a caller without device-resident data makes (the reference's
+    DataLoader workers hand CPU tensors to the trainer, `src/dataloader/simple_dataloader.py:72-102`).
+
+    `depth` device slots and three streams: while the kernel works on trajectory i, the node fields of trajectory i+1
+    are on their way up and the states of trajectory i-1 on their way down, so a steady stream of trajectories runs at
+    the speed of the slower PCIe direction (the output: 13 bytes per pixel-frame) instead of the sum of all three.
+    Host tensors must be pinned for the copies to be asynchronous; `run` does not synchronise -- call `wait()` (or
+    synchronise the device) before reading the host outputs.
+    """
+
+    def __init__(self, plans, tables, personality: Personality, n_steps: int, t0: int = 0, interval: int = 1,
+                 n_frames=None, depth: int = 2, want_mask: bool = True):
+        _lib.require_cuda()
+        if len(plans) != len(tables) or not plans:
+            raise ValueError("plans and tables must be non-empty and of equal length")
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.personality, self.n = personality, len(plans)
+        self.n_frames = int(n_frames) if n_frames is not None else (int(n_steps) - int(t0) + int(interval) - 1) // int(interval)
+        dev = plans[0].device
+        self.device, self.depth, self.want_mask = dev, min(depth, self.n), want_mask
+        tab0 = tables[0]
+        L, px, py = tab0.n_patches, tab0.px, tab0.py
+        max_stride = max((pl.n_nodes + 3) // 4 * 4 for pl in plans)
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.slots = []
+        for _ in range(self.depth):
+            self.slots.append({
+                "vel": torch.zeros((n_steps, 2 * max_stride), dtype=torch.float32, device=dev),
+                "prs": torch.zeros((n_steps, max_stride), dtype=torch.float32, device=dev),
+                "states": torch.empty((1, self.n_frames, L, 3, px, py), dtype=torch.float32, device=dev),
+                "mask": torch.empty((1, self.n_frames, L, px, py), dtype=torch.uint8, device=dev) if want_mask else None,
+                "in_done": torch.cuda.Event(), "run_done": torch.cuda.Event(), "out_done": torch.cuda.Event(),
+            })
+        # one descriptor per (trajectory, slot it will use): the device views of that slot in the trajectory's own pitch
+        self.items = []
+        for i, (pl, tab) in enumerate(zip(plans, tables)):
+            sl = self.slots[i % self.depth]
+            tr = DeviceTrajectory.__new__(DeviceTrajectory)
+            N = pl.n_nodes
+            tr.prs_stride = (N + 3) // 4 * 4
+            tr.vel_stride = 2 * tr.prs_stride
+            tr.vel_buf = sl["vel"].view(-1)[: n_steps * tr.vel_stride].view(n_steps, tr.vel_stride)
+            tr.prs_buf = sl["prs"].view(-1)[: n_steps * tr.prs_stride].view(n_steps, tr.prs_stride)
+            tr.velocity = tr.vel_buf[:, :2 * N].view(n_steps, N, 2)
+            tr.pressure = tr.prs_buf[:, :N].unsqueeze(-1)
+            tr.plan, tr.n_steps = pl, int(n_steps)
+            batch = TrajBatch([tr], [tab], [t0], interval, self.n_frames, want_mask=want_mask, out=(sl["states"], sl["mask"]))
+            self.items.append((tr, batch, sl))
+        torch.cuda.current_stream(dev).synchronize()      # slot buffers were zero-filled on the current stream
+        self._first = True
+
+    def run(self, h_velocity, h_pressure, h_states, h_mask=None, normalize=True):
+        """h_velocity[i] (T, N_i, 2) / h_pressure[i] (T, N_i, 1) pinned host tensors -> h_states[i] (n_frames, L, 3, px, py),
+        h_mask[i] (n_frames, L, px, py) pinned host tensors.  Everything is enqueued asynchronously."""
+        if len(h_velocity) != self.n or len(h_pressure) != self.n or len(h_states) != self.n:
+            raise ValueError(f"expected {self.n} trajectories")
+        if self.want_mask and (h_mask is None or len(h_mask) != self.n):
+            raise ValueError("h_mask missing")
+        with torch.cuda.device(self.device):
+            for i, (tr, batch, sl) in enumerate(self.items):
+                with torch.cuda.stream(self.s_in):
+                    if not self._first or i >= self.depth:
+                        self.s_in.wait_event(sl["run_done"])          # the slot's previous kernel has consumed its inputs
+                    tr.velocity.copy_(h_velocity[i], non_blocking=True)
+                    tr.pressure.copy_(h_pressure[i], non_blocking=True)
+                    sl["in_done"].record(self.s_in)
+                with torch.cuda.stream(self.s_run):
+                    self.s_run.wait_event(sl["in_done"])
+                    if not self._first or i >= self.depth:
+                        self.s_run.wait_event(sl["out_done"])         # the slot's previous outputs have left
+                    batch.run(self.personality, normalize)
+                    sl["run_done"].record(self.s_run)
+                with torch.cuda.stream(self.s_out):
+                    self.s_out.wait_event(sl["run_done"])
+                    h_states[i].copy_(sl["states"][0], non_blocking=True)
+                    if self.want_mask:
+                        h_mask[i].copy_(sl["mask"][0], non_blocking=True)
+                    sl["out_done"].record(self.s_out)
+            self._first = False
+
+    def wait(self):
+        self.s_out.synchronize()

@@ -159,6 +159,35 @@ def test_interp_patchify_batch_of_meshes():
         TrajBatch(trajs, tabs, [0, 0, 7], 1, 4)      # runs past the end of the trajectory
 
 
+def test_host_pipeline_matches_oracle():
+    """Host buffers in / host buffers out through the three-stream pipeline: five trajectories with different meshes
+    over two device slots, run twice (slot reuse across calls)."""
+    from fluid_llm_b200.field_path import CYLINDER, HostPipeline
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    seeds = (0, 1, 2, 0, 2)
+    plans, tabs, hv, hp, want = [], [], [], [], []
+    for k, seed in enumerate(seeds):
+        tr = trajectory("cylinder", 8, seed, 20 + k)
+        plan = MeshPlan(tr["mesh_pos"], tr["cells"], 238)
+        plans.append(plan)
+        tabs.append(plan.patch_table(PATCH))
+        hv.append(torch.from_numpy(np.ascontiguousarray(tr["velocity"], dtype=np.float32)).pin_memory())
+        hp.append(torch.from_numpy(np.ascontiguousarray(tr["pressure"], dtype=np.float32).reshape(8, -1, 1)).pin_memory())
+        want.append(oracle_ds_get("cylinder", 1, 3, 2, mesh_seed=seed, field_seed=20 + k)[1])
+    pipe = HostPipeline(plans, tabs, CYLINDER, n_steps=8, t0=1, interval=2, n_frames=3, depth=2)
+    L = tabs[0].n_patches
+    for rep in range(2):
+        hs = [torch.full((3, L, 3, 16, 16), float("nan")).pin_memory() for _ in seeds]
+        hm = [torch.full((3, L, 16, 16), 7, dtype=torch.uint8).pin_memory() for _ in seeds]
+        pipe.run(hv, hp, hs, hm)
+        pipe.wait()
+        for i, ex in enumerate(want):
+            assert np.array_equal(hs[i].numpy(), ex["states"]), (rep, i)
+            assert np.array_equal(hm[i].numpy().astype(bool), ex["masks"].astype(bool)), (rep, i)
+    with pytest.raises(ValueError):
+        pipe.run(hv[:2], hp[:2], hs[:2], hm[:2])
+
+
 def test_custom_mean_std():
     from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
     tr = trajectory("eagle")
