@@ -51,6 +51,11 @@ SIGNATURES = {
                                 c_int, c_void_p]),
     "fl_grid2mesh": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                              c_double, c_double, c_void_p]),
+    "fl_dyn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "fl_dyn_capacity": (c_int, [c_int, c_int, c_int, c_int, c_size_t]),
+    "fl_dyn_interp_patchify": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_int, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), c_uint,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fl_stats_workspace_bytes": (c_size_t, []),
     "fl_ds_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fl_stats_merge": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),

@@ -9,28 +9,16 @@
 // to fp32.  Here the same point value is the fp64 barycentric sum w0*z0 + w1*z1 + w2*z2 (weights
 // fp64, from the static table), rounded once to fp32, then (v - mean) and / std in fp32 with
 // IEEE division, i.e. the same two roundings as simple_dataloader.py:213-214.
-#include "fl_common.cuh"
+#include "fl_geom.cuh"
 #include <string.h>
 #include <stdlib.h>
 #include <math.h>
 
+using flg::NormConst;
+using flg::interp3;
+using flg::finite_f;
+
 namespace {
-
-struct NormConst { float mean[3]; float stdv[3]; };
-
-// one output pixel, three channels, fp64 barycentric sum rounded once to fp32
-__device__ __forceinline__ void interp3(const float* __restrict__ vel, const float* __restrict__ prs, FlCellIdx id,
-                                        double w0, double w1, double w2, float out[3]) {
-    const float2 a0 = __ldg((const float2*)vel + id.v0);
-    const float2 a1 = __ldg((const float2*)vel + id.v1);
-    const float2 a2 = __ldg((const float2*)vel + id.v2);
-    const float p0 = __ldg(prs + id.v0), p1 = __ldg(prs + id.v1), p2 = __ldg(prs + id.v2);
-    out[0] = (float)fma(w2, (double)a2.x, fma(w1, (double)a1.x, w0 * (double)a0.x));
-    out[1] = (float)fma(w2, (double)a2.y, fma(w1, (double)a1.y, w0 * (double)a0.y));
-    out[2] = (float)fma(w2, (double)p2, fma(w1, (double)p1, w0 * (double)p0));
-}
-
-__device__ __forceinline__ bool finite_f(float v) { return (__float_as_uint(v) & 0x7f800000u) != 0x7f800000u; }
 
 // Generic kernel: one CTA = one patch (px*py threads) x a chunk of frames of one trajectory.
 // Each thread keeps its cell record in registers and walks the frames; node values are gathered

@@ -15,39 +15,25 @@
 //   k_locate        per grid cell: evaluate the rule over its bin, emit tri id + table record
 // Bins are blocks of BIN x BIN grid cells, so the cost follows the number of grid cells and a
 // triangle that covers no grid point is dropped in the first kernel.
-#include "fl_common.cuh"
+#include "fl_geom.cuh"
+
+using namespace flg;
 
 namespace {
 
-constexpr int BIN = 4;  // grid cells per bin side
-
-struct TriRange { short bx0, bx1, by0, by1; };  // inclusive bin range, bx0 > bx1 = empty
-
-__device__ __forceinline__ int lower_bound_f(const float* a, int n, double v) {  // first i: a[i] >= v
-    int lo = 0, hi = n;
-    while (lo < hi) { int m = (lo + hi) >> 1; if ((double)a[m] < v) lo = m + 1; else hi = m; }
-    return lo;
-}
-__device__ __forceinline__ int upper_bound_f(const float* a, int n, double v) {  // first i: a[i] > v
-    int lo = 0, hi = n;
-    while (lo < hi) { int m = (lo + hi) >> 1; if ((double)a[m] <= v) lo = m + 1; else hi = m; }
-    return lo;
-}
-
-// (p - l) x (r - l) with every product and difference rounded separately (no FMA contraction):
-// the expression matplotlib's Edge::get_point_orientation evaluates on x86-64.
-__device__ __forceinline__ double orient(double px, double py, double lx, double ly, double rx, double ry) {
-    double a = __dmul_rn(__dsub_rn(px, lx), __dsub_rn(ry, ly));
-    double b = __dmul_rn(__dsub_rn(py, ly), __dsub_rn(rx, lx));
-    return __dsub_rn(a, b);
-}
-
-__global__ void k_tri_prepare(const float* __restrict__ pos, const int* __restrict__ cells, int n_nodes, int n_cells,
-                              const float* __restrict__ ax, const float* __restrict__ ay, int nx, int ny, int nbx,
-                              int nby, int* __restrict__ tri_v, TriRange* __restrict__ tri_range,
-                              int* __restrict__ bin_count, int* __restrict__ flags) {
+// blockIdx.y = frame (mesh); the single-mesh entry point runs with one frame
+__global__ void k_tri_prepare(const float* __restrict__ pos_all, size_t pos_stride, const int* __restrict__ cells_all,
+                              int n_nodes, int n_cells, const float* __restrict__ ax, const float* __restrict__ ay, int nx,
+                              int ny, int nby, int nbins, int* __restrict__ tri_v_all, TriRange* __restrict__ tri_range_all,
+                              int* __restrict__ bin_count_all, int* __restrict__ flags) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_cells) return;
+    const int f = blockIdx.y;
+    const float* pos = pos_all + (size_t)f * pos_stride;
+    const int* cells = cells_all + (size_t)f * 3 * n_cells;
+    int* tri_v = tri_v_all + (size_t)f * 3 * n_cells;
+    TriRange* tri_range = tri_range_all + (size_t)f * n_cells;
+    int* bin_count = bin_count_all + (size_t)f * (nbins + 1);
     int v0 = cells[3 * t], v1 = cells[3 * t + 1], v2 = cells[3 * t + 2];
     TriRange r{1, 0, 1, 0};
     if ((unsigned)v0 >= (unsigned)n_nodes || (unsigned)v1 >= (unsigned)n_nodes || (unsigned)v2 >= (unsigned)n_nodes) {
@@ -76,10 +62,12 @@ __global__ void k_tri_prepare(const float* __restrict__ pos, const int* __restri
     tri_range[t] = r;
 }
 
-// exclusive scan of count[0..n) into start[0..n], total in start[n] and flags[1]
-__global__ void k_scan(const int* __restrict__ count, int* __restrict__ start, int n, int* __restrict__ flags) {
+// one CTA per frame: exclusive scan of count[0..n) into start[0..n], total in start[n]; flags[1] = max total over the frames
+__global__ void k_scan(const int* __restrict__ count_all, int* __restrict__ start_all, int n, int* __restrict__ flags) {
     __shared__ int warp_sum[32];
     __shared__ int carry;
+    const int* count = count_all + (size_t)blockIdx.x * (n + 1);
+    int* start = start_all + (size_t)blockIdx.x * (n + 1);
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -102,38 +90,25 @@ __global__ void k_scan(const int* __restrict__ count, int* __restrict__ start, i
         if (threadIdx.x == blockDim.x - 1) carry = prefix + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) { start[n] = carry; flags[1] = carry; }
+    if (threadIdx.x == 0) { start[n] = carry; atomicMax(&flags[1], carry); }
 }
 
-__global__ void k_fill(const TriRange* __restrict__ tri_range, int n_cells, int nby, const int* __restrict__ bin_start,
-                       int* __restrict__ cursor, int* __restrict__ items, int capacity) {
+__global__ void k_fill(const TriRange* __restrict__ tri_range_all, int n_cells, int nby, int nbins,
+                       const int* __restrict__ bin_start_all, int* __restrict__ cursor_all, int* __restrict__ items_all,
+                       int capacity) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_cells) return;
-    TriRange r = tri_range[t];
+    const int f = blockIdx.y;
+    const int* bin_start = bin_start_all + (size_t)f * (nbins + 1);
+    int* cursor = cursor_all + (size_t)f * (nbins + 1);
+    int* items = items_all + (size_t)f * capacity;
+    TriRange r = tri_range_all[(size_t)f * n_cells + t];
     for (int bx = r.bx0; bx <= r.bx1; ++bx)
         for (int by = r.by0; by <= r.by1; ++by) {
             int b = bx * nby + by;
             int p = bin_start[b] + atomicAdd(&cursor[b], 1);
             if (p < capacity) items[p] = t;
         }
-}
-
-// The tie-break rule (include/fluidgrid.h), evaluated for one (cell, triangle) pair.
-// Returns -1 = rejected, 0 = accepted with full priority (strictly inside, on a vertex, or on
-// an edge the triangle lies above), 1 = accepted only if nothing lies above that edge.
-__device__ __forceinline__ int rule_eval(double qx, double qy, const double* vx, const double* vy) {
-    if ((qx == vx[0] && qy == vy[0]) || (qx == vx[1] && qy == vy[1]) || (qx == vx[2] && qy == vy[2])) return 0;
-    int prio = 0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        int k1 = (k + 1) % 3;
-        bool end_right = (vx[k1] == vx[k]) ? (vy[k1] > vy[k]) : (vx[k1] > vx[k]);
-        double s = end_right ? orient(qx, qy, vx[k], vy[k], vx[k1], vy[k1])
-                             : orient(qx, qy, vx[k1], vy[k1], vx[k], vy[k]);
-        if (end_right) { if (!(s <= 0.0)) return -1; }         // triangle is above this edge
-        else { if (!(s >= 0.0)) return -1; if (s == 0.0) prio = 1; }  // triangle is below it
-    }
-    return prio;
 }
 
 __global__ void k_locate(const float* __restrict__ pos, const int* __restrict__ tri_v, const float* __restrict__ ax,
@@ -145,31 +120,14 @@ __global__ void k_locate(const float* __restrict__ pos, const int* __restrict__ 
     int ix = c / ny, iy = c - ix * ny;
     double qx = (double)ax[ix], qy = (double)ay[iy];
     int b = (ix / BIN) * nby + iy / BIN;
-    unsigned best = 0xffffffffu;  // (prio << 31) | tri
-    for (int k = bin_start[b]; k < bin_start[b + 1]; ++k) {
-        int t = items[k];
-        double vx[3], vy[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) { int v = tri_v[3 * t + j]; vx[j] = pos[2 * v]; vy[j] = pos[2 * v + 1]; }
-        int p = rule_eval(qx, qy, vx, vy);
-        if (p >= 0) best = min(best, ((unsigned)p << 31) | (unsigned)t);
-    }
-    int tri = best == 0xffffffffu ? -1 : (int)(best & 0x7fffffffu);
+    int tri = locate_in_bin(pos, tri_v, items, bin_start[b], bin_start[b + 1], qx, qy);
     if (tri_index) tri_index[c] = tri;
     if (cell_idx) {
         FlCellIdx rec{0, 0, 0, -1};
         FlCellW w{0.0, 0.0};
         if (tri >= 0) {
             rec.v0 = tri_v[3 * tri]; rec.v1 = tri_v[3 * tri + 1]; rec.v2 = tri_v[3 * tri + 2]; rec.tri = tri;
-            double x0 = pos[2 * rec.v0], y0 = pos[2 * rec.v0 + 1];
-            double e1x = (double)pos[2 * rec.v1] - x0, e1y = (double)pos[2 * rec.v1 + 1] - y0;
-            double e2x = (double)pos[2 * rec.v2] - x0, e2y = (double)pos[2 * rec.v2 + 1] - y0;
-            double dx = qx - x0, dy = qy - y0;
-            double d = e1x * e2y - e2x * e1y;
-            if (d != 0.0) {
-                w.w1 = (dx * e2y - e2x * dy) / d;
-                w.w2 = (e1x * dy - dx * e1y) / d;
-            }
+            cell_weights(pos, rec.v0, rec.v1, rec.v2, qx, qy, w.w1, w.w2);
         }
         cell_idx[c] = rec;
         cell_w[c] = w;
@@ -195,28 +153,31 @@ __global__ void k_plan_patch_table(const FlCellIdx* __restrict__ cell_idx, const
     out_w[o] = w;
 }
 
-struct LocateWs {
-    int* tri_v; TriRange* tri_range; int* bin_count; int* bin_start; int* cursor; int* flags; int* items;
-    int nbx, nby, nbins, capacity;
-};
-
-size_t locate_fixed_bytes(int n_cells, int nbins) {
-    size_t b = 0;
-    b += fl_align_up(sizeof(int) * 3 * (size_t)n_cells, 256);
-    b += fl_align_up(sizeof(TriRange) * (size_t)n_cells, 256);
-    b += 3 * fl_align_up(sizeof(int) * ((size_t)nbins + 1), 256);
-    b += 256;  // flags
-    return b;
-}
-
 }  // namespace
+
+int flg::bin_frames(const float* d_pos, size_t pos_stride, const int* d_cells, int n_nodes, const float* d_ax, const float* d_ay,
+                    int nx, int ny, const BinWs& w, bool keep_flags, cudaStream_t st) {
+    // bin_count, bin_start, cursor (and the flags behind them) start at zero
+    FL_CUDA(cudaMemsetAsync(w.bin_count, 0, w.zero_bytes, st));
+    if (!keep_flags) FL_CUDA(cudaMemsetAsync(w.flags, 0, 2 * sizeof(int), st));
+    const int tb = 128;
+    dim3 grid((w.n_cells + tb - 1) / tb, w.n_frames);
+    k_tri_prepare<<<grid, tb, 0, st>>>(d_pos, pos_stride, d_cells, n_nodes, w.n_cells, d_ax, d_ay, nx, ny, w.nby, w.nbins,
+                                       w.tri_v, w.tri_range, w.bin_count, w.flags);
+    FL_LAUNCH_CHECK();
+    k_scan<<<w.n_frames, 1024, 0, st>>>(w.bin_count, w.bin_start, w.nbins, w.flags);
+    FL_LAUNCH_CHECK();
+    k_fill<<<grid, tb, 0, st>>>(w.tri_range, w.n_cells, w.nby, w.nbins, w.bin_start, w.cursor, w.items, w.capacity);
+    FL_LAUNCH_CHECK();
+    return FL_OK;
+}
 
 extern "C" size_t fl_locate_workspace_bytes(int n_nodes, int n_cells) {
     (void)n_nodes;
     if (n_cells < 0) return 0;
     // fixed part for grids up to 4096 x 4096 cells plus room for 16 bin entries per triangle
     size_t nbins_max = (size_t)(4096 / BIN) * (4096 / BIN);
-    return locate_fixed_bytes(n_cells, (int)nbins_max) + sizeof(int) * (16 * (size_t)n_cells + 4 * nbins_max) + 256;
+    return bin_ws_fixed_bytes(1, n_cells, (int)nbins_max) + sizeof(int) * (16 * (size_t)n_cells + 4 * nbins_max) + 256;
 }
 
 extern "C" int fl_locate(const float* d_pos, const int32_t* d_cells, int n_nodes, int n_cells, const float* d_grid_ax,
@@ -228,37 +189,17 @@ extern "C" int fl_locate(const float* d_pos, const int32_t* d_cells, int n_nodes
     FL_REQUIRE((d_cell_idx == nullptr) == (d_cell_w == nullptr), FL_E_ARG, "fl_locate: d_cell_idx and d_cell_w go together");
     FL_REQUIRE(((uintptr_t)d_workspace & 255) == 0, FL_E_ALIGN, "fl_locate: workspace must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    LocateWs w;
-    w.nbx = (nx + BIN - 1) / BIN; w.nby = (ny + BIN - 1) / BIN; w.nbins = w.nbx * w.nby;
-    size_t fixed = locate_fixed_bytes(n_cells, w.nbins);
-    FL_REQUIRE(workspace_bytes >= fixed + 1024, FL_E_WORKSPACE, "fl_locate: workspace too small (%zu < %zu)",
-               workspace_bytes, fixed + 1024);
-    char* p = (char*)d_workspace;
-    w.tri_v = (int*)p; p += fl_align_up(sizeof(int) * 3 * (size_t)n_cells, 256);
-    w.tri_range = (TriRange*)p; p += fl_align_up(sizeof(TriRange) * (size_t)n_cells, 256);
-    w.bin_count = (int*)p; p += fl_align_up(sizeof(int) * ((size_t)w.nbins + 1), 256);
-    w.bin_start = (int*)p; p += fl_align_up(sizeof(int) * ((size_t)w.nbins + 1), 256);
-    w.cursor = (int*)p; p += fl_align_up(sizeof(int) * ((size_t)w.nbins + 1), 256);
-    w.flags = (int*)p; p += 256;
-    w.items = (int*)p;
-    size_t cap = (workspace_bytes - (size_t)(p - (char*)d_workspace)) / sizeof(int);
-    w.capacity = cap > 0x7fffffff ? 0x7fffffff : (int)cap;
-
-    FL_CUDA(cudaMemsetAsync(w.bin_count, 0, (size_t)((char*)w.items - (char*)w.bin_count), st));
-    int tb = 128;
-    k_tri_prepare<<<(n_cells + tb - 1) / tb, tb, 0, st>>>(d_pos, d_cells, n_nodes, n_cells, d_grid_ax, d_grid_ay, nx, ny,
-                                                          w.nbx, w.nby, w.tri_v, w.tri_range, w.bin_count, w.flags);
-    FL_LAUNCH_CHECK();
-    k_scan<<<1, 1024, 0, st>>>(w.bin_count, w.bin_start, w.nbins, w.flags);
-    FL_LAUNCH_CHECK();
+    BinWs w;
+    FL_REQUIRE(bin_ws_carve(d_workspace, workspace_bytes, 1, n_cells, nx, ny, &w), FL_E_WORKSPACE,
+               "fl_locate: workspace too small (%zu bytes)", workspace_bytes);
+    int rc = bin_frames(d_pos, 0, d_cells, n_nodes, d_grid_ax, d_grid_ay, nx, ny, w, false, st);
+    if (rc) return rc;
     int h_flags[2];
     FL_CUDA(cudaMemcpyAsync(h_flags, w.flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
     FL_CUDA(cudaStreamSynchronize(st));  // one-off per mesh: the item count decides whether the workspace fits
     FL_REQUIRE(h_flags[0] == 0, FL_E_RANGE, "fl_locate: %d triangles index nodes outside 0 <= i < %d", h_flags[0], n_nodes);
     FL_REQUIRE(h_flags[1] <= w.capacity, FL_E_WORKSPACE, "fl_locate: workspace too small, need %zu more bytes",
                sizeof(int) * ((size_t)h_flags[1] - (size_t)w.capacity));
-    k_fill<<<(n_cells + tb - 1) / tb, tb, 0, st>>>(w.tri_range, n_cells, w.nby, w.bin_start, w.cursor, w.items, w.capacity);
-    FL_LAUNCH_CHECK();
     int n = nx * ny;
     k_locate<<<(n + 127) / 128, 128, 0, st>>>(d_pos, w.tri_v, d_grid_ax, d_grid_ay, nx, ny, w.nby, w.bin_start, w.items,
                                               d_tri_index, d_cell_idx, d_cell_w);

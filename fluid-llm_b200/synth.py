@@ -19,7 +19,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["make_mesh", "make_fields", "make_trajectory", "MESH_KINDS"]
+__all__ = ["make_mesh", "make_fields", "make_trajectory", "make_dynamic_trajectory", "MESH_KINDS"]
 
 MESH_KINDS = ("cylinder", "airfoil", "eagle", "big")
 
@@ -214,3 +214,69 @@ def make_trajectory(kind: str, T: int, mesh_seed: int = 0, field_seed: int = 1, 
     return {"mesh_pos": pos, "cells": tri, "velocity": vel, "pressure": prs,
             "density": np.ones((T, len(pos), 1), dtype=np.float32),
             "node_type": np.zeros((len(pos), 1), dtype=np.int32)}
+
+
+def _flip_edges(pos64, tri, rng, frac):
+    """Flip the shared diagonal of a random set of adjacent triangle pairs whose union is a strictly convex quad:
+    same nodes, same triangle count, different connectivity."""
+    tri = tri.copy()
+    edge_owner = {}
+    pairs = []
+    for t, (a, b, c) in enumerate(tri):
+        for (u, v, w) in ((a, b, c), (b, c, a), (c, a, b)):
+            key = (min(u, v), max(u, v))
+            if key in edge_owner:
+                pairs.append((edge_owner[key], (t, w), key))
+            else:
+                edge_owner[key] = (t, w)
+    if not pairs:
+        return tri
+    order = rng.permutation(len(pairs))[: max(1, int(frac * len(pairs)))]
+    touched = set()
+
+    def area2(p, q, r):
+        return (q[0] - p[0]) * (r[1] - p[1]) - (q[1] - p[1]) * (r[0] - p[0])
+
+    for i in order:
+        (t1, w1), (t2, w2), (u, v) = pairs[i]
+        if t1 in touched or t2 in touched:
+            continue
+        pu, pv, p1, p2 = pos64[u], pos64[v], pos64[w1], pos64[w2]
+        # the new diagonal w1-w2 must separate u and v strictly, and both new triangles must keep some area
+        s1, s2 = area2(p1, p2, pu), area2(p1, p2, pv)
+        scale = abs(area2(pu, pv, p1)) + abs(area2(pu, pv, p2))
+        if s1 * s2 >= 0 or min(abs(s1), abs(s2)) < 0.05 * scale:
+            continue
+        tri[t1] = (w1, w2, u)
+        tri[t2] = (w2, w1, v)
+        touched.update((t1, t2))
+    return tri
+
+
+def make_dynamic_trajectory(kind: str, T: int, mesh_seed: int = 0, field_seed: int = 1, flip_frac: float = 0.05, **kw):
+    """A trajectory whose mesh changes every frame, in the layout of EAGLE's sim.npz + triangles.npy
+    (max/ds_download/eagle.py:123-144): mesh_pos f32[T,N,2], cells i32[T,F,3], velocity f32[T,N,2], pressure f32[T,N,1].
+    Interior nodes drift smoothly (the bounding box stays put), a few diagonals are flipped per frame, and every frame
+    lists its triangles in a different order with random winding."""
+    pos, tri = make_mesh(kind, mesh_seed, **kw)
+    rng = np.random.default_rng(7919 * mesh_seed + 17)
+    p64 = pos.astype(np.float64)
+    lo, hi = p64.min(axis=0), p64.max(axis=0)
+    ext = hi - lo
+    u = (p64 - lo) / ext
+    bump = np.sin(np.pi * u[:, 0]) * np.sin(np.pi * u[:, 1])          # zero on the bounding box
+    amp = 0.2 * np.sqrt(ext[0] * ext[1] / len(pos))                      # a fraction of the mean node spacing
+    ph = rng.uniform(0, 2 * np.pi, size=4)
+    mesh_pos = np.empty((T, len(pos), 2), dtype=np.float32)
+    cells = np.empty((T, len(tri), 3), dtype=np.int32)
+    for t in range(T):
+        a = 0.31 * t
+        d = np.stack([np.sin(2 * np.pi * u[:, 1] + a + ph[0]) * np.cos(a + ph[1]),
+                      np.cos(2 * np.pi * u[:, 0] - a + ph[2]) * np.sin(a + ph[3])], axis=1)
+        pt = (p64 + amp * bump[:, None] * d).astype(np.float32)
+        mesh_pos[t] = pt
+        tt = _flip_edges(pt.astype(np.float64), tri, rng, flip_frac)
+        tt = _flip_half(tt[rng.permutation(len(tt))], rng)
+        cells[t] = tt
+    vel, prs = make_fields(kind, pos, T, field_seed)
+    return {"mesh_pos": mesh_pos, "cells": cells, "velocity": vel, "pressure": prs}

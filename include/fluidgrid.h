@@ -32,7 +32,7 @@ extern "C" {
 #define FL_E_WORKSPACE (-3)/* workspace too small */
 #define FL_E_ALIGN (-4)    /* pointer not aligned as documented */
 
-#define FL_ABI_VERSION 4
+#define FL_ABI_VERSION 5
 
 /* personality flags of fl_plan_patch_table / fl_interp_patchify */
 #define FL_FLIP_Y 1u          /* airfoil_ds.py:80  -- y axis reversed after padding */
@@ -161,6 +161,29 @@ int fl_rollout_step(const float* d_pred_img, const uint8_t* d_mask, const float*
  * index arithmetic in float32 exactly as NumPy 1.26 evaluates it.  Negative row indices wrap. */
 int fl_grid2mesh(const float* d_grid, const float* d_mesh_pos, float* d_out, int T, int N, int H, int W, int C,
                  float x_min, float y_min, double step_x, double step_y, void* stream);
+
+/* ---- per-frame dynamic meshes --------------------------------------------------------------------
+ * True EAGLE trajectories (max/ds_download/eagle.py:123-144: pointcloud[T,N,2], triangles[T,F,3], VX/VY/PS per frame)
+ * have a different mesh in every frame, so the chain get_mesh_interpolation -> 3 x to_grid -> _pad -> _patch ->
+ * _normalize (src/dataloader/mesh_utils.py:82-106, simple_dataloader.py:104-152,193-216) runs once per FRAME: point
+ * location becomes part of the per-frame loop.  One call handles a window of frames without host synchronisation.
+ *   d_pos f32[T, n_nodes, 2], d_cells i32[T, n_cells, 3], d_velocity f32[T, n_nodes, 2], d_pressure f32[T, n_nodes]
+ *   d_grid_ax/d_grid_ay: ONE grid for all frames (the reference's per-frame grid is the same whenever the frames share
+ *       their bounding box, as EAGLE's fixed domain does); px, py, crop_patches, flags (FL_FLIP_Y, FL_MASK_AWARE_NORM,
+ *       FL_NO_NORM), h_mean/h_std as for fl_plan_patch_table + fl_interp_patchify
+ *   d_states f32[T, L, 3, px, py]; d_mask u8[T, L, px, py] or NULL; d_tri i32[T, L, px, py] or NULL (triangle id of
+ *       every output pixel in that frame's mesh, -1 = outside / padding; same tie-break rule as fl_locate)
+ *   d_status i32[2], written on the stream: [0] = triangles with a node id outside 0 <= i < n_nodes (their frames are
+ *       located without them), [1] = the largest per-frame bin-item count; results are valid iff [0] == 0 and
+ *       [1] <= fl_dyn_capacity(...) for the workspace passed (retry with a larger workspace otherwise)
+ * Workspace: fl_dyn_workspace_bytes(n_frames, n_cells, nx, ny) bytes or more, 256-B aligned. */
+size_t fl_dyn_workspace_bytes(int n_frames, int n_cells, int nx, int ny);
+int fl_dyn_capacity(int n_frames, int n_cells, int nx, int ny, size_t workspace_bytes);
+int fl_dyn_interp_patchify(const float* d_pos, const int32_t* d_cells, const float* d_velocity, const float* d_pressure,
+                           int n_frames, int n_nodes, int n_cells, const float* d_grid_ax, const float* d_grid_ay,
+                           int nx, int ny, int px, int py, int crop_patches, const float* h_mean, const float* h_std,
+                           unsigned flags, float* d_states, uint8_t* d_mask, int32_t* d_tri, int32_t* d_status,
+                           void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---- dataset statistics (max/compute_ds_stats.py:20-34,52-62) ---------------------------------
  * Per-channel (n, mean, M2) of states and of diffs (states[t+1]-states[t]) over unmasked pixels.

@@ -237,6 +237,44 @@ def ds_get(traj, step_num, seq_len, seq_interval=1, resolution=238, patch_size=(
     return out
 
 
+def dynamic_ds_get(mesh_pos, cells, velocity, pressure, step_num, seq_len, seq_interval=1, resolution=238,
+                   patch_size=(16, 16), personality="cylinder", normalize_ds=True, extents=None,
+                   numpy_semantics="1.26", means=None, stds=None):
+    """Per-frame dynamic meshes (max/ds_download/eagle.py:123-144 data fed to the static path): for every frame
+    mesh_utils.py:94-106 on THAT frame's mesh, then simple_dataloader.py:104-121 and the rest of ds_get.  The grid is
+    the one of `extents` (default: the bounding box of the first selected frame, which the reference would use when all
+    frames share it).  -> dict(states (T,L,3,px,py), masks (T,L,px,py), tri_index (T,nx,ny), N_x_patch, N_y_patch)."""
+    frames = list(range(step_num, step_num + seq_len * seq_interval, seq_interval))
+    if extents is None:
+        p0 = np.asarray(mesh_pos[frames[0]])
+        (x_min, y_min), (x_max, y_max) = np.min(p0, axis=0), np.max(p0, axis=0)
+    else:
+        x_min, x_max, y_min, y_max = (F32(e) for e in extents)
+    gx, gy = grid_pos(x_min, x_max, y_min, y_max, resolution, numpy_semantics)
+    out, tris = [], []
+    for t in frames:
+        pos = np.asarray(mesh_pos[t])
+        triang = mpl_tri.Triangulation(pos[:, 0], pos[:, 1], triangles=np.asarray(cells[t]))
+        tri_index = triang.get_trifinder()(gx, gy)
+        prs = np.asarray(pressure)
+        prs = prs if prs.ndim == 3 else prs[:, :, None]
+        state, mask = get_step(triang, tri_index, gx, gy, velocity, prs, t, patch_size, True)
+        out.append(np.concatenate([state, mask[None].astype(state.dtype)], axis=0))
+        tris.append(tri_index)
+    seq = np.stack(out).astype(F32)
+    if personality == "airfoil":
+        seq = np.ascontiguousarray(seq[:, :, :, ::-1])
+        seq = seq[:, :, patch_size[0]:-patch_size[0], patch_size[1]:-patch_size[1]]
+    patches = unfold_patches(seq, patch_size)
+    states = np.ascontiguousarray(patches[:, :-1].transpose(0, 4, 1, 2, 3))
+    masks = np.ascontiguousarray(patches[:, -1].transpose(0, 3, 1, 2))
+    if normalize_ds:
+        states = normalize(states, masks, personality, means, stds)
+    X, Y = seq.shape[2:]
+    return dict(states=states, masks=masks, tri_index=np.stack(tris), N_x_patch=X // patch_size[0],
+                N_y_patch=Y // patch_size[1], grid_x=gx, grid_y=gy)
+
+
 def img_mgn_item(traj, t, window_length, kind, numpy_semantics="1.26"):
     """eagle/Dataloader/IMG_MGN.py:46-128,141-157 -> states float32 (T, H, W, 3) normalised, mask bool (T, H, W)."""
     pos, faces, vel, prs = traj["mesh_pos"], traj["cells"], traj["velocity"], traj["pressure"]

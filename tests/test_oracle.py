@@ -215,3 +215,31 @@ def test_oracle_vs_reference_patch_ops_and_interpolator_live():
     t2, ti2, gx2, gy2 = P.get_mesh_interpolation(tr["mesh_pos"], tr["cells"], 238, "2.x")
     d, m = P.to_grid(tr["pressure"][2][:, 0], gx2, gy2, t2, ti2)
     assert np.array_equal(ti2, tri_index) and np.array_equal(d, d_ref) and np.array_equal(m, m_ref)
+
+
+def test_dynamic_oracle_on_a_repeated_static_mesh_equals_ds_get():
+    """dynamic_ds_get (per-frame meshes) degenerates to ds_get when every frame carries the same mesh."""
+    from fluid_llm_b200 import synth
+    tr = synth.make_trajectory("cylinder", 5, mesh_seed=1, field_seed=2)
+    T = 5
+    dyn = P.dynamic_ds_get(np.repeat(tr["mesh_pos"][None], T, 0), np.repeat(tr["cells"][None], T, 0), tr["velocity"],
+                           tr["pressure"], 1, 3, 1)
+    _, extra = P.ds_get(tr, 1, 3, 1, return_all=True)
+    assert np.array_equal(dyn["states"], extra["states"]) and np.array_equal(dyn["masks"], extra["masks"])
+    assert np.array_equal(dyn["tri_index"][0], extra["tri_index"]) and np.array_equal(dyn["tri_index"][2], extra["tri_index"])
+
+
+def test_dynamic_synth_frames_are_valid_triangulations():
+    """Every frame of the synthetic dynamic trajectory: same bounding box, triangles cover the same area as frame 0's
+    node set allows (edge flips keep the area), trapezoid map and rule-based locator agree."""
+    from fluid_llm_b200 import synth
+    from oracle import mpl_tri
+    tr = synth.make_dynamic_trajectory("cylinder", 4, mesh_seed=2, field_seed=1, flip_frac=0.2)
+    lo, hi = tr["mesh_pos"].min(axis=1), tr["mesh_pos"].max(axis=1)
+    assert (lo == lo[0]).all() and (hi == hi[0]).all()
+    assert (tr["cells"][1] != tr["cells"][0]).any()
+    gx, gy = P.grid_pos(lo[0, 0], hi[0, 0], lo[0, 1], hi[0, 1], 238)
+    for t in range(4):
+        pos = tr["mesh_pos"][t]
+        triang = mpl_tri.Triangulation(pos[:, 0], pos[:, 1], triangles=tr["cells"][t])
+        assert np.array_equal(triang.get_trifinder()(gx, gy), mpl_tri.rule_find_many(triang, gx, gy))
