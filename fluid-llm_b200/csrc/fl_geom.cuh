@@ -46,6 +46,23 @@ __device__ __forceinline__ int rule_eval(double qx, double qy, const double* vx,
     return prio;
 }
 
+// rule_eval without early exits (same result): for warps whose lanes hold unrelated (point, triangle) pairs
+__device__ __forceinline__ int rule_eval_flat(double qx, double qy, const double* vx, const double* vy) {
+    const bool on_vertex = (qx == vx[0] && qy == vy[0]) || (qx == vx[1] && qy == vy[1]) || (qx == vx[2] && qy == vy[2]);
+    bool reject = false, below_on_edge = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int k1 = (k + 1) % 3;
+        const bool end_right = (vx[k1] == vx[k]) ? (vy[k1] > vy[k]) : (vx[k1] > vx[k]);
+        const double lx = end_right ? vx[k] : vx[k1], ly = end_right ? vy[k] : vy[k1];
+        const double rx = end_right ? vx[k1] : vx[k], ry = end_right ? vy[k1] : vy[k];
+        const double s = orient(qx, qy, lx, ly, rx, ry);
+        reject |= end_right ? !(s <= 0.0) : !(s >= 0.0);
+        below_on_edge |= !end_right && s == 0.0;
+    }
+    return on_vertex ? 0 : (reject ? -1 : (below_on_edge ? 1 : 0));
+}
+
 // triangle id of the grid point (qx, qy): the rule over the candidates of its bin; -1 = outside the mesh
 __device__ __forceinline__ int locate_in_bin(const float* __restrict__ pos, const int* __restrict__ tri_v,
                                              const int* __restrict__ items, int kbeg, int kend, double qx, double qy) {

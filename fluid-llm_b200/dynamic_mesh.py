@@ -86,7 +86,7 @@ class DynamicTrajectory:
         return n_bx, n_by
 
     def interp_patchify(self, step_num, seq_len, seq_interval, patch_size, personality: Personality, normalize=True,
-                        means=None, stds=None, want_tri=False):
+                        means=None, stds=None, want_tri=False, force_binned=False):
         """Frames step_num, step_num + interval, ... -> (states (T, L, 3, px, py) f32, mask (T, L, px, py) u8,
         tri (T, L, px, py) i32 or None).  One host synchronisation at the end (the status words)."""
         last = int(step_num) + (int(seq_len) - 1) * int(seq_interval)
@@ -102,7 +102,7 @@ class DynamicTrajectory:
             pos, cells, vel, prs = (t[sel].contiguous() for t in (self.pos, self.cells, self.velocity, self.pressure))
         T = int(pos.shape[0])
         flags = (FL_FLIP_Y if personality.flip_y else 0) | (FL_MASK_AWARE_NORM if personality.mask_aware_norm else 0) \
-            | (0 if normalize else FL_NO_NORM)
+            | (0 if normalize else FL_NO_NORM) | (_lib.FL_FORCE_GATHER if force_binned else 0)
         m = (ctypes.c_float * 3)(*(means if means is not None else personality.means))
         s = (ctypes.c_float * 3)(*(stds if stds is not None else personality.stds))
         with torch.cuda.device(dev):

@@ -275,7 +275,7 @@ def make_dynamic_trajectory(kind: str, T: int, mesh_seed: int = 0, field_seed: i
                       np.cos(2 * np.pi * u[:, 0] - a + ph[2]) * np.sin(a + ph[3])], axis=1)
         pt = (p64 + amp * bump[:, None] * d).astype(np.float32)
         mesh_pos[t] = pt
-        tt = _flip_edges(pt.astype(np.float64), tri, rng, flip_frac)
+        tt = _flip_edges(pt.astype(np.float64), tri, rng, flip_frac) if flip_frac > 0 else tri
         tt = _flip_half(tt[rng.permutation(len(tt))], rng)
         cells[t] = tt
     vel, prs = make_fields(kind, pos, T, field_seed)

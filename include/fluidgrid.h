@@ -170,7 +170,8 @@ int fl_grid2mesh(const float* d_grid, const float* d_mesh_pos, float* d_out, int
  *   d_pos f32[T, n_nodes, 2], d_cells i32[T, n_cells, 3], d_velocity f32[T, n_nodes, 2], d_pressure f32[T, n_nodes]
  *   d_grid_ax/d_grid_ay: ONE grid for all frames (the reference's per-frame grid is the same whenever the frames share
  *       their bounding box, as EAGLE's fixed domain does); px, py, crop_patches, flags (FL_FLIP_Y, FL_MASK_AWARE_NORM,
- *       FL_NO_NORM), h_mean/h_std as for fl_plan_patch_table + fl_interp_patchify
+ *       FL_NO_NORM), h_mean/h_std as for fl_plan_patch_table + fl_interp_patchify; FL_FORCE_GATHER (testing) selects
+ *       the binned form even when the shared-memory rasterising form would fit
  *   d_states f32[T, L, 3, px, py]; d_mask u8[T, L, px, py] or NULL; d_tri i32[T, L, px, py] or NULL (triangle id of
  *       every output pixel in that frame's mesh, -1 = outside / padding; same tie-break rule as fl_locate)
  *   d_status i32[2], written on the stream: [0] = triangles with a node id outside 0 <= i < n_nodes (their frames are

@@ -74,6 +74,21 @@ def test_dynamic_equals_static_path_on_a_static_mesh():
     s_st, m_st, tab = interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 0, T, 1, PATCH, CYLINDER)
     assert torch.equal(s_dyn, s_st) and torch.equal(m_dyn, m_st)
     assert torch.equal(tri_dyn[0].reshape(-1), tab.idx[:, 3])
+    # the binned form (grids too large for shared memory) gives the same bits as the rasterising form
+    s_bin, m_bin, tri_bin = dt.interp_patchify(0, T, 1, PATCH, CYLINDER, want_tri=True, force_binned=True)
+    assert torch.equal(s_bin, s_dyn) and torch.equal(m_bin, m_dyn) and torch.equal(tri_bin, tri_dyn)
+
+
+def test_dynamic_binned_and_raster_forms_agree_on_moving_meshes():
+    from fluid_llm_b200.dynamic_mesh import DynamicTrajectory
+    from fluid_llm_b200.field_path import AIRFOIL, CYLINDER
+    for kind, pers in (("eagle", CYLINDER), ("cylinder", AIRFOIL)):
+        tr = synth.make_dynamic_trajectory(kind, 9, mesh_seed=4, field_seed=6, flip_frac=0.1)
+        dt = DynamicTrajectory(tr["mesh_pos"], tr["cells"], tr["velocity"], tr["pressure"])
+        a = dt.interp_patchify(0, 9, 1, PATCH, pers, want_tri=True)
+        b = dt.interp_patchify(0, 9, 1, PATCH, pers, want_tri=True, force_binned=True)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
 
 
 def test_dynamic_five_tuple_and_errors():
