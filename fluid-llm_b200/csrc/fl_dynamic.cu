@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_dyn_raster_interp(
             const int lane = tid & 31, t = base + lane;
             float fx0 = 0.f, fy0 = 0.f, fx1 = 0.f, fy1 = 0.f, fx2 = 0.f, fy2 = 0.f;
             int ix0 = 0, iy0 = 0, h = 1, cnt = 0;
+            unsigned hmagic = 0;            // ceil(2^32 / h): r / h == umulhi(r, hmagic) for r * h < 2^32 (0 when h == 1)
             if (t < n_cells) {
                 const int v0 = cells[3 * t], v1 = cells[3 * t + 1], v2 = cells[3 * t + 2];
                 if ((unsigned)v0 >= (unsigned)n_nodes || (unsigned)v1 >= (unsigned)n_nodes || (unsigned)v2 >= (unsigned)n_nodes) {
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_dyn_raster_interp(
                     h = lo - iy0;
                     cnt = (w > 0 && h > 0) ? w * h : 0;
                     if (h < 1) h = 1;
+                    hmagic = h == 1 ? 0u : 0xffffffffu / (unsigned)h + 1u;
                 }
             }
             int incl = cnt;
@@ -169,13 +171,14 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_dyn_raster_interp(
                 const bool act = j < total;
                 k = act ? k : 31;
                 const int r = j - (__shfl_sync(0xffffffffu, incl, k) - __shfl_sync(0xffffffffu, cnt, k));
+                const unsigned omagic = __shfl_sync(0xffffffffu, hmagic, k);
                 const int oh = __shfl_sync(0xffffffffu, h, k), oix0 = __shfl_sync(0xffffffffu, ix0, k), oiy0 = __shfl_sync(0xffffffffu, iy0, k);
                 double vx[3], vy[3];
                 vx[0] = (double)__shfl_sync(0xffffffffu, fx0, k); vy[0] = (double)__shfl_sync(0xffffffffu, fy0, k);
                 vx[1] = (double)__shfl_sync(0xffffffffu, fx1, k); vy[1] = (double)__shfl_sync(0xffffffffu, fy1, k);
                 vx[2] = (double)__shfl_sync(0xffffffffu, fx2, k); vy[2] = (double)__shfl_sync(0xffffffffu, fy2, k);
                 if (act) {
-                    const int rx = (int)((unsigned)r / (unsigned)oh), ry = r - rx * oh;
+                    const int rx = oh == 1 ? r : (int)__umulhi((unsigned)r, omagic), ry = r - rx * oh;
                     const int ix = oix0 + rx, iy = oiy0 + ry;
                     const int p = rule_eval_flat((double)s_ax[ix], (double)s_ay[iy], vx, vy);
                     if (p >= 0) atomicMin(&s_cell[ix * g.ny + iy], ((unsigned)p << 31) | (unsigned)(base + k));
