@@ -37,6 +37,20 @@ void fl_set_error(const char* fmt, ...);
         }                                                                              \
     } while (0)
 
+// cudaFuncSetAttribute is per device: one of these per call site remembers which devices already have it
+// (setting it twice is harmless, so a race between two threads on first use only costs a repeated call)
+struct FlOncePerDevice {
+    unsigned long long done[4] = {0, 0, 0, 0};     // up to 256 devices
+    bool first_use() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 256) return true;
+        const unsigned long long bit = 1ull << (d & 63);
+        if (done[d >> 6] & bit) return false;
+        done[d >> 6] |= bit;
+        return true;
+    }
+};
+
 static inline size_t fl_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // streaming (read-once / write-once) 128-bit accesses that do not allocate in L1

@@ -297,11 +297,8 @@ extern "C" int fl_dyn_interp_patchify(const float* d_pos, const int32_t* d_cells
     int stage_fields = 0;
     const size_t smem = raster_smem_bytes(nx, ny, n_nodes, &stage_fields);
     if (smem <= 227 * 1024 && n_cells < 0x7fffffff && !(flags & FL_FORCE_GATHER)) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            FL_CUDA(cudaFuncSetAttribute(k_dyn_raster_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_set = true;
-        }
+        static FlOncePerDevice attr;
+        if (attr.first_use()) FL_CUDA(cudaFuncSetAttribute(k_dyn_raster_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         FL_CUDA(cudaMemsetAsync(d_status, 0, 2 * sizeof(int32_t), st));
         const int grid = n_frames < FL_SM_COUNT ? n_frames : FL_SM_COUNT;      // one persistent CTA per SM
         k_dyn_raster_interp<<<grid, RS_THREADS, smem, st>>>(d_pos, d_cells, d_velocity, d_pressure, n_frames, n_nodes, n_cells,

@@ -242,11 +242,8 @@ int launch_gemm(const void* A, const void* B, int M, int N, int K, const Epilogu
     rc = make_map(&mb, B, N, K, BN);
     if (rc) return rc;
     const size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16;
-    static bool attr = false;
-    if (!attr) {
-        FL_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    static FlOncePerDevice attr;
+    if (attr.first_use()) FL_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((M + BM - 1) / BM, N / BN);
     k_gemm_tcgen05<BN><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, M, N, K, ep);
     FL_LAUNCH_CHECK();

@@ -480,11 +480,10 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             const int gpt = (max_frames + TF - 1) / TF;
             const long n_items = (long)gpt * n_traj;
             const size_t smem = (size_t)TF * frame_bytes;
-            static bool attr_set = false;
-            if (!attr_set) {
+            static FlOncePerDevice attr;
+            if (attr.first_use()) {
                 FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
                 FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                attr_set = true;
             }
             int ppx_shift = -1;
             for (int b = 0; b < 16; ++b) if ((1 << b) == ppx) ppx_shift = b;

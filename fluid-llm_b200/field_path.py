@@ -229,13 +229,20 @@ class HostPipeline:
         torch.cuda.current_stream(dev).synchronize()      # slot buffers were zero-filled on the current stream
         self._first = True
 
-    def run(self, h_velocity, h_pressure, h_states, h_mask=None, normalize=True):
+    def run(self, h_velocity, h_pressure, h_states=None, h_mask=None, normalize=True, on_device=None):
         """h_velocity[i] (T, N_i, 2) / h_pressure[i] (T, N_i, 1) pinned host tensors -> h_states[i] (n_frames, L, 3, px, py),
-        h_mask[i] (n_frames, L, px, py) pinned host tensors.  Everything is enqueued asynchronously."""
-        if len(h_velocity) != self.n or len(h_pressure) != self.n or len(h_states) != self.n:
+        h_mask[i] (n_frames, L, px, py) pinned host tensors.  Everything is enqueued asynchronously.
+
+        A consumer that lives on the GPU passes `on_device(i, states, mask)` instead of host outputs: it is called with
+        the device slot of trajectory i while the compute stream is current (enqueue the consumer's work there; the slot
+        is reused `depth` trajectories later)."""
+        if len(h_velocity) != self.n or len(h_pressure) != self.n:
             raise ValueError(f"expected {self.n} trajectories")
-        if self.want_mask and (h_mask is None or len(h_mask) != self.n):
-            raise ValueError("h_mask missing")
+        if on_device is None:
+            if h_states is None or len(h_states) != self.n:
+                raise ValueError(f"expected {self.n} host output tensors")
+            if self.want_mask and (h_mask is None or len(h_mask) != self.n):
+                raise ValueError("h_mask missing")
         with torch.cuda.device(self.device):
             for i, (tr, batch, sl) in enumerate(self.items):
                 with torch.cuda.stream(self.s_in):
@@ -249,12 +256,15 @@ class HostPipeline:
                     if not self._first or i >= self.depth:
                         self.s_run.wait_event(sl["out_done"])         # the slot's previous outputs have left
                     batch.run(self.personality, normalize)
+                    if on_device is not None:
+                        on_device(i, sl["states"][0], sl["mask"][0] if self.want_mask else None)
                     sl["run_done"].record(self.s_run)
                 with torch.cuda.stream(self.s_out):
                     self.s_out.wait_event(sl["run_done"])
-                    h_states[i].copy_(sl["states"][0], non_blocking=True)
-                    if self.want_mask:
-                        h_mask[i].copy_(sl["mask"][0], non_blocking=True)
+                    if on_device is None:
+                        h_states[i].copy_(sl["states"][0], non_blocking=True)
+                        if self.want_mask:
+                            h_mask[i].copy_(sl["mask"][0], non_blocking=True)
                     sl["out_done"].record(self.s_out)
             self._first = False
 

@@ -186,6 +186,16 @@ def test_host_pipeline_matches_oracle():
             assert np.array_equal(hm[i].numpy().astype(bool), ex["masks"].astype(bool)), (rep, i)
     with pytest.raises(ValueError):
         pipe.run(hv[:2], hp[:2], hs[:2], hm[:2])
+    # a consumer on the GPU: called per trajectory with the device slot, on the compute stream
+    got = {}
+
+    def consume(i, states, mask):
+        got[i] = (states.clone(), mask.clone())
+
+    pipe.run(hv, hp, on_device=consume)
+    torch.cuda.synchronize()
+    for i, ex in enumerate(want):
+        assert np.array_equal(got[i][0].cpu().numpy(), ex["states"]) and np.array_equal(got[i][1].cpu().numpy().astype(bool), ex["masks"].astype(bool))
 
 
 def test_custom_mean_std():
