@@ -8,20 +8,23 @@
 //   out = bf16( h @ W2^T + b2 ) + (x_emb[p0] + y_emb[p1] + t_emb[p2])  512 -> llm_dim, fp32 result
 // One kernel, C[M,N] = epilogue(A[M,K] . B[N,K]^T), used twice; nn.Linear weights are [N,K] K-major already.
 //
-// Kernel anatomy (one 128 x BLOCK_N output tile per CTA, 192 threads):
+// Kernel anatomy (one 128 x BLOCK_N output tile per CTA, 320 threads):
 //   warp 0     TMA producer: cp.async.bulk.tensor.2d of the A (128 x 64) and B (BLOCK_N x 64) bf16 tiles,
 //              128-byte swizzle, into a 2-stage shared-memory ring (two CTAs per SM) (full/empty mbarriers)
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BLOCK_N,
 //              K = 16) four times per stage, tcgen05.commit releases the stage / signals the epilogue
-//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per call) -> bias, bf16 rounding, LeakyReLU or
-//              positional-embedding add -> global
+//   warps 2-9  epilogue (two warps per TMEM lane quarter, half of the columns each): tcgen05.ld (32 lanes x 32
+//              columns per call) -> bias, bf16 rounding, LeakyReLU or positional-embedding add -> global
 #include "fl_common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
 
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 2, GEMM_THREADS = 192;   // 2 stages = 96 KB: two CTAs per SM, one runs its epilogue while the other feeds the tensor core
+constexpr int BM = 128, BK = 64, GEMM_THREADS = 320;
+// operand ring depth: 2 stages = 96 KB, two CTAs per SM (one runs its epilogue while the other feeds the tensor core) when
+// the grid has more tiles than SMs; 4 stages, one CTA per SM, when every tile has an SM to itself (the k-loop is then
+// bound by TMA latency, which a deeper ring hides)
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(uint64_t* b, unsigned n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(n) : "memory"); }
@@ -87,8 +90,8 @@ struct Epilogue {
     int max_x, max_y, max_t;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, STAGES <= 2 ? 2 : 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K, Epilogue ep) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
@@ -99,7 +102,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, kblocks = K / BK;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, kblocks = K / BK;   // the N tiles of one row block are neighbours: its A tile is fetched from HBM once
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
@@ -142,16 +145,17 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             umma_commit(tmem_full);                             // accumulator complete
         }
-    } else {                                                    // ===== epilogue warps 2..5 =====
+    } else {                                                    // ===== epilogue warps 2..9 =====
         mb_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+        const int ew = warp - 2, chalf = ew >> 2;               // two warps per lane quarter: each takes half of the columns
         // The accumulator arrives one ROW per lane (32 columns per tcgen05.ld).  Written out like that, every
         // store instruction would touch 32 different rows; instead each 32 x 32 block goes through a per-warp,
         // XOR-swizzled shared tile (the operand ring is free once tmem_full has fired) and leaves with 8 lanes
         // per row: 128-bit accesses, 4 full rows per instruction, bias / activation / positional add applied there.
-        float4* tile = (float4*)(smem + q * 4096);              // [32 rows][8 float4], index r*8 + (c4 ^ (r & 7))
-        long long* s_pos = (long long*)(smem + 16384 + q * 768);   // [32 rows][3] clamped position ids
+        float4* tile = (float4*)(smem + ew * 4096);             // [32 rows][8 float4], index r*8 + (c4 ^ (r & 7))
+        int* s_pos = (int*)(smem + 32768 + ew * 384);           // [32 rows][3] clamped position ids
         if (ep.pos_ids) {
             const int row = m0 + q * 32 + lane;
             long long p0 = 0, p1 = 0, p2 = 0;
@@ -161,10 +165,10 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 p1 = p1 < 0 ? 0 : (p1 >= ep.max_y ? ep.max_y - 1 : p1);
                 p2 = p2 < 0 ? 0 : (p2 >= ep.max_t ? ep.max_t - 1 : p2);
             }
-            s_pos[3 * lane] = p0; s_pos[3 * lane + 1] = p1; s_pos[3 * lane + 2] = p2;
+            s_pos[3 * lane] = (int)p0; s_pos[3 * lane + 1] = (int)p1; s_pos[3 * lane + 2] = (int)p2;
         }
         const int c4 = lane & 7, rsub = lane >> 3;              // after the transpose: this lane's float4 column and row phase
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
             __syncwarp();                                       // the previous block has been read out of the tile
@@ -174,26 +178,34 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int col = n0 + c + 4 * c4;
             const float4 b4 = __ldg((const float4*)(ep.bias + col));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = 4 * i + rsub, row = m0 + q * 32 + r;
-                const float4 a = tile[r * 8 + (c4 ^ (r & 7))];
-                if (row >= M) continue;
-                float x[4] = {a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w};
+            for (int ih = 0; ih < 2; ++ih) {                    // 4 rows at a time: their 12 table loads are in flight together
+                float4 e[4];
+                if (!ep.leaky && ep.pos_ids) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = __bfloat162float(__float2bfloat16_rn(x[j]));      // the Linear's bf16 output
-                if (ep.leaky) {
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(x[0] > 0.f ? x[0] : 0.01f * x[0], x[1] > 0.f ? x[1] : 0.01f * x[1]);
-                    __nv_bfloat162 hi = __floats2bfloat162_rn(x[2] > 0.f ? x[2] : 0.01f * x[2], x[3] > 0.f ? x[3] : 0.01f * x[3]);
-                    *(uint2*)((__nv_bfloat16*)ep.out + (size_t)row * N + col) = make_uint2(*(unsigned*)&lo, *(unsigned*)&hi);
-                } else {
-                    if (ep.pos_ids) {
+                    for (int ii = 0; ii < 4; ++ii) {
+                        const int r = 4 * (4 * ih + ii) + rsub;
                         const float4 e0 = __ldg((const float4*)(ep.x_emb + (size_t)s_pos[3 * r] * N + col));
                         const float4 e1 = __ldg((const float4*)(ep.y_emb + (size_t)s_pos[3 * r + 1] * N + col));
                         const float4 e2 = __ldg((const float4*)(ep.t_emb + (size_t)s_pos[3 * r + 2] * N + col));
-                        x[0] += (e0.x + e1.x) + e2.x; x[1] += (e0.y + e1.y) + e2.y;
-                        x[2] += (e0.z + e1.z) + e2.z; x[3] += (e0.w + e1.w) + e2.w;
+                        e[ii] = make_float4((e0.x + e1.x) + e2.x, (e0.y + e1.y) + e2.y, (e0.z + e1.z) + e2.z, (e0.w + e1.w) + e2.w);
                     }
-                    fl_stg_stream4((float4*)((float*)ep.out + (size_t)row * N + col), make_float4(x[0], x[1], x[2], x[3]));
+                }
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {
+                    const int r = 4 * (4 * ih + ii) + rsub, row = m0 + q * 32 + r;
+                    const float4 a = tile[r * 8 + (c4 ^ (r & 7))];
+                    if (row >= M) continue;
+                    float x[4] = {a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] = __bfloat162float(__float2bfloat16_rn(x[j]));      // the Linear's bf16 output
+                    if (ep.leaky) {
+                        __nv_bfloat162 lo = __floats2bfloat162_rn(x[0] > 0.f ? x[0] : 0.01f * x[0], x[1] > 0.f ? x[1] : 0.01f * x[1]);
+                        __nv_bfloat162 hi = __floats2bfloat162_rn(x[2] > 0.f ? x[2] : 0.01f * x[2], x[3] > 0.f ? x[3] : 0.01f * x[3]);
+                        *(uint2*)((__nv_bfloat16*)ep.out + (size_t)row * N + col) = make_uint2(*(unsigned*)&lo, *(unsigned*)&hi);
+                    } else {
+                        if (ep.pos_ids) { x[0] += e[ii].x; x[1] += e[ii].y; x[2] += e[ii].z; x[3] += e[ii].w; }
+                        fl_stg_stream4((float4*)((float*)ep.out + (size_t)row * N + col), make_float4(x[0], x[1], x[2], x[3]));
+                    }
                 }
             }
         }
@@ -234,6 +246,8 @@ int make_map(CUtensorMap* map, const void* base, int rows, int cols, int box_row
     return FL_OK;
 }
 
+static size_t gemm_smem_bytes(int bn, int stages) { return (size_t)stages * (BM * BK * 2 + bn * BK * 2) + (2 * stages + 1) * 8 + 16; }
+
 template <int BN>
 int launch_gemm(const void* A, const void* B, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
     CUtensorMap ma, mb;
@@ -241,11 +255,16 @@ int launch_gemm(const void* A, const void* B, int M, int N, int K, const Epilogu
     if (rc) return rc;
     rc = make_map(&mb, B, N, K, BN);
     if (rc) return rc;
-    const size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16;
+    dim3 grid(N / BN, (M + BM - 1) / BM);
     static FlOncePerDevice attr;
-    if (attr.first_use()) FL_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((M + BM - 1) / BM, N / BN);
-    k_gemm_tcgen05<BN><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, M, N, K, ep);
+    if (attr.first_use()) {
+        FL_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(BN, 2)));
+        FL_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<BN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(BN, 4)));
+    }
+    if ((long)grid.x * grid.y <= FL_SM_COUNT)
+        k_gemm_tcgen05<BN, 4><<<grid, GEMM_THREADS, gemm_smem_bytes(BN, 4), st>>>(ma, mb, M, N, K, ep);
+    else
+        k_gemm_tcgen05<BN, 2><<<grid, GEMM_THREADS, gemm_smem_bytes(BN, 2), st>>>(ma, mb, M, N, K, ep);
     FL_LAUNCH_CHECK();
     return FL_OK;
 }
@@ -266,6 +285,7 @@ extern "C" int fl_patch_embed(const void* d_x_bf16, const void* d_w1_bf16, const
                               const long long* d_pos_ids, int max_x, int max_y, int max_t, void* d_hidden_bf16, float* d_out,
                               int n_tokens, int in_dim, int hid_dim, int out_dim, void* stream) {
     FL_REQUIRE(d_x_bf16 && d_w1_bf16 && d_b1 && d_w2_bf16 && d_b2 && d_hidden_bf16 && d_out, FL_E_ARG, "fl_patch_embed: null pointer");
+    FL_REQUIRE(n_tokens <= 65535 * BM, FL_E_ARG, "fl_patch_embed: at most %d tokens per call", 65535 * BM);
     FL_REQUIRE(n_tokens > 0 && in_dim % BK == 0 && hid_dim % BK == 0 && hid_dim % 256 == 0 && out_dim % 256 == 0, FL_E_ARG,
                "fl_patch_embed: dims (%d -> %d -> %d) must be multiples of 64 (K) and 256 (N)", in_dim, hid_dim, out_dim);
     FL_REQUIRE((d_pos_ids == nullptr) || (d_x_emb && d_y_emb && d_t_emb && max_x > 0 && max_y > 0 && max_t > 0), FL_E_ARG,

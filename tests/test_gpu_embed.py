@@ -18,7 +18,7 @@ def _reference(x, w1, b1, w2, b2, tabs, ids):
     return y + (xe[ids[..., 0]] + ye[ids[..., 1]] + te[ids[..., 2]])   # positional_embeddings.py:32-37
 
 
-@pytest.mark.parametrize("n_tokens", [128, 4800, 1000])
+@pytest.mark.parametrize("n_tokens", [128, 4800, 1000, 20000])    # 20000: more tiles than SMs -> the 2-stage, 2-CTA/SM variant
 def test_patch_embed_matches_autocast_reference(n_tokens):
     from fluid_llm_b200.patch_embed import PatchEmbedder
     g = torch.Generator(device="cuda").manual_seed(n_tokens)
@@ -58,3 +58,19 @@ def test_patch_embed_shapes_and_errors():
         emb(x, torch.zeros(2, 3, 60, 3, dtype=torch.int64, device="cuda"))      # no tables
     with pytest.raises(ValueError):
         PatchEmbedder(w1, b1, torch.randn(768, 256), b2)
+
+
+def test_graphed_patch_embed_replays_the_same_bits():
+    from fluid_llm_b200.patch_embed import PatchEmbedder
+    g = torch.Generator(device="cuda").manual_seed(5)
+    w1, b1 = torch.randn(512, 768, device="cuda", generator=g) * 0.03, torch.randn(512, device="cuda", generator=g) * 0.1
+    w2, b2 = torch.randn(768, 512, device="cuda", generator=g) * 0.04, torch.randn(768, device="cuda", generator=g) * 0.1
+    tabs = [torch.randn(m, 768, device="cuda", generator=g) * 0.03 for m in (20, 10, 30)]
+    emb = PatchEmbedder(w1, b1, w2, b2, *tabs)
+    ge = emb.graphed(600, with_position_ids=True)
+    for seed in (1, 2):
+        x = torch.randn(10, 60, 3, 16, 16, device="cuda", generator=g)
+        ids = torch.stack([torch.randint(0, m, (10, 60), device="cuda", generator=g) for m in (20, 10, 30)], dim=-1)
+        assert torch.equal(ge(x, ids), emb(x, ids).reshape(600, 768))
+    with pytest.raises(ValueError):
+        ge(x)

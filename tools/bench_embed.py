@@ -41,8 +41,13 @@ def main():
 
         flops = 2.0 * n * (768 * 512 + 512 * 768)
         t_ours, t_ours_bf16, t_ref = timeit(lambda: emb(x, ids)), timeit(lambda: emb(xb, ids)), timeit(ref)
+        g32, g16 = emb.graphed(n, True, torch.float32), emb.graphed(n, True, torch.bfloat16)
+        g32.x.copy_(x); g32.ids.copy_(ids); g16.x.copy_(xb); g16.ids.copy_(ids)
+        assert torch.equal(g32.replay(), emb(x, ids)) and torch.equal(g16.replay(), emb(xb, ids))
+        t_g32, t_g16 = timeit(g32.replay), timeit(g16.replay)
         print(f"tokens {n:7d}: ours {t_ours * 1e3:8.1f} us ({flops / t_ours / 1e9:7.1f} TFLOP/s)  bf16-in {t_ours_bf16 * 1e3:8.1f} us "
-              f"({flops / t_ours_bf16 / 1e9:7.1f} TFLOP/s)  torch autocast {t_ref * 1e3:8.1f} us ({flops / t_ref / 1e9:7.1f} TFLOP/s)")
+              f"({flops / t_ours_bf16 / 1e9:7.1f} TFLOP/s)  graphed {t_g32 * 1e3:8.1f} / bf16-in {t_g16 * 1e3:8.1f} us "
+              f"({flops / t_g16 / 1e9:7.1f} TFLOP/s)  torch autocast {t_ref * 1e3:8.1f} us ({flops / t_ref / 1e9:7.1f} TFLOP/s)")
 
 
 if __name__ == "__main__":
