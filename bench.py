@@ -227,6 +227,12 @@ def run_ours(args, w):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    try:        # run (and first-touch the pinned host buffers) on the CPUs next to this rank's GPU
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     fluid_llm_b200.load()

@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64, GEMM_THREADS = 320;
+constexpr int BM = 128, BK = 64, GEMM_THREADS = 320, STAGES = 4, EPI_WARPS = 8, EPI_SCRATCH = 4096 + 192;
 // operand ring depth: 2 stages = 96 KB, two CTAs per SM (one runs its epilogue while the other feeds the tensor core) when
 // the grid has more tiles than SMs; 4 stages, one CTA per SM, when every tile has an SM to itself (the k-loop is then
 // bound by TMA latency, which a deeper ring hides)
@@ -90,29 +90,34 @@ struct Epilogue {
     int max_x, max_y, max_t;
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(GEMM_THREADS, STAGES <= 2 ? 2 : 1)
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N, int K, Epilogue ep) {
     extern __shared__ __align__(1024) unsigned char smem[];
     constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     unsigned char* sa = smem;                                   // [STAGES][128 x 64 bf16], 1024-byte aligned tiles
     unsigned char* sb = smem + STAGES * A_BYTES;                // [STAGES][BN x 64 bf16]
-    uint64_t* full = (uint64_t*)(smem + STAGES * (A_BYTES + B_BYTES));
+    unsigned char* scratch = smem + STAGES * (A_BYTES + B_BYTES);   // epilogue: 8 warps x (4 KB transpose tile + 192 B position ids)
+    uint64_t* full = (uint64_t*)(scratch + EPI_WARPS * EPI_SCRATCH);
     uint64_t* empty = full + STAGES;
-    uint64_t* tmem_full = empty + STAGES;
-    uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+    uint64_t* tmem_full = empty + STAGES;                       // [2] accumulator buffer complete
+    uint64_t* tmem_empty = tmem_full + 2;                       // [2] accumulator buffer drained by the epilogue
+    uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN, kblocks = K / BK;   // the N tiles of one row block are neighbours: its A tile is fetched from HBM once
+    const int kblocks = K / BK, n_tiles = N / BN, tiles = n_tiles * ((M + BM - 1) / BM);
+    const uint32_t tmem_cols = tiles > (int)gridDim.x ? 2 * BN : BN;      // a second accumulator buffer only if this CTA gets a second tile
+    // persistent: CTA b takes tiles b, b + grid, ...; the N tiles of one row block are consecutive tile ids, so they run on
+    // neighbouring SMs at the same time and the row block's A tile is fetched from HBM once
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], 1); }
-        mb_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) { mb_init(&tmem_full[i], 1); mb_init(&tmem_empty[i], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
-    if (warp == 2) {   // TMEM allocation: BN fp32 accumulator columns (power of two >= 32), by one warp
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(BN) : "memory");
+    if (warp == 2) {   // TMEM allocation: two accumulator buffers of BN fp32 columns each, by one warp
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -122,88 +127,113 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
     if (warp == 0) {
         if (lane == 0) {                                        // ===== TMA producer =====
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % STAGES, round = kb / STAGES;
-                mb_wait(&empty[s], (round & 1) ^ 1);            // slot free (first round passes immediately)
-                mb_expect_tx(&full[s], A_BYTES + B_BYTES);
-                tma_load_2d(sa + s * A_BYTES, &map_a, &full[s], kb * BK, m0);
-                tma_load_2d(sb + s * B_BYTES, &map_b, &full[s], kb * BK, n0);
+            int it = 0;                                         // k-block counter across tiles: the ring never drains between tiles
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % STAGES, round = it / STAGES;
+                    mb_wait(&empty[s], (round & 1) ^ 1);        // slot free (first round passes immediately)
+                    mb_expect_tx(&full[s], A_BYTES + B_BYTES);
+                    tma_load_2d(sa + s * A_BYTES, &map_a, &full[s], kb * BK, m0);
+                    tma_load_2d(sb + s * B_BYTES, &map_b, &full[s], kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                        // ===== MMA issuer =====
             const uint32_t idesc = umma_idesc(BN);
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % STAGES, round = kb / STAGES;
-                mb_wait(&full[s], round & 1);
+            int it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
+                const int buf = j & 1;
+                mb_wait(&tmem_empty[buf], ((j >> 1) & 1) ^ 1);  // the epilogue has drained this buffer (first two tiles pass)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t da = umma_desc(sa + s * A_BYTES), db = umma_desc(sb + s * B_BYTES);
+                const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const int s = it % STAGES, round = it / STAGES;
+                    mb_wait(&full[s], round & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t da = umma_desc(sa + s * A_BYTES), db = umma_desc(sb + s * B_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)               // 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the address field
-                    umma_f16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                umma_commit(&empty[s]);                         // frees the stage once these MMAs have read it
+                    for (int k = 0; k < BK / 16; ++k)           // 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the address field
+                        umma_f16(acc, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty[s]);                     // frees the stage once these MMAs have read it
+                }
+                umma_commit(&tmem_full[buf]);                   // accumulator complete
             }
-            umma_commit(tmem_full);                             // accumulator complete
         }
     } else {                                                    // ===== epilogue warps 2..9 =====
-        mb_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                                 // a warp may only touch TMEM lanes 32*(warp%4) .. +31
         const int ew = warp - 2, chalf = ew >> 2;               // two warps per lane quarter: each takes half of the columns
         // The accumulator arrives one ROW per lane (32 columns per tcgen05.ld).  Written out like that, every
         // store instruction would touch 32 different rows; instead each 32 x 32 block goes through a per-warp,
-        // XOR-swizzled shared tile (the operand ring is free once tmem_full has fired) and leaves with 8 lanes
-        // per row: 128-bit accesses, 4 full rows per instruction, bias / activation / positional add applied there.
-        float4* tile = (float4*)(smem + ew * 4096);             // [32 rows][8 float4], index r*8 + (c4 ^ (r & 7))
-        int* s_pos = (int*)(smem + 32768 + ew * 384);           // [32 rows][3] clamped position ids
-        if (ep.pos_ids) {
-            const int row = m0 + q * 32 + lane;
-            long long p0 = 0, p1 = 0, p2 = 0;
-            if (row < M) {
-                p0 = ep.pos_ids[3 * (size_t)row]; p1 = ep.pos_ids[3 * (size_t)row + 1]; p2 = ep.pos_ids[3 * (size_t)row + 2];
-                p0 = p0 < 0 ? 0 : (p0 >= ep.max_x ? ep.max_x - 1 : p0);
-                p1 = p1 < 0 ? 0 : (p1 >= ep.max_y ? ep.max_y - 1 : p1);
-                p2 = p2 < 0 ? 0 : (p2 >= ep.max_t ? ep.max_t - 1 : p2);
-            }
-            s_pos[3 * lane] = (int)p0; s_pos[3 * lane + 1] = (int)p1; s_pos[3 * lane + 2] = (int)p2;
-        }
+        // XOR-swizzled shared tile and leaves with 8 lanes per row: 128-bit accesses, 4 full rows per instruction,
+        // bias / activation / positional add applied there.
+        float4* tile_s = (float4*)(scratch + ew * EPI_SCRATCH); // [32 rows][8 float4], index r*8 + (c4 ^ (r & 7))
+        short* s_pos = (short*)(scratch + ew * EPI_SCRATCH + 4096);   // [32 rows][3] clamped position ids
         const int c4 = lane & 7, rsub = lane >> 3;              // after the transpose: this lane's float4 column and row phase
-        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            __syncwarp();                                       // the previous block has been read out of the tile
-#pragma unroll
-            for (int j = 0; j < 8; ++j) tile[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            __syncwarp();
-            const int col = n0 + c + 4 * c4;
-            const float4 b4 = __ldg((const float4*)(ep.bias + col));
-#pragma unroll
-            for (int ih = 0; ih < 2; ++ih) {                    // 4 rows at a time: their 12 table loads are in flight together
-                float4 e[4];
-                if (!ep.leaky && ep.pos_ids) {
-#pragma unroll
-                    for (int ii = 0; ii < 4; ++ii) {
-                        const int r = 4 * (4 * ih + ii) + rsub;
-                        const float4 e0 = __ldg((const float4*)(ep.x_emb + (size_t)s_pos[3 * r] * N + col));
-                        const float4 e1 = __ldg((const float4*)(ep.y_emb + (size_t)s_pos[3 * r + 1] * N + col));
-                        const float4 e2 = __ldg((const float4*)(ep.t_emb + (size_t)s_pos[3 * r + 2] * N + col));
-                        e[ii] = make_float4((e0.x + e1.x) + e2.x, (e0.y + e1.y) + e2.y, (e0.z + e1.z) + e2.z, (e0.w + e1.w) + e2.w);
-                    }
+        int j = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++j) {
+            const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN, buf = j & 1;
+            if (ep.pos_ids) {
+                const int row = m0 + q * 32 + lane;
+                long long p0 = 0, p1 = 0, p2 = 0;
+                if (row < M) {
+                    p0 = ep.pos_ids[3 * (size_t)row]; p1 = ep.pos_ids[3 * (size_t)row + 1]; p2 = ep.pos_ids[3 * (size_t)row + 2];
+                    p0 = p0 < 0 ? 0 : (p0 >= ep.max_x ? ep.max_x - 1 : p0);
+                    p1 = p1 < 0 ? 0 : (p1 >= ep.max_y ? ep.max_y - 1 : p1);
+                    p2 = p2 < 0 ? 0 : (p2 >= ep.max_t ? ep.max_t - 1 : p2);
                 }
+                __syncwarp();                                   // the previous tile's rows have been consumed
+                s_pos[3 * lane] = (short)p0; s_pos[3 * lane + 1] = (short)p1; s_pos[3 * lane + 2] = (short)p2;
+            }
+            mb_wait(&tmem_full[buf], (j >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem_base + (uint32_t)(buf * BN) + ((uint32_t)(q * 32) << 16);
+            for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
+                // the positional-table rows of this block's 8 output rows per lane: all 24 loads leave before the accumulator
+                // read below, so one L2 round trip covers them and the TMEM read together
+                const int col = n0 + c + 4 * c4;
+                float4 e[8];
+                if (!ep.leaky && ep.pos_ids) {
+                    float4 e0[8], e1[8], e2[8];
 #pragma unroll
-                for (int ii = 0; ii < 4; ++ii) {
-                    const int r = 4 * (4 * ih + ii) + rsub, row = m0 + q * 32 + r;
-                    const float4 a = tile[r * 8 + (c4 ^ (r & 7))];
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + rsub;
+                        e0[i] = __ldg((const float4*)(ep.x_emb + (size_t)s_pos[3 * r] * N + col));
+                        e1[i] = __ldg((const float4*)(ep.y_emb + (size_t)s_pos[3 * r + 1] * N + col));
+                        e2[i] = __ldg((const float4*)(ep.t_emb + (size_t)s_pos[3 * r + 2] * N + col));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        e[i] = make_float4((e0[i].x + e1[i].x) + e2[i].x, (e0[i].y + e1[i].y) + e2[i].y, (e0[i].z + e1[i].z) + e2[i].z,
+                                           (e0[i].w + e1[i].w) + e2[i].w);
+                }
+                const float4 b4 = __ldg((const float4*)(ep.bias + col));
+                float v[32];
+                tmem_ld32(acc + (uint32_t)c, v);
+                if (c + 32 >= (chalf + 1) * (BN / 2)) {         // last read of this buffer by this warp: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&tmem_empty[buf])) : "memory");
+                }
+                __syncwarp();                                   // the previous block has been read out of the tile
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) tile_s[lane * 8 + (jj ^ (lane & 7))] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + rsub, row = m0 + q * 32 + r;
+                    const float4 a = tile_s[r * 8 + (c4 ^ (r & 7))];
                     if (row >= M) continue;
                     float x[4] = {a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) x[j] = __bfloat162float(__float2bfloat16_rn(x[j]));      // the Linear's bf16 output
+                    for (int jj = 0; jj < 4; ++jj) x[jj] = __bfloat162float(__float2bfloat16_rn(x[jj]));      // the Linear's bf16 output
                     if (ep.leaky) {
                         __nv_bfloat162 lo = __floats2bfloat162_rn(x[0] > 0.f ? x[0] : 0.01f * x[0], x[1] > 0.f ? x[1] : 0.01f * x[1]);
                         __nv_bfloat162 hi = __floats2bfloat162_rn(x[2] > 0.f ? x[2] : 0.01f * x[2], x[3] > 0.f ? x[3] : 0.01f * x[3]);
                         *(uint2*)((__nv_bfloat16*)ep.out + (size_t)row * N + col) = make_uint2(*(unsigned*)&lo, *(unsigned*)&hi);
                     } else {
-                        if (ep.pos_ids) { x[0] += e[ii].x; x[1] += e[ii].y; x[2] += e[ii].z; x[3] += e[ii].w; }
+                        if (ep.pos_ids) { x[0] += e[i].x; x[1] += e[i].y; x[2] += e[i].z; x[3] += e[i].w; }
                         fl_stg_stream4((float4*)((float*)ep.out + (size_t)row * N + col), make_float4(x[0], x[1], x[2], x[3]));
                     }
                 }
@@ -212,7 +242,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
 }
 
 __global__ void k_cast_bf16(const float4* __restrict__ in, uint2* __restrict__ out, long n4) {
@@ -246,7 +276,7 @@ int make_map(CUtensorMap* map, const void* base, int rows, int cols, int box_row
     return FL_OK;
 }
 
-static size_t gemm_smem_bytes(int bn, int stages) { return (size_t)stages * (BM * BK * 2 + bn * BK * 2) + (2 * stages + 1) * 8 + 16; }
+static size_t gemm_smem_bytes(int bn) { return (size_t)STAGES * (BM * BK * 2 + bn * BK * 2) + EPI_WARPS * EPI_SCRATCH + (2 * STAGES + 4) * 8 + 16; }
 
 template <int BN>
 int launch_gemm(const void* A, const void* B, int M, int N, int K, const Epilogue& ep, cudaStream_t st) {
@@ -255,16 +285,12 @@ int launch_gemm(const void* A, const void* B, int M, int N, int K, const Epilogu
     if (rc) return rc;
     rc = make_map(&mb, B, N, K, BN);
     if (rc) return rc;
-    dim3 grid(N / BN, (M + BM - 1) / BM);
+    const size_t smem = gemm_smem_bytes(BN);
     static FlOncePerDevice attr;
-    if (attr.first_use()) {
-        FL_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(BN, 2)));
-        FL_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<BN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes(BN, 4)));
-    }
-    if ((long)grid.x * grid.y <= FL_SM_COUNT)
-        k_gemm_tcgen05<BN, 4><<<grid, GEMM_THREADS, gemm_smem_bytes(BN, 4), st>>>(ma, mb, M, N, K, ep);
-    else
-        k_gemm_tcgen05<BN, 2><<<grid, GEMM_THREADS, gemm_smem_bytes(BN, 2), st>>>(ma, mb, M, N, K, ep);
+    if (attr.first_use()) FL_CUDA(cudaFuncSetAttribute(k_gemm_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long tiles = (long)(N / BN) * ((M + BM - 1) / BM);
+    const int grid = tiles < FL_SM_COUNT ? (int)tiles : FL_SM_COUNT;          // persistent: one CTA per SM
+    k_gemm_tcgen05<BN><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, M, N, K, ep);
     FL_LAUNCH_CHECK();
     return FL_OK;
 }

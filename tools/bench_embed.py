@@ -32,7 +32,12 @@ def main():
     for n in sizes:
         x = torch.randn(n, 768, device="cuda")
         xb = x.bfloat16()
-        ids = torch.stack([torch.randint(0, m, (n,), device="cuda") for m in (20, 10, 30)], dim=1)
+        if os.environ.get("EMBED_RANDOM_IDS"):
+            ids = torch.stack([torch.randint(0, m, (n,), device="cuda") for m in (20, 10, 30)], dim=1)   # worst case: no table-row reuse
+        else:
+            # the ids the data path produces (simple_dataloader.py:218-226): 60 patches per frame, frames in order
+            a = torch.arange(n, device="cuda")
+            ids = torch.stack([a % 15, (a // 15) % 4, (a // 60) % 30], dim=1)
 
         def ref():
             with torch.autocast("cuda", dtype=torch.bfloat16):
