@@ -173,14 +173,35 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_dyn_raster_interp(
                 const int r = j - (__shfl_sync(0xffffffffu, incl, k) - __shfl_sync(0xffffffffu, cnt, k));
                 const unsigned omagic = __shfl_sync(0xffffffffu, hmagic, k);
                 const int oh = __shfl_sync(0xffffffffu, h, k), oix0 = __shfl_sync(0xffffffffu, ix0, k), oiy0 = __shfl_sync(0xffffffffu, iy0, k);
-                double vx[3], vy[3];
-                vx[0] = (double)__shfl_sync(0xffffffffu, fx0, k); vy[0] = (double)__shfl_sync(0xffffffffu, fy0, k);
-                vx[1] = (double)__shfl_sync(0xffffffffu, fx1, k); vy[1] = (double)__shfl_sync(0xffffffffu, fy1, k);
-                vx[2] = (double)__shfl_sync(0xffffffffu, fx2, k); vy[2] = (double)__shfl_sync(0xffffffffu, fy2, k);
+                const float ax0 = __shfl_sync(0xffffffffu, fx0, k), ay0 = __shfl_sync(0xffffffffu, fy0, k);
+                const float ax1 = __shfl_sync(0xffffffffu, fx1, k), ay1 = __shfl_sync(0xffffffffu, fy1, k);
+                const float ax2 = __shfl_sync(0xffffffffu, fx2, k), ay2 = __shfl_sync(0xffffffffu, fy2, k);
                 if (act) {
                     const int rx = oh == 1 ? r : (int)__umulhi((unsigned)r, omagic), ry = r - rx * oh;
                     const int ix = oix0 + rx, iy = oiy0 + ry;
-                    const int p = rule_eval_flat((double)s_ax[ix], (double)s_ay[iy], vx, vy);
+                    const float qx = s_ax[ix], qy = s_ay[iy];
+                    // fp32 screen: cross(edge, point - start) for the three edges of the counter-clockwise triangle.  Every
+                    // input is an fp32 number, so the computed value is within 2^-22 (|a| + |b|) of the exact one; with a
+                    // 4x margin a value beyond the bound has the exact sign, which is all the tie-break rule looks at when
+                    // the point is on no edge.  Clearly outside one edge -> rejected; clearly inside all three -> accepted
+                    // with full priority; anything else (a point on or next to an edge or vertex) -> the exact fp64 rule.
+                    float e_min, m_in;      // smallest (value - bound) and smallest (value + bound) over the edges
+                    {
+                        const float a0 = (ax1 - ax0) * (qy - ay0), b0 = (ay1 - ay0) * (qx - ax0);
+                        const float a1 = (ax2 - ax1) * (qy - ay1), b1 = (ay2 - ay1) * (qx - ax1);
+                        const float a2 = (ax0 - ax2) * (qy - ay2), b2 = (ay0 - ay2) * (qx - ax2);
+                        const float c = 9.5367431640625e-07f;         // 2^-20
+                        const float t0 = c * (fabsf(a0) + fabsf(b0)), t1 = c * (fabsf(a1) + fabsf(b1)), t2 = c * (fabsf(a2) + fabsf(b2));
+                        const float e0 = a0 - b0, e1 = a1 - b1, e2 = a2 - b2;
+                        e_min = fminf(fminf(e0 - t0, e1 - t1), e2 - t2);
+                        m_in = fminf(fminf(e0 + t0, e1 + t1), e2 + t2);
+                    }
+                    int p = -1;
+                    if (e_min > 0.f) p = 0;                          // strictly inside, beyond rounding doubt
+                    else if (!(m_in < 0.f)) {                        // not clearly outside: exact evaluation
+                        const double vx[3] = {(double)ax0, (double)ax1, (double)ax2}, vy[3] = {(double)ay0, (double)ay1, (double)ay2};
+                        p = rule_eval_flat((double)qx, (double)qy, vx, vy);
+                    }
                     if (p >= 0) atomicMin(&s_cell[ix * g.ny + iy], ((unsigned)p << 31) | (unsigned)(base + k));
                 }
             }

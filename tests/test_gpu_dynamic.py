@@ -6,9 +6,10 @@ import pytest
 import torch
 
 from fluid_llm_b200 import synth
+from oracle import mpl_tri
 from oracle import pipeline as P
 
-from helpers import PATCH
+from helpers import PATCH, tie_mesh
 
 pytestmark = pytest.mark.gpu
 
@@ -141,3 +142,28 @@ def test_dynamic_long_window_chunks():
     for r in (0, 31, 32, 63, 64, reps - 1):
         assert np.array_equal(s[r], want["states"]), r
     assert np.array_equal(mask.cpu().numpy().reshape(reps, 4, *mask.shape[1:])[reps - 1].astype(bool), want["masks"].astype(bool))
+
+
+@pytest.mark.parametrize("force_binned", [False, True])
+def test_dynamic_tie_breaks_on_the_hand_built_mesh(force_binned):
+    """Grid points on vertices, on horizontal / vertical / oblique edges, on the boundary and in holes: both forms of the
+    dynamic path must return the trapezoid map's triangle for every one of them (small patches so the 9 x 9 ... 33 x 33
+    grids are not all padding)."""
+    from fluid_llm_b200.dynamic_mesh import DynamicTrajectory
+    from fluid_llm_b200.field_path import CYLINDER
+    pos, tris = tie_mesh()
+    rng = np.random.default_rng(3)
+    T = 3
+    vel = rng.standard_normal((T, len(pos), 2)).astype(np.float32)
+    prs = rng.standard_normal((T, len(pos))).astype(np.float32)
+    perm = [tris, tris[::-1].copy(), tris[rng.permutation(len(tris))]]          # triangle ids differ per frame
+    for res in (9, 5, 17, 33):
+        dt = DynamicTrajectory(np.repeat(pos[None], T, 0), np.stack(perm), vel, prs, grid_res=res)
+        _, mask, tri = dt.interp_patchify(0, T, 1, (8, 4), CYLINDER, want_tri=True, force_binned=force_binned)
+        for t in range(T):
+            triang = mpl_tri.Triangulation(pos[:, 0], pos[:, 1], triangles=perm[t])
+            gx, gy = P.grid_pos(pos[:, 0].min(), pos[:, 0].max(), pos[:, 1].min(), pos[:, 1].max(), res)
+            want = triang.get_trifinder()(gx, gy)
+            got = _patch_order_tri(want[None], (8, 4), 0, False)[0]
+            assert np.array_equal(tri[t].cpu().numpy(), got), (res, t)
+            assert np.array_equal(mask[t].cpu().numpy().astype(bool), got < 0)
