@@ -167,3 +167,46 @@ def test_dynamic_tie_breaks_on_the_hand_built_mesh(force_binned):
             got = _patch_order_tri(want[None], (8, 4), 0, False)[0]
             assert np.array_equal(tri[t].cpu().numpy(), got), (res, t)
             assert np.array_equal(mask[t].cpu().numpy().astype(bool), got < 0)
+
+
+@pytest.mark.parametrize("force_binned", [False, True])
+def test_dynamic_writes_stay_inside_the_output_buffers(force_binned):
+    """Straight through the C ABI with guard bands around every output: nothing outside [T, L, ...] may change."""
+    import ctypes
+    from fluid_llm_b200._lib import FL_FORCE_GATHER, check, load, ptr, stream_ptr
+    from fluid_llm_b200.mesh_utils import _grid_axes
+    tr = synth.make_dynamic_trajectory("cylinder", 5, mesh_seed=5, field_seed=7)
+    T, N, F = 5, tr["mesh_pos"].shape[1], tr["cells"].shape[1]
+    lo, hi = tr["mesh_pos"][0].min(axis=0), tr["mesh_pos"][0].max(axis=0)
+    ax, ay = _grid_axes(float(lo[0]), float(hi[0]), float(lo[1]), float(hi[1]), 238, "1.26")
+    nx, ny = len(ax), len(ay)
+    L = ((nx + 15) // 16) * ((ny + 15) // 16)
+    G = 4096                                                    # guard elements on both sides
+    dev = "cuda"
+    pos = torch.from_numpy(tr["mesh_pos"]).to(dev)
+    cells = torch.from_numpy(tr["cells"]).to(dev)
+    vel = torch.from_numpy(tr["velocity"]).to(dev)
+    prs = torch.from_numpy(np.ascontiguousarray(tr["pressure"][:, :, 0])).to(dev)
+    ax_d, ay_d = torch.from_numpy(ax).to(dev), torch.from_numpy(ay).to(dev)
+    n_out = T * L * 256
+    states = torch.full((G + 3 * n_out + G,), 777.0, dtype=torch.float32, device=dev)
+    mask = torch.full((G + n_out + G,), 77, dtype=torch.uint8, device=dev)
+    tri = torch.full((G + n_out + G,), -777, dtype=torch.int32, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    lib = load()
+    ws = torch.empty(int(lib.fl_dyn_workspace_bytes(T, F, nx, ny)) + 256, dtype=torch.uint8, device=dev)
+    ws_tail = ws[-256:]
+    ws_tail.fill_(99)
+    m = (ctypes.c_float * 3)(0.823, 0.0005865, 0.04763)
+    s = (ctypes.c_float * 3)(0.275, 0.275, 0.275)
+    check(lib.fl_dyn_interp_patchify(ptr(pos), ptr(cells), ptr(vel), ptr(prs), T, N, F, ptr(ax_d), ptr(ay_d), nx, ny, 16, 16, 0, m, s,
+                                     FL_FORCE_GATHER if force_binned else 0, ptr(states[G:]), ptr(mask[G:]), ptr(tri[G:]),
+                                     ptr(status), ptr(ws), ws.numel() - 256, stream_ptr()), "fl_dyn_interp_patchify")
+    torch.cuda.synchronize()
+    assert int(status[0]) == 0
+    for buf, fill in ((states, 777.0), (mask, 77), (tri, -777)):
+        assert bool((buf[:G] == fill).all()) and bool((buf[-G:] == fill).all())
+    assert bool((ws_tail == 99).all())
+    inner = states[G:-G]
+    assert bool(torch.isfinite(inner).all()) and not bool((inner == 777.0).any())          # every output element was written
+    assert not bool((mask[G:-G] == 77).any()) and not bool((tri[G:-G] == -777).any())

@@ -74,3 +74,24 @@ def test_graphed_patch_embed_replays_the_same_bits():
         assert torch.equal(ge(x, ids), emb(x, ids).reshape(600, 768))
     with pytest.raises(ValueError):
         ge(x)
+
+
+@pytest.mark.parametrize("n_tokens", [130, 19000])          # a ragged last row block; more tiles than SMs
+def test_patch_embed_writes_stay_inside_the_output_buffers(n_tokens):
+    from fluid_llm_b200._lib import check, load, ptr, stream_ptr
+    g = torch.Generator(device="cuda").manual_seed(11)
+    G = 8192
+    x = (torch.randn(n_tokens, 768, device="cuda", generator=g)).bfloat16()
+    w1 = (torch.randn(512, 768, device="cuda", generator=g) * 0.03).bfloat16()
+    w2 = (torch.randn(768, 512, device="cuda", generator=g) * 0.04).bfloat16()
+    b1, b2 = torch.zeros(512, device="cuda"), torch.zeros(768, device="cuda")
+    hidden = torch.full((G + n_tokens * 512 + G,), 3.0, dtype=torch.bfloat16, device="cuda")
+    out = torch.full((G + n_tokens * 768 + G,), 777.0, dtype=torch.float32, device="cuda")
+    check(load().fl_patch_embed(ptr(x), ptr(w1), ptr(b1), ptr(w2), ptr(b2), None, None, None, None, 0, 0, 0, ptr(hidden[G:]), ptr(out[G:]),
+                                n_tokens, 768, 512, 768, stream_ptr()), "fl_patch_embed")
+    torch.cuda.synchronize()
+    assert bool((out[:G] == 777.0).all()) and bool((out[-G:] == 777.0).all())
+    assert bool((hidden[:G] == 3.0).all()) and bool((hidden[-G:] == 3.0).all())
+    ref = torch.nn.functional.leaky_relu((x.float() @ w1.float().T).bfloat16().float(), 0.01).bfloat16()
+    y = (ref.float() @ w2.float().T).bfloat16().float()
+    torch.testing.assert_close(out[G:-G].view(n_tokens, 768), y, rtol=2e-2, atol=2e-2)
