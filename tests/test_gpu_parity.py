@@ -354,3 +354,34 @@ def test_c_abi_called_directly_as_integration_md_shows():
     traj.vel_stride = N          # too small for [N, 2]
     assert lib.fl_interp_patchify(ctypes.byref(traj), 1, tab.n_patches, 16, 16, mean, std, 0, None) == -1
     assert b"stride" in lib.fl_last_error()
+
+
+@pytest.mark.parametrize("kind,force_gather", [("cylinder", False), ("airfoil", False), ("eagle", False), ("cylinder", True)])
+def test_interp_patchify_writes_stay_inside_the_output_buffers(kind, force_gather):
+    """Outputs placed inside guarded buffers (TrajBatch(out=...)): the staged and the gather kernel write every element of
+    [n_traj, n_frames, L, ...] and nothing around it."""
+    from fluid_llm_b200.field_path import AIRFOIL, CYLINDER, DeviceTrajectory, TrajBatch
+    pers = AIRFOIL if kind == "airfoil" else CYLINDER
+    plan, _, _ = _plan(kind)
+    tr = trajectory(kind)
+    vel, prs = tr["velocity"], tr["pressure"]
+    if kind == "airfoil":
+        from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
+        nmask, _, _ = crop_airfoil_mesh(tr["mesh_pos"], tr["cells"])
+        vel, prs = vel[:, nmask], prs[:, nmask]
+    tab = plan.patch_table(PATCH, pers.crop_patches, pers.flip_y)
+    trajs = [DeviceTrajectory(vel, prs, plan) for _ in range(2)]
+    n_traj, T, L, G = 2, 7, tab.n_patches, 4096
+    n = n_traj * T * L * 256
+    sbuf = torch.full((G + 3 * n + G,), 777.0, dtype=torch.float32, device="cuda")
+    mbuf = torch.full((G + n + G,), 77, dtype=torch.uint8, device="cuda")
+    states = sbuf[G:G + 3 * n].view(n_traj, T, L, 3, 16, 16)
+    mask = mbuf[G:G + n].view(n_traj, T, L, 16, 16)
+    batch = TrajBatch(trajs, [tab, tab], [0, 1], 1, T, out=(states, mask))
+    batch.run(pers, force_gather=force_gather)
+    torch.cuda.synchronize()
+    assert bool((sbuf[:G] == 777.0).all()) and bool((sbuf[-G:] == 777.0).all())
+    assert bool((mbuf[:G] == 77).all()) and bool((mbuf[-G:] == 77).all())
+    assert not bool((states == 777.0).any()) and not bool((mask == 77).any())
+    _, extra = oracle_ds_get(kind, 1, T, 1)
+    assert np.array_equal(states[1].cpu().numpy(), extra["states"])
