@@ -11,7 +11,7 @@
 namespace {
 
 constexpr int NACC = 6;          // state ch0..2, diff ch0..2
-constexpr int CHUNK_T = 32;      // frames per CTA chunk
+constexpr int CHUNK_T = 64;      // frames per CTA chunk
 
 struct Agg { double n, mean, m2; };
 
@@ -39,55 +39,92 @@ __device__ __forceinline__ Agg warp_merge(Agg a) {
     return a;
 }
 
-// grid: x = pixel tiles (256 pixels each over L*ppx), y = frame chunks
-__global__ void __launch_bounds__(256) k_stats_partial(const float* __restrict__ states, const uint8_t* __restrict__ mask,
-                                                       int T, int L, int ppx, double* __restrict__ partials) {
+// grid: x = pixel tiles (256 pixels each over L*ppx), y = frame chunks.  The loop is bound by memory latency, not by
+// arithmetic: four CTAs per SM (<= 64 registers: the shifts are kept as the fp32 numbers they are) and the loads of the
+// frame after next are issued before the current pair is accumulated.
+__global__ void __launch_bounds__(256, 4) k_stats_partial(const float* __restrict__ states, const uint8_t* __restrict__ mask,
+                                                          int T, int L, int ppx, double* __restrict__ partials) {
     const long npix = (long)L * ppx;
     const long pix = (long)blockIdx.x * 256 + threadIdx.x;
     const int t_begin = blockIdx.y * CHUNK_T;              // pairs (t, t+1) for t in [t_begin, t_end)
     const int t_end = min(T - 1, t_begin + CHUNK_T);
     // per-thread running sums around a per-thread shift (first accepted sample), fp64
     double cnt[2] = {0.0, 0.0};
-    double shift[NACC], s1[NACC], s2[NACC];
+    float shift_f[NACC];
+    double s1[NACC], s2[NACC];
 #pragma unroll
-    for (int a = 0; a < NACC; ++a) { shift[a] = 0.0; s1[a] = 0.0; s2[a] = 0.0; }
+    for (int a = 0; a < NACC; ++a) { shift_f[a] = 0.f; s1[a] = 0.0; s2[a] = 0.0; }
     if (pix < npix && t_begin < t_end) {
         const long l = pix / ppx, k = pix - l * ppx;
-        auto addr = [&](int t, int c) { return (((long)t * L + l) * 3 + c) * ppx + k; };
-        float prev[3];
+        const size_t fstride = (size_t)L * 3 * ppx, mstride = (size_t)L * ppx;
+        const float* sp = states + ((size_t)t_begin * L + l) * 3 * ppx + k;          // channel c at sp[c * ppx]
+        const uint8_t* mp = mask + ((size_t)t_begin * L + l) * ppx + k;
+        // three frame buffers rotate through the roles (previous, current, being loaded) with the loop unrolled three
+        // times, so no register move has to wait for the load in flight
+        float f0[3], f1[3], f2[3] = {0.f, 0.f, 0.f};
+        uint8_t m1, m2 = 1, m0 = 1;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) prev[c] = __ldg(states + addr(t_begin, c));
+        for (int c = 0; c < 3; ++c) { f0[c] = __ldg(sp + (size_t)c * ppx); f1[c] = __ldg(sp + fstride + (size_t)c * ppx); }
+        m1 = __ldg(mp + mstride);
         bool first = true;
-        for (int t = t_begin; t < t_end; ++t) {
-            float cur[3];
+        auto fetch = [&](float (&dst)[3], uint8_t& mdst, int t) {       // frame t + 2, needed by the next step
+            if (t + 1 < t_end) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) cur[c] = __ldg(states + addr(t + 1, c));
-            if (!mask[((long)(t + 1) * L + l) * ppx + k]) {   // masks[1:] (simple_dataloader.py:100)
+                for (int c = 0; c < 3; ++c) dst[c] = __ldg(sp + 2 * fstride + (size_t)c * ppx);
+                mdst = __ldg(mp + 2 * mstride);
+            }
+            sp += fstride; mp += mstride;
+        };
+        auto accumulate = [&](const float (&prev)[3], const float (&cur)[3], uint8_t mcur) {
+            if (!mcur) {                                    // masks[1:] (simple_dataloader.py:100)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    double sv = (double)prev[c], dv = (double)__fsub_rn(cur[c], prev[c]);
-                    if (first) { shift[c] = sv; shift[3 + c] = dv; }
-                    double a = sv - shift[c], b = dv - shift[3 + c];
+                    const float dvf = __fsub_rn(cur[c], prev[c]);
+                    if (first) { shift_f[c] = prev[c]; shift_f[3 + c] = dvf; }
+                    const double a = (double)prev[c] - (double)shift_f[c], b = (double)dvf - (double)shift_f[3 + c];
                     s1[c] += a; s2[c] += a * a;
                     s1[3 + c] += b; s2[3 + c] += b * b;
                 }
                 first = false;
                 cnt[0] += 1.0;
             }
-#pragma unroll
-            for (int c = 0; c < 3; ++c) prev[c] = cur[c];
+        };
+        int t = t_begin;
+        while (true) {
+            fetch(f2, m2, t); accumulate(f0, f1, m1); if (++t >= t_end) break;
+            fetch(f0, m0, t); accumulate(f1, f2, m2); if (++t >= t_end) break;
+            fetch(f1, m1, t); accumulate(f2, f0, m0); if (++t >= t_end) break;
         }
     }
+    double shift[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) shift[a] = (double)shift_f[a];
+    // Per-warp reduction without a division per lane: every lane re-bases its sums to one shift of the warp (the shift of
+    // the first lane that accepted a sample), then the three sums are added across the lanes in a fixed butterfly order.
+    //   sum(x - K) = s1 + n (shift - K),   sum (x - K)^2 = s2 + 2 (shift - K) s1 + n (shift - K)^2
+    // One lane per warp turns the totals into (n, mean, M2); the eight warp aggregates are merged with Chan's formula.
     __shared__ Agg sm[NACC][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned have = __ballot_sync(0xffffffffu, cnt[0] > 0.0);
+    const int src = have ? __ffs(have) - 1 : 0;
+    double n_w = cnt[0];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) n_w += __shfl_xor_sync(0xffffffffu, n_w, o);
 #pragma unroll
     for (int a = 0; a < NACC; ++a) {
-        Agg g;
-        g.n = cnt[0];
-        g.mean = g.n > 0.0 ? shift[a] + s1[a] / g.n : 0.0;
-        g.m2 = g.n > 0.0 ? s2[a] - s1[a] * s1[a] / g.n : 0.0;
-        g = warp_merge(g);
-        if (lane == 0) sm[a][warp] = g;
+        const double K = __shfl_sync(0xffffffffu, shift[a], src);
+        const double d = shift[a] - K;
+        double t1 = cnt[0] > 0.0 ? s1[a] + cnt[0] * d : 0.0;
+        double t2 = cnt[0] > 0.0 ? s2[a] + 2.0 * d * s1[a] + cnt[0] * d * d : 0.0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { t1 += __shfl_xor_sync(0xffffffffu, t1, o); t2 += __shfl_xor_sync(0xffffffffu, t2, o); }
+        if (lane == 0) {
+            Agg g;
+            g.n = n_w;
+            g.mean = n_w > 0.0 ? K + t1 / n_w : 0.0;
+            g.m2 = n_w > 0.0 ? fmax(t2 - t1 * t1 / n_w, 0.0) : 0.0;
+            sm[a][warp] = g;
+        }
     }
     __syncthreads();
     if (threadIdx.x < NACC) {
@@ -98,17 +135,29 @@ __global__ void __launch_bounds__(256) k_stats_partial(const float* __restrict__
     }
 }
 
-// fixed-shape pairwise tree over the partials: deterministic, one warp per accumulator
-__global__ void k_stats_merge(const double* __restrict__ parts, int n_parts, double* __restrict__ out) {
-    const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;   // blockDim = NACC*32
+// fixed-shape tree over the partials: deterministic.  MERGE_WARPS warps per accumulator; every lane folds a contiguous
+// slice in order, a butterfly merges the lanes, and the warps' results are folded in warp order.
+constexpr int MERGE_WARPS = 5;
+__global__ void __launch_bounds__(NACC * MERGE_WARPS * 32) k_stats_merge(const double* __restrict__ parts, int n_parts,
+                                                                         double* __restrict__ out) {
+    __shared__ Agg sm[NACC][MERGE_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = warp / MERGE_WARPS, sub = warp - a * MERGE_WARPS;
+    const int slot = sub * 32 + lane, slots = MERGE_WARPS * 32;
     Agg g{0.0, 0.0, 0.0};
-    const int per = (n_parts + 31) / 32;                       // contiguous slice per lane, in order
-    for (int i = lane * per; i < min(n_parts, (lane + 1) * per); ++i) {
+    const int per = (n_parts + slots - 1) / slots;             // contiguous slice per lane, in order
+    for (int i = slot * per; i < min(n_parts, (slot + 1) * per); ++i) {
         const double* p = parts + ((long)i * NACC + a) * 3;
         g = chan(g, Agg{p[0], p[1], p[2]});
     }
     g = warp_merge(g);
-    if (lane == 0) { out[a * 3] = g.n; out[a * 3 + 1] = g.mean; out[a * 3 + 2] = g.m2; }
+    if (lane == 0) sm[a][sub] = g;
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        Agg r = sm[threadIdx.x][0];
+        for (int w = 1; w < MERGE_WARPS; ++w) r = chan(r, sm[threadIdx.x][w]);
+        out[threadIdx.x * 3] = r.n; out[threadIdx.x * 3 + 1] = r.mean; out[threadIdx.x * 3 + 2] = r.m2;
+    }
 }
 
 constexpr size_t MAX_PARTS = 1 << 16;
@@ -130,14 +179,14 @@ extern "C" int fl_ds_stats(const float* d_states, const uint8_t* d_mask, int T, 
     cudaStream_t st = (cudaStream_t)stream;
     k_stats_partial<<<dim3(gx, gy), 256, 0, st>>>(d_states, d_mask, T, L, ppx, (double*)d_workspace);
     FL_LAUNCH_CHECK();
-    k_stats_merge<<<1, NACC * 32, 0, st>>>((const double*)d_workspace, (int)parts, d_agg);
+    k_stats_merge<<<1, NACC * MERGE_WARPS * 32, 0, st>>>((const double*)d_workspace, (int)parts, d_agg);
     FL_LAUNCH_CHECK();
     return FL_OK;
 }
 
 extern "C" int fl_stats_merge(const double* d_parts, int n_parts, double* d_out, void* stream) {
     FL_REQUIRE(d_parts && d_out && n_parts > 0, FL_E_ARG, "fl_stats_merge: bad arguments");
-    k_stats_merge<<<1, NACC * 32, 0, (cudaStream_t)stream>>>(d_parts, n_parts, d_out);
+    k_stats_merge<<<1, NACC * MERGE_WARPS * 32, 0, (cudaStream_t)stream>>>(d_parts, n_parts, d_out);
     FL_LAUNCH_CHECK();
     return FL_OK;
 }
