@@ -13,37 +13,39 @@
 
 namespace {
 
-// unit = 16 bytes; upr = units per patch row (py * elem_size / 16)
-template <bool TO_IMG>
-__global__ void k_permute16(const uint4* __restrict__ src, uint4* __restrict__ dst, long total_units, int n_bx, int n_by,
-                            int C, int px, int upr) {
-    long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= total_units) return;
+// unit = 16 bytes; upr = units per patch row (py * elem_size / 16).  IDX = unsigned when every unit index fits 32 bits
+// (a 64-bit division costs an order of magnitude more instructions than the copy it addresses).
+template <bool TO_IMG, typename IDX>
+__global__ void __launch_bounds__(256) k_permute16(const uint4* __restrict__ src, uint4* __restrict__ dst, long total_units,
+                                                   int n_bx, int n_by, int C, int px, int upr) {
+    const long u0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u0 >= total_units) return;
+    const IDX u = (IDX)u0;
+    const IDX row_units = (IDX)n_by * (IDX)upr;
     // decompose the IMAGE-side unit index: [b][c][X][Yu] with Yu over n_by*upr units
-    long img_u, pat_u;
+    IDX img_u, pat_u;
     if (TO_IMG) {
         img_u = u;
-        int yu = (int)(u % ((long)n_by * upr));
-        long r = u / ((long)n_by * upr);
-        int X = (int)(r % ((long)n_bx * px));
-        r /= (long)n_bx * px;
-        int c = (int)(r % C);
-        long b = r / C;
-        int by = yu / upr, ju = yu - by * upr, bx = X / px, i = X - bx * px;
+        IDX r = u / row_units;
+        const IDX yu = u - r * row_units;
+        const IDX X = r % (IDX)(n_bx * px);
+        r /= (IDX)(n_bx * px);
+        const IDX c = r % (IDX)C, b = r / (IDX)C;
+        const IDX by = yu / (IDX)upr, ju = yu - by * (IDX)upr, bx = X / (IDX)px, i = X - bx * (IDX)px;
         pat_u = ((((b * n_bx + bx) * n_by + by) * C + c) * px + i) * upr + ju;
     } else {
         pat_u = u;
-        int ju = (int)(u % upr);
-        long r = u / upr;
-        int i = (int)(r % px); r /= px;
-        int c = (int)(r % C); r /= C;
-        int by = (int)(r % n_by); r /= n_by;
-        int bx = (int)(r % n_bx);
-        long b = r / n_bx;
-        img_u = (((b * C + c) * n_bx + bx) * px + i) * ((long)n_by * upr) + (long)by * upr + ju;
+        IDX r = u / (IDX)upr;
+        const IDX ju = u - r * (IDX)upr;
+        const IDX i = r % (IDX)px; r /= (IDX)px;
+        const IDX c = r % (IDX)C; r /= (IDX)C;
+        const IDX by = r % (IDX)n_by; r /= (IDX)n_by;
+        const IDX bx = r % (IDX)n_bx, b = r / (IDX)n_bx;
+        img_u = (((b * C + c) * n_bx + bx) * px + i) * row_units + by * upr + ju;
     }
-    if (TO_IMG) dst[img_u] = __ldg(src + pat_u);
-    else dst[pat_u] = __ldg(src + img_u);
+    // read-once / write-once: keep both streams out of L1
+    const float4 v = fl_ldg_stream4((const float4*)src + (TO_IMG ? pat_u : img_u));
+    fl_stg_stream4((float4*)dst + (TO_IMG ? img_u : pat_u), v);
 }
 
 // scalar fallback (row bytes not a multiple of 16, or unaligned pointers)
@@ -130,8 +132,12 @@ int permute(const void* src, void* dst, int B, int n_bx, int n_by, int C, int px
     if (vec) {
         int upr = py * es / 16;
         long units = total * es / 16;
-        k_permute16<TO_IMG><<<(unsigned)((units + 255) / 256), 256, 0, st>>>((const uint4*)src, (uint4*)dst, units, n_bx,
-                                                                             n_by, C, px, upr);
+        if (units < 0x7fffffffL)
+            k_permute16<TO_IMG, unsigned><<<(unsigned)((units + 255) / 256), 256, 0, st>>>((const uint4*)src, (uint4*)dst, units,
+                                                                                           n_bx, n_by, C, px, upr);
+        else
+            k_permute16<TO_IMG, unsigned long long><<<(unsigned)((units + 255) / 256), 256, 0, st>>>((const uint4*)src, (uint4*)dst,
+                                                                                                     units, n_bx, n_by, C, px, upr);
     } else if (es == 4) {
         k_permute_elem<uint32_t, TO_IMG><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const uint32_t*)src, (uint32_t*)dst,
                                                                                        total, n_bx, n_by, C, px, py);
