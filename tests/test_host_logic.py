@@ -91,3 +91,20 @@ def test_fgt_file_roundtrip(tmp_path):
     (tmp_path / "junk.fgt").write_bytes(b"not a trajectory")
     with pytest.raises(ValueError):
         TrajectoryFile(str(tmp_path / "junk.fgt"))
+
+
+def test_load_eagle_sim_reads_the_reference_layout(tmp_path):
+    """max/ds_download/eagle.py:123-144 (get_data): sim.npz with pointcloud / VX / VY / PS / PG / mask + triangles.npy."""
+    from fluid_llm_b200 import synth
+    from fluid_llm_b200.dynamic_mesh import load_eagle_sim
+    tr = synth.make_dynamic_trajectory("cylinder", 6, mesh_seed=0, field_seed=1, flip_frac=0.0)
+    T, N = tr["mesh_pos"].shape[:2]
+    np.savez(tmp_path / "sim.npz", pointcloud=tr["mesh_pos"], VX=tr["velocity"][..., 0], VY=tr["velocity"][..., 1],
+             PS=tr["pressure"][..., 0], PG=np.zeros((T, N), np.float32), mask=np.zeros((T, N), np.int32))
+    np.save(tmp_path / "triangles.npy", tr["cells"].astype(np.int64))
+    pos, cells, vel, prs = load_eagle_sim(str(tmp_path), t0=1, window_length=4)
+    assert pos.shape == (4, N, 2) and cells.shape == (4, tr["cells"].shape[1], 3) and cells.dtype == np.int32
+    assert np.array_equal(pos, tr["mesh_pos"][1:5]) and np.array_equal(cells, tr["cells"][1:5])
+    assert np.array_equal(vel, tr["velocity"][1:5]) and np.array_equal(prs, tr["pressure"][1:5, :, 0])
+    pos_all, _, _, _ = load_eagle_sim(str(tmp_path))
+    assert pos_all.shape[0] == T
