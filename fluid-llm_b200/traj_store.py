@@ -105,12 +105,17 @@ class TrajectoryFile:
     def cells(self):
         return np.asarray(self.array("cells"))
 
-    def to_device(self, plan, stream=None, pinned=None):
-        """-> DeviceTrajectory with the node fields copied file -> pinned host -> HBM (async on `stream`)."""
+    def to_device(self, plan, stream=None, pinned=None, first=0, last=None):
+        """-> DeviceTrajectory with the node fields copied file -> pinned host -> HBM (async on `stream`).
+        `first` / `last` select a window of time steps [first, last): only those rows are read from the file."""
         from .field_path import DeviceTrajectory
         if plan.n_nodes != self.n_nodes:
             raise ValueError(f"{self.path}: {self.n_nodes} nodes, plan has {plan.n_nodes}")
-        return DeviceTrajectory.from_padded(self.array("velocity"), self.array("pressure"), plan, stream, pinned)
+        last = self.n_steps if last is None else last
+        if not (0 <= first < last <= self.n_steps):
+            raise ValueError(f"{self.path}: window [{first}, {last}) outside 0..{self.n_steps}")
+        return DeviceTrajectory.from_padded(self.array("velocity")[first:last], self.array("pressure")[first:last], plan, stream,
+                                            pinned)
 
 
 class PinnedStage:

@@ -177,9 +177,13 @@ def test_datasets_on_flat_fgt_files(kind, tmp_path):
     DS = MGNDataset if kind == "cylinder" else AirfoilDataset
     kw = dict(resolution=238, patch_size=PATCH, stride=PATCH, seq_len=4, seq_interval=2, mode="valid")
     a, b = DS(load_dir=str(pk), **kw), DS(load_dir=str(fg), **kw)
+    b.cache_size = 1            # fewer slots than files: file 0 is not resident and goes through the window-load route
     assert b.save_files == ["0.fgt", "1.fgt"] and (a.N_x_patch, a.N_y_patch) == (b.N_x_patch, b.N_y_patch)
     for x, y in zip(a[1], b[1]):
         assert torch.equal(x, y)
     want = P.ds_get(trajs[0], 100, 4, 2, 238, PATCH, "airfoil" if kind == "airfoil" else "cylinder")
     for x, w in zip(b[0], want):
+        assert np.array_equal(x.cpu().numpy(), w)
+    assert len(b._plans) == 1                                   # the window route cached file 0's mesh plan, not its node fields
+    for x, w in zip(b[0], want):                                # second hit: plan from the cache
         assert np.array_equal(x.cpu().numpy(), w)
