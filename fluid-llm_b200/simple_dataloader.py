@@ -18,7 +18,7 @@ import numpy as np
 import torch
 from torch.utils.data import Dataset
 
-from .field_path import CYLINDER, DeviceTrajectory, Personality, interp_patchify
+from .field_path import TrajBatch, CYLINDER, DeviceTrajectory, Personality, interp_patchify
 from .mesh_utils import MeshPlan
 from .traj_store import PinnedStage, TrajectoryFile
 
@@ -177,6 +177,38 @@ class _GpuFieldDataset(Dataset):
         if self.output_device is not None:
             out = tuple(t.to(self.output_device) for t in out)
         return out
+
+    def ds_get_many(self, requests):
+        """[(save_file or index, step_num), ...] -> list of 5-tuples, all samples in ONE kernel launch.
+
+        The per-sample call is bound by host work (descriptor set-up, one launch, five small tensor ops); a DataLoader batch
+        of B samples costs little more than one.  Differences and mask expansion are done once on the stacked tensors."""
+        trajs, steps = [], []
+        for save_file, step_num in requests:
+            if isinstance(save_file, int):
+                save_file = self.save_files[save_file]
+            step_num = min(int(step_num), self.max_step_num)          # simple_dataloader.py:177-179
+            traj, local_step = self._load_window(save_file, step_num)
+            trajs.append(traj)
+            steps.append(local_step)
+        tabs = [t.plan.patch_table(self.patch_size, self.personality.crop_patches, self.personality.flip_y) for t in trajs]
+        batch = TrajBatch(trajs, tabs, steps, self.seq_interval, self.seq_len)
+        states, mask = batch.run(self.personality, self.normalize)     # (B, T, L, 3, px, py), (B, T, L, px, py)
+        diffs = states[:, 1:] - states[:, :-1]
+        masks = mask[:, 1:].unsqueeze(3).repeat(1, 1, 1, 3, 1, 1).bool()
+        pos = self._get_pos_id().to(states.device)
+        out = [(states[b, :-1], states[b, 1:], diffs[b], masks[b], pos) for b in range(len(trajs))]
+        if self.output_device is not None:
+            out = [tuple(t.to(self.output_device) for t in o) for o in out]
+        return out
+
+    def __getitems__(self, indices):
+        """torch's DataLoader fetches a whole batch through this when it exists: one launch per batch."""
+        reqs = []
+        for idx in indices:
+            step_num = random.randint(0, self.max_step_num)
+            reqs.append((self.save_files[idx], 100 if self.mode in ["test", "valid"] else step_num))
+        return self.ds_get_many(reqs)
 
     def _get_pos_id(self):
         """simple_dataloader.py:218-226 (the labelling quirk is reproduced as is)."""

@@ -187,3 +187,23 @@ def test_datasets_on_flat_fgt_files(kind, tmp_path):
     assert len(b._plans) == 1                                   # the window route cached file 0's mesh plan, not its node fields
     for x, w in zip(b[0], want):                                # second hit: plan from the cache
         assert np.array_equal(x.cpu().numpy(), w)
+
+
+def test_ds_get_many_equals_per_sample_calls(tmp_path):
+    """One launch for a DataLoader batch (`__getitems__` / `ds_get_many`) returns what the per-sample calls return."""
+    from fluid_llm_b200.simple_dataloader import MGNDataset
+    from torch.utils.data import DataLoader
+    trajs = [trajectory("cylinder", 140, s, 30 + s) for s in (0, 1, 2)]
+    _write(tmp_path, copy.deepcopy(trajs))
+    ds = MGNDataset(load_dir=str(tmp_path), resolution=238, patch_size=PATCH, stride=PATCH, seq_len=5, seq_interval=2, mode="valid")
+    ds.max_step_num = 120
+    reqs = [(0, 3), (2, 100), (1, 57), (2, 500)]                 # the last one is clamped to max_step_num
+    many = ds.ds_get_many(reqs)
+    for (f, st), got in zip(reqs, many):
+        for x, y in zip(got, ds.ds_get(f, st)):
+            assert torch.equal(x, y)
+    batch = next(iter(DataLoader(ds, batch_size=3, shuffle=False)))      # goes through __getitems__ + default collate
+    assert batch[0].shape == (3, 4, ds.N_patch, 3, 16, 16) and batch[3].dtype == torch.bool and batch[4].shape == (3, 4, ds.N_patch, 3)
+    for b in range(3):
+        for x, y in zip(batch, ds.ds_get(b, 100)):
+            assert torch.equal(x[b], y)

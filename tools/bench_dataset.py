@@ -71,6 +71,15 @@ def main():
         for i in range(args.files):
             ds.ds_get(i, 0)
         run(ds, f"{name} warm (trajectory and plan resident on the device)")
+        if name.strip() == ".fgt":
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(0, len(order), 8):
+                ds.ds_get_many(order[i:i + 8])
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            print(f"{name + ' warm, batches of 8 in one launch (ds_get_many)':58s} {args.samples / dt:9.1f} samples/s  "
+                  f"{args.samples * args.seq_len / dt:10.1f} frames/s  {dt / args.samples * 1e3:8.2f} ms/sample")
     # the oracle: what one DataLoader worker of the reference does per sample
     n = max(2, args.samples // 8)
     t0 = time.perf_counter()
