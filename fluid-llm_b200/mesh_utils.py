@@ -265,9 +265,10 @@ class MeshPlan:
                 check(lib.fl_plan_patch_table(ptr(self.cell_idx_d), ptr(self.cell_w_d), self.nx, self.ny, px, py, key[2],
                                               flags, ptr(idx), ptr(w), ctypes.byref(nbx), ctypes.byref(nby),
                                               stream_ptr()), "fl_plan_patch_table")
-                idx_slot = idx.clone()
-                inside = idx[:, 3] >= 0
-                idx_slot[inside, :3] = self.node_slot_d[idx[inside, :3].long()]
+                # node ids -> shared-memory slots for the cells inside the mesh (no boolean indexing: that would synchronise)
+                inside = (idx[:, 3] >= 0).unsqueeze(1)
+                slots = self.node_slot_d[idx[:, :3].clamp(min=0, max=self.n_nodes - 1).long()]
+                idx_slot = torch.cat([torch.where(inside, slots, idx[:, :3]), idx[:, 3:4]], dim=1).contiguous()
             tab = PatchTable(idx, w, nbx.value, nby.value, px, py, idx_slot)
             self._tables[key] = tab
         return tab
