@@ -8,13 +8,15 @@
 //   out = bf16( h @ W2^T + b2 ) + (x_emb[p0] + y_emb[p1] + t_emb[p2])  512 -> llm_dim, fp32 result
 // One kernel, C[M,N] = epilogue(A[M,K] . B[N,K]^T), used twice; nn.Linear weights are [N,K] K-major already.
 //
-// Kernel anatomy (one 128 x BLOCK_N output tile per CTA, 320 threads):
+// Kernel anatomy (persistent: one 320-thread CTA per SM walks 128 x BLOCK_N output tiles):
 //   warp 0     TMA producer: cp.async.bulk.tensor.2d of the A (128 x 64) and B (BLOCK_N x 64) bf16 tiles,
-//              128-byte swizzle, into a 2-stage shared-memory ring (two CTAs per SM) (full/empty mbarriers)
+//              128-byte swizzle, into a 4-stage shared-memory ring that keeps running across tiles (full/empty mbarriers)
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BLOCK_N,
-//              K = 16) four times per stage, tcgen05.commit releases the stage / signals the epilogue
+//              K = 16) four times per stage into one of two TMEM accumulator buffers; tcgen05.commit releases the
+//              stage / hands the finished accumulator to the epilogue (tmem_full), which hands it back (tmem_empty)
 //   warps 2-9  epilogue (two warps per TMEM lane quarter, half of the columns each): tcgen05.ld (32 lanes x 32
-//              columns per call) -> bias, bf16 rounding, LeakyReLU or positional-embedding add -> global
+//              columns per call) -> bias, bf16 rounding, LeakyReLU or positional-embedding add -> global; runs under
+//              the main loop of the next tile
 #include "fl_common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -22,9 +24,7 @@
 namespace {
 
 constexpr int BM = 128, BK = 64, GEMM_THREADS = 320, STAGES = 4, EPI_WARPS = 8, EPI_SCRATCH = 4096 + 192;
-// operand ring depth: 2 stages = 96 KB, two CTAs per SM (one runs its epilogue while the other feeds the tensor core) when
-// the grid has more tiles than SMs; 4 stages, one CTA per SM, when every tile has an SM to itself (the k-loop is then
-// bound by TMA latency, which a deeper ring hides)
+// 4 stages x 48 KB operand ring + 8 x 4.2 KB epilogue scratch + barriers = 226 KB of shared memory: one CTA per SM
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(uint64_t* b, unsigned n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(n) : "memory"); }
