@@ -18,9 +18,8 @@ FL_FORCE_GATHER = 8
 class FlTraj(ctypes.Structure):
     _fields_ = [("d_velocity", c_void_p), ("d_pressure", c_void_p), ("d_idx", c_void_p), ("d_w", c_void_p),
                 ("d_idx_slot", c_void_p), ("d_node_slot", c_void_p),
-                ("d_blk_ids", c_void_p), ("d_blk_idx", c_void_p), ("d_blk_w", c_void_p), ("d_b_list", c_void_p),
                 ("d_states", c_void_p), ("d_mask", c_void_p),
-                ("n_nodes", c_int32), ("t0", c_int32), ("interval", c_int32), ("n_frames", c_int32), ("n_b", c_int32), ("pad0", c_int32),
+                ("n_nodes", c_int32), ("t0", c_int32), ("interval", c_int32), ("n_frames", c_int32),
                 ("vel_stride", c_int32), ("prs_stride", c_int32)]
 
 

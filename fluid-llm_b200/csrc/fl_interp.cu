@@ -251,147 +251,6 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
     }
 }
 
-// 2 x 2 pixel blocks (16 x 16 patches, unchecked items).  The four pixels of a block touch at most six distinct
-// nodes in ~95 % of the blocks (usually 4): each distinct node is gathered (one LDS.128) and converted ONCE per frame
-// and the four pixels are dense weighted sums over the block's node list (a vertex a pixel does not use has weight
-// exactly 0, and fma(0, z, acc) == acc for the finite z of unchecked items).  Per pixel this is 1.5 gathers and 3
-// input conversions instead of 3 and 6 -- the two resources that bound the per-pixel form.  Blocks with more than six
-// distinct nodes are skipped here and done pixel by pixel at the end (d_b_list).
-// Lane l of a warp owns block (rp = l / 8, cp = l % 8) of the warp's 128-pixel chunk (8 patch rows): a quarter-warp
-// covers two full patch rows, every store instruction writes 8-byte pieces of four rows.
-__device__ __forceinline__ void staged_item_blocks(const FlTraj& tr, const unsigned char* __restrict__ s_nodes, int slot_b,
-                                                   int fbeg, int nf, int n_patches, const StagedConst& sc, unsigned flags) {
-    constexpr int PPX = 256, KM = 6;
-    const bool mask_aware = flags & FL_MASK_AWARE_NORM, no_norm = flags & FL_NO_NORM;
-    const int nchunks = n_patches * 2;
-    const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
-    const int rp = lane >> 3, cp = lane & 7;
-    const size_t frame_out = (size_t)n_patches * 3 * PPX;
-    for (int ch = threadIdx.x >> 5; ch < nchunks; ch += warps) {
-        const int blk = ch * 32 + lane;
-        const int4 ia = __ldg((const int4*)tr.d_blk_ids + 2 * blk), ib = __ldg((const int4*)tr.d_blk_ids + 2 * blk + 1);
-        const bool skip = ib.z != 0;                     // more than six distinct nodes: per-pixel pass below
-        const uint32_t ov[KM] = {(uint32_t)ia.x * 16u, (uint32_t)ia.y * 16u, (uint32_t)ia.z * 16u,
-                                 (uint32_t)ia.w * 16u, (uint32_t)ib.x * 16u, (uint32_t)ib.y * 16u};
-        double W[4][KM];
-        unsigned mbits = 0;                              // byte r = 1 if pixel r is outside the mesh
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int4 id = __ldg((const int4*)tr.d_blk_idx + 4 * blk + r);
-            const double2 ww = __ldg((const double2*)tr.d_blk_w + 4 * blk + r);
-            const bool out = id.w < 0;
-            mbits |= out ? (1u << (8 * r)) : 0u;
-            const double w0 = (out || skip) ? 0.0 : 1.0 - ww.x - ww.y, w1 = (out || skip) ? 0.0 : ww.x, w2 = (out || skip) ? 0.0 : ww.y;
-#pragma unroll
-            for (int k = 0; k < KM; ++k) W[r][k] = id.x == k ? w0 : (id.y == k ? w1 : (id.z == k ? w2 : 0.0));
-        }
-        const int o0 = ch * 128, l = o0 >> 8, k0 = (o0 & 255) + rp * 32 + cp * 2;       // first pixel of the block inside its patch
-        float* dst = tr.d_states + ((size_t)fbeg * n_patches + l) * 3 * PPX + k0;
-        uint8_t* mdst = tr.d_mask ? tr.d_mask + ((size_t)fbeg * n_patches + l) * PPX + k0 : nullptr;
-        const unsigned short m01 = (unsigned short)((mbits & 1u) | ((mbits >> 8) & 1u) << 8);
-        const unsigned short m23 = (unsigned short)(((mbits >> 16) & 1u) | ((mbits >> 24) & 1u) << 8);
-        const unsigned char* nb = s_nodes;
-#pragma unroll 1
-        for (int f = 0; f < nf; ++f, nb += slot_b) {
-            float4 a[KM];
-#pragma unroll
-            for (int k = 0; k < KM; ++k) a[k] = *reinterpret_cast<const float4*>(nb + ov[k]);     // one gather per distinct node
-            float res[3][4];
-            {
-                double z[KM];
-#pragma unroll
-                for (int k = 0; k < KM; ++k) z[k] = (double)a[k].x;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    double acc = W[r][0] * z[0];
-#pragma unroll
-                    for (int k = 1; k < KM; ++k) acc = fma(W[r][k], z[k], acc);
-                    res[0][r] = (float)acc;
-                }
-#pragma unroll
-                for (int k = 0; k < KM; ++k) z[k] = (double)a[k].y;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    double acc = W[r][0] * z[0];
-#pragma unroll
-                    for (int k = 1; k < KM; ++k) acc = fma(W[r][k], z[k], acc);
-                    res[1][r] = (float)acc;
-                }
-#pragma unroll
-                for (int k = 0; k < KM; ++k) z[k] = __hiloint2double(__float_as_int(a[k].w), __float_as_int(a[k].z));
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    double acc = W[r][0] * z[0];
-#pragma unroll
-                    for (int k = 1; k < KM; ++k) acc = fma(W[r][k], z[k], acc);
-                    res[2][r] = (float)acc;
-                }
-            }
-            if (!no_norm) {
-                if (mask_aware && mbits) {          // rare: pixels on the mesh boundary / padding stay raw (airfoil_ds.py:241-242)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-#pragma unroll
-                        for (int r = 0; r < 4; ++r)
-                            if (!((mbits >> (8 * r)) & 1u)) res[c][r] = norm_fast(res[c][r], sc.mean[c], sc.stdv[c], sc.rcp[c]);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const unsigned long long nm = pack2(-sc.mean[c], -sc.mean[c]), ns = pack2(-sc.stdv[c], -sc.stdv[c]),
-                                                 rc = pack2(sc.rcp[c], sc.rcp[c]);
-                        norm_fast2(res[c][0], res[c][1], nm, ns, rc);
-                        norm_fast2(res[c][2], res[c][3], nm, ns, rc);
-                    }
-                }
-            }
-            if (!skip) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    fl_stg_stream2((float2*)(dst + c * PPX), make_float2(res[c][0], res[c][1]));            // row 2rp
-                    fl_stg_stream2((float2*)(dst + c * PPX + 16), make_float2(res[c][2], res[c][3]));       // row 2rp + 1
-                }
-                if (mdst) { *(unsigned short*)mdst = m01; *(unsigned short*)(mdst + 16) = m23; }
-            }
-            dst += frame_out;
-            if (mdst) mdst += (size_t)n_patches * PPX;
-        }
-    }
-    // blocks with more than six distinct nodes: one pixel per thread, three gathers each
-    const FlCellIdx* idx_tab = tr.d_idx_slot ? tr.d_idx_slot : tr.d_idx;
-    for (int i = threadIdx.x; i < tr.n_b; i += blockDim.x) {
-        const int o = __ldg(tr.d_b_list + i);
-        const int4 id = __ldg((const int4*)idx_tab + o);
-        const double2 ww = __ldg((const double2*)tr.d_w + o);
-        const bool out = id.w < 0;
-        const double w0 = out ? 0.0 : 1.0 - ww.x - ww.y, w1 = out ? 0.0 : ww.x, w2 = out ? 0.0 : ww.y;
-        const uint32_t o0 = out ? 0u : (uint32_t)id.x * 16u, o1 = out ? 0u : (uint32_t)id.y * 16u, o2 = out ? 0u : (uint32_t)id.z * 16u;
-        const int l = o >> 8, k = o & 255;
-        float* dst = tr.d_states + ((size_t)fbeg * n_patches + l) * 3 * PPX + k;
-        uint8_t* mdst = tr.d_mask ? tr.d_mask + ((size_t)fbeg * n_patches + l) * PPX + k : nullptr;
-        const unsigned char* nb = s_nodes;
-        for (int f = 0; f < nf; ++f, nb += slot_b) {
-            const float4 a0 = *reinterpret_cast<const float4*>(nb + o0), a1 = *reinterpret_cast<const float4*>(nb + o1),
-                         a2 = *reinterpret_cast<const float4*>(nb + o2);
-            float v[3];
-            v[0] = (float)fma(w2, (double)a2.x, fma(w1, (double)a1.x, w0 * (double)a0.x));
-            v[1] = (float)fma(w2, (double)a2.y, fma(w1, (double)a1.y, w0 * (double)a0.y));
-            v[2] = (float)fma(w2, __hiloint2double(__float_as_int(a2.w), __float_as_int(a2.z)),
-                              fma(w1, __hiloint2double(__float_as_int(a1.w), __float_as_int(a1.z)),
-                                  w0 * __hiloint2double(__float_as_int(a0.w), __float_as_int(a0.z))));
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float x = v[c];
-                if (!no_norm && !(mask_aware && out)) x = norm_fast(x, sc.mean[c], sc.stdv[c], sc.rcp[c]);
-                fl_stg_stream1(dst + c * PPX, x);
-            }
-            if (mdst) { *mdst = out ? 1 : 0; mdst += (size_t)n_patches * PPX; }
-            dst += frame_out;
-        }
-    }
-}
-
-// BLOCKS: the experimental 2 x 2 pixel-block form instead of the per-pixel form
-template <bool BLOCKS>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int groups_per_traj, int TF, int n_patches,
                          int ppx, int ppx_shift, int slot_nodes, StagedConst sc, unsigned flags) {
@@ -430,7 +289,6 @@ k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int grou
         const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || !sc.fast_div);
         const unsigned char* snb = (const unsigned char*)s_nodes;
         if (bad) staged_item<true>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
-        else if (BLOCKS) staged_item_blocks(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, sc, flags);
         else staged_item<false>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
         __syncthreads();   // every gather of this item is done before the next item's staging lands
     }
@@ -463,8 +321,7 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             ok = t.vel_stride % 4 == 0 && t.prs_stride % 4 == 0 && t.vel_stride >= 2 * t.prs_stride && t.prs_stride >= t.n_nodes &&
                  ((uintptr_t)t.d_velocity % 16 == 0) && ((uintptr_t)t.d_pressure % 16 == 0) && ((uintptr_t)t.d_states % 16 == 0) &&
                  (t.d_mask == nullptr || (uintptr_t)t.d_mask % 4 == 0) && ((uintptr_t)t.d_node_slot % 16 == 0) &&
-                 ((uintptr_t)t.d_idx_slot % 16 == 0) && ((uintptr_t)t.d_blk_ids % 16 == 0) && ((uintptr_t)t.d_blk_idx % 16 == 0) &&
-                 ((uintptr_t)t.d_blk_w % 16 == 0) && (t.d_blk_ids == nullptr || (px == 16 && py == 16 && t.d_blk_idx && t.d_blk_w && (t.n_b == 0 || t.d_b_list)));
+                 ((uintptr_t)t.d_idx_slot % 16 == 0);
             slot_vel = t.vel_stride > slot_vel ? t.vel_stride : slot_vel;
             slot_prs = t.prs_stride > slot_prs ? t.prs_stride : slot_prs;
         }
@@ -482,20 +339,13 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             const size_t smem = (size_t)TF * frame_bytes;
             static FlOncePerDevice attr;
             if (attr.first_use()) {
-                FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_staged<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_staged<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             }
             int ppx_shift = -1;
             for (int b = 0; b < 16; ++b) if ((1 << b) == ppx) ppx_shift = b;
             const int grid = n_items < FL_SM_COUNT ? (int)n_items : FL_SM_COUNT;      // one persistent CTA per SM
-            bool blocks = ppx == 256;                 // the block form needs its tables on every trajectory
-            for (int i = 0; i < n_traj; ++i) blocks = blocks && h_trajs[i].d_blk_ids != nullptr;
-            if (blocks)
-                k_interp_patchify_staged<true><<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift,
-                                                                              slot_prs, sc, flags);
-            else
-                k_interp_patchify_staged<false><<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift,
-                                                                               slot_prs, sc, flags);
+            k_interp_patchify_staged<<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift, slot_prs,
+                                                                     sc, flags);
             FL_LAUNCH_CHECK();
             return FL_OK;
         }

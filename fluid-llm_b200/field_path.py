@@ -109,8 +109,6 @@ class TrajBatch:
     def __init__(self, trajs, tables, t0s, interval, n_frames, want_mask=True, use_slots=None, out=None):
         if use_slots is None:
             use_slots = os.environ.get("FLUIDGRID_SLOTS", "1") != "0"
-        # experimental 2 x 2 block path of the staged kernel (slower today, see profiles/README.md): opt-in
-        use_blocks = os.environ.get("FLUIDGRID_BLOCKS", "0") == "1"
         if not (len(trajs) == len(tables) == len(t0s)) or not trajs:
             raise ValueError("trajs, tables and t0s must be non-empty and of equal length")
         tab0 = tables[0]
@@ -141,11 +139,8 @@ class TrajBatch:
             arr[i] = FlTraj(tr.vel_buf.data_ptr(), tr.prs_buf.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(),
                             tab.idx_slot.data_ptr() if use_slots and tab.idx_slot is not None else 0,
                             tr.plan.node_slot_d.data_ptr() if use_slots and tab.idx_slot is not None else 0,
-                            *((tab.blk_ids.data_ptr(), tab.blk_idx.data_ptr(), tab.blk_w.data_ptr(), tab.b_list.data_ptr())
-                              if use_blocks and use_slots and tab.block_tables() else (0, 0, 0, 0)),
                             self.states[i].data_ptr(), self.mask[i].data_ptr() if want_mask else 0,
-                            tr.plan.n_nodes, int(t0), int(interval), self.n_frames,
-                            tab.n_b if use_blocks and use_slots and tab.block_tables() else 0, 0, tr.vel_stride, tr.prs_stride)
+                            tr.plan.n_nodes, int(t0), int(interval), self.n_frames, tr.vel_stride, tr.prs_stride)
         self.host_desc = arr
         raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
         self.desc = torch.from_numpy(raw).to(dev)

@@ -74,66 +74,6 @@ class PatchTable:
         self.idx, self.w, self.n_bx, self.n_by, self.px, self.py = idx, w, n_bx, n_by, px, py
         self.idx_slot = idx_slot
         self.n_patches = n_bx * n_by
-        self.blk_ids = self.blk_idx = self.blk_w = self.b_list = None      # 2 x 2 block tables (16 x 16 patches), built on demand
-        self.n_b = 0
-
-    def block_tables(self) -> bool:
-        """Build (once) the 2 x 2 pixel-block tables of the experimental block path; False if the patch is not 16 x 16."""
-        if (self.px, self.py) != (16, 16) or self.idx_slot is None:
-            return False
-        if self.blk_ids is None:
-            bi, bx_, bw, bl = build_block_tables(self.idx_slot.cpu().numpy(), self.w.cpu().numpy())
-            dev = self.idx.device
-            self.blk_ids = torch.from_numpy(bi).to(dev)
-            self.blk_idx = torch.from_numpy(bx_).to(dev)
-            self.blk_w = torch.from_numpy(bw).to(dev)
-            self.b_list = torch.from_numpy(bl if len(bl) else np.zeros(1, np.int32)).to(dev)
-            self.n_b = int(len(bl))
-        return True
-
-
-BLOCK_KMAX = 6
-
-
-def build_block_tables(idx_slot, w, kmax=BLOCK_KMAX):
-    """Group the patch-ordered table into 2 x 2 pixel blocks (host, one-off per mesh and personality).
-
-    idx_slot int32 [P, 4] (three node slots + tri), w float64 [P, 2], P a multiple of 128 with 16-pixel patch rows.
-    -> blk_ids int32 [nb, 8] (<= kmax distinct slots, [6] = 1 if the block has more and takes the per-pixel path),
-       blk_idx int32 [nb*4, 4] (local vertex indices + tri, block order), blk_w float64 [nb*4, 2], b_list int32."""
-    P = idx_slot.shape[0]
-    nchunks = P // 128
-    lane = np.arange(32)
-    rp, cp = lane // 8, lane % 8
-    off = np.stack([(2 * rp + a) * 16 + 2 * cp + b for a in (0, 1) for b in (0, 1)], axis=1)          # [32, 4]
-    pxi = (np.arange(nchunks)[:, None, None] * 128 + off[None]).reshape(-1, 4)                         # [nb, 4]
-    rec = idx_slot[pxi]                                                                                # [nb, 4, 4]
-    ids, tri = rec[:, :, :3].astype(np.int64), rec[:, :, 3]
-    inside = tri >= 0
-    big = np.int64(1) << 40
-    flat = np.where(inside[:, :, None], ids, big).reshape(-1, 12)
-    srt = np.sort(flat, axis=1)
-    first = np.ones_like(srt, dtype=bool)
-    first[:, 1:] = srt[:, 1:] != srt[:, :-1]
-    first &= srt != big
-    K = first.sum(axis=1)
-    order = np.argsort(~first, axis=1, kind="stable")                    # distinct ids first, in ascending order
-    u = np.take_along_axis(srt, order, axis=1)[:, :kmax]
-    valid = np.arange(kmax)[None, :] < K[:, None]
-    u = np.where(valid, u, np.where(K[:, None] > 0, u[:, :1], 0))        # pad with the first id (weight 0 there)
-    u[u >= big] = 0
-    class_b = K > kmax
-    loc = (ids[:, :, :, None] == u[:, None, None, :]).argmax(axis=-1)    # [nb, 4, 3] position of every vertex in the list
-    nb = len(pxi)
-    blk_ids = np.zeros((nb, 8), dtype=np.int32)
-    blk_ids[:, :kmax] = u
-    blk_ids[:, 6] = class_b
-    blk_idx = np.zeros((nb, 4, 4), dtype=np.int32)
-    blk_idx[:, :, :3] = np.where(inside[:, :, None], loc, 0)
-    blk_idx[:, :, 3] = tri
-    blk_w = w[pxi]                                                        # [nb, 4, 2]
-    b_list = pxi[class_b].reshape(-1).astype(np.int32)
-    return blk_ids, blk_idx.reshape(-1, 4), np.ascontiguousarray(blk_w.reshape(-1, 2)), b_list
 
 
 def morton_slots(pos32, n_padded):

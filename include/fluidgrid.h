@@ -32,7 +32,7 @@ extern "C" {
 #define FL_E_WORKSPACE (-3)/* workspace too small */
 #define FL_E_ALIGN (-4)    /* pointer not aligned as documented */
 
-#define FL_ABI_VERSION 5
+#define FL_ABI_VERSION 6
 
 /* personality flags of fl_plan_patch_table / fl_interp_patchify */
 #define FL_FLIP_Y 1u          /* airfoil_ds.py:80  -- y axis reversed after padding */
@@ -96,21 +96,9 @@ typedef struct FlTraj {
     const FlCellIdx* d_idx_slot; /* optional (NULL = d_idx): same table with node ids replaced by shared-memory slots */
     const int32_t* d_node_slot;  /* optional (NULL = identity): slot of every node, [prs_stride]; a spatially sorted
                                     (Morton) order keeps the gathers of neighbouring pixels in neighbouring banks */
-    /* optional 2 x 2 pixel-block tables (16 x 16 patches only; all NULL = not used).  A block is the four pixels
-     * (2rp+a, 2cp+b), a,b in {0,1}, of a 128-pixel chunk (8 patch rows); block index = chunk*32 + rp*8 + cp.
-     * d_blk_ids [n_blocks][8]: up to 6 distinct node slots of the block's pixels, [6] != 0 marks a block with more
-     * than 6 distinct nodes (its pixels are listed in d_b_list and take the per-pixel path); d_blk_idx/d_blk_w
-     * [n_blocks*4]: per pixel (r = 2a+b) the LOCAL indices (0..5) of its three vertices + tri, and w1, w2.
-     * Sharing converted vertex values between the four pixels halves the gathers and conversions per pixel. */
-    const int32_t* d_blk_ids;
-    const FlCellIdx* d_blk_idx;
-    const FlCellW* d_blk_w;
-    const int32_t* d_b_list;     /* [n_b] patch-order pixel indices of the blocks marked in d_blk_ids */
     float* d_states;           /* [n_frames, L, 3, px, py] */
     uint8_t* d_mask;           /* [n_frames, L, px, py] or NULL */
     int32_t n_nodes, t0, interval, n_frames;
-    int32_t n_b;               /* length of d_b_list */
-    int32_t pad0;
     int32_t vel_stride;        /* floats between consecutive frames of d_velocity (>= 2*n_nodes) */
     int32_t prs_stride;        /* floats between consecutive frames of d_pressure (>= n_nodes)   */
 } FlTraj;

@@ -22,13 +22,13 @@ def test_library_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/fluidgrid.h but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES and the header disagree"
-    assert lib.fl_abi_version() == 5
+    assert lib.fl_abi_version() == 6
 
 
 def test_struct_layout_matches_header():
     from fluid_llm_b200._lib import FlTraj
-    assert ctypes.sizeof(FlTraj) == 12 * 8 + 8 * 4
-    assert FlTraj.n_nodes.offset == 96 and FlTraj.prs_stride.offset == 124
+    assert ctypes.sizeof(FlTraj) == 8 * 8 + 6 * 4
+    assert FlTraj.n_nodes.offset == 64 and FlTraj.prs_stride.offset == 84
 
 
 def test_argument_errors_without_a_device(lib):

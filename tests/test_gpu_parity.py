@@ -288,28 +288,6 @@ def test_unsupported_patch_size_is_an_error():
         interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 0, 2, 1, (5, 5), CYLINDER)
 
 
-@pytest.mark.parametrize("kind", ["cylinder", "airfoil", "eagle"])
-def test_experimental_block_path_matches_oracle(kind, monkeypatch):
-    """FLUIDGRID_BLOCKS=1: the 2 x 2 pixel-block form of the staged kernel (dense sums over <= 6 shared nodes)."""
-    monkeypatch.setenv("FLUIDGRID_BLOCKS", "1")
-    from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
-    from fluid_llm_b200.field_path import AIRFOIL, CYLINDER, DeviceTrajectory, interp_patchify
-    tr = trajectory(kind)
-    plan, pos, faces = _plan(kind)
-    vel, prs = tr["velocity"], tr["pressure"]
-    if kind == "airfoil":
-        nmask, _, _ = crop_airfoil_mesh(tr["mesh_pos"], tr["cells"])
-        vel, prs = vel[:, nmask], prs[:, nmask]
-    pers = AIRFOIL if kind == "airfoil" else CYLINDER
-    states, mask, tab = interp_patchify(DeviceTrajectory(vel, prs, plan), 0, 7, 1, PATCH, pers)
-    assert tab.blk_ids is not None
-    _, extra = oracle_ds_get(kind, 0, 7, 1)
-    assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
-    s, so = states.cpu().numpy(), extra["states"]
-    np.testing.assert_allclose(s, so, rtol=1e-6, atol=0)
-    assert np.array_equal(s, so)
-
-
 def test_c_abi_called_directly_as_integration_md_shows():
     """fl_interp_patchify with host-side descriptors, bound with plain ctypes exactly like INTEGRATION.md section 5
     (unpadded node arrays straight from the pickle layout -> the gather kernel)."""
@@ -324,11 +302,9 @@ def test_c_abi_called_directly_as_integration_md_shows():
         _fields_ = [("d_velocity", ctypes.c_void_p), ("d_pressure", ctypes.c_void_p),
                     ("d_idx", ctypes.c_void_p), ("d_w", ctypes.c_void_p),
                     ("d_idx_slot", ctypes.c_void_p), ("d_node_slot", ctypes.c_void_p),
-                    ("d_blk_ids", ctypes.c_void_p), ("d_blk_idx", ctypes.c_void_p),
-                    ("d_blk_w", ctypes.c_void_p), ("d_b_list", ctypes.c_void_p),
                     ("d_states", ctypes.c_void_p), ("d_mask", ctypes.c_void_p),
                     ("n_nodes", ctypes.c_int32), ("t0", ctypes.c_int32), ("interval", ctypes.c_int32), ("n_frames", ctypes.c_int32),
-                    ("n_b", ctypes.c_int32), ("pad0", ctypes.c_int32), ("vel_stride", ctypes.c_int32), ("prs_stride", ctypes.c_int32)]
+                    ("vel_stride", ctypes.c_int32), ("prs_stride", ctypes.c_int32)]
 
     lib.fl_interp_patchify.restype = ctypes.c_int
     lib.fl_interp_patchify.argtypes = [ctypes.POINTER(FlTraj), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -339,8 +315,8 @@ def test_c_abi_called_directly_as_integration_md_shows():
     N, seq_len, step, interval = vel.shape[1], 3, 1, 2
     states = torch.empty((seq_len, tab.n_patches, 3, 16, 16), dtype=torch.float32, device="cuda")
     mask = torch.empty((seq_len, tab.n_patches, 16, 16), dtype=torch.uint8, device="cuda")
-    traj = FlTraj(vel.data_ptr(), prs.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(), None, None, None, None, None, None,
-                  states.data_ptr(), mask.data_ptr(), N, step, interval, seq_len, 0, 0, vel.stride(0), prs.stride(0))
+    traj = FlTraj(vel.data_ptr(), prs.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(), None, None,
+                  states.data_ptr(), mask.data_ptr(), N, step, interval, seq_len, vel.stride(0), prs.stride(0))
     mean = (ctypes.c_float * 3)(0.823, 0.0005865, 0.04763)
     std = (ctypes.c_float * 3)(0.275, 0.275, 0.275)
     rc = lib.fl_interp_patchify(ctypes.byref(traj), 1, tab.n_patches, 16, 16, mean, std, 0,
