@@ -210,3 +210,25 @@ def test_dynamic_writes_stay_inside_the_output_buffers(force_binned):
     inner = states[G:-G]
     assert bool(torch.isfinite(inner).all()) and not bool((inner == 777.0).any())          # every output element was written
     assert not bool((mask[G:-G] == 77).any()) and not bool((tri[G:-G] == -777).any())
+
+
+@pytest.mark.parametrize("pers_name", ["cylinder", "airfoil"])
+def test_dynamic_nonfinite_node_values(pers_name):
+    """NaN / inf node values on per-frame meshes: per channel zeroing (mesh_utils.py:86-89), only the pressure mask is kept,
+    the mask-aware personality leaves masked pixels un-normalised -- in both forms of the dynamic path."""
+    from fluid_llm_b200.dynamic_mesh import DynamicTrajectory
+    from fluid_llm_b200.field_path import AIRFOIL, CYLINDER
+    pers = AIRFOIL if pers_name == "airfoil" else CYLINDER
+    tr = synth.make_dynamic_trajectory("cylinder", 5, mesh_seed=6, field_seed=8)
+    tr["pressure"][2, 50:60, 0] = np.nan
+    tr["velocity"][3, 70, 0] = np.inf
+    tr["velocity"][1, 80, 1] = -np.inf
+    with np.errstate(all="ignore"):
+        want = P.dynamic_ds_get(tr["mesh_pos"], tr["cells"], tr["velocity"], tr["pressure"], 0, 5, 1, personality=pers_name)
+    dt = DynamicTrajectory(tr["mesh_pos"], tr["cells"], tr["velocity"], tr["pressure"])
+    for fb in (False, True):
+        states, mask, _ = dt.interp_patchify(0, 5, 1, PATCH, pers, force_binned=fb)
+        assert np.array_equal(mask.cpu().numpy().astype(bool), want["masks"].astype(bool))
+        s = states.cpu().numpy()
+        assert np.isfinite(s).all()
+        np.testing.assert_allclose(s, want["states"], rtol=1e-6, atol=0)
