@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_double, c_float, c_int, c_int32, c_size_t, c_uint, c_uint8, c_void_p
+from ctypes import POINTER, c_double, c_float, c_int, c_int32, c_size_t, c_uint, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libfluidgrid.so")

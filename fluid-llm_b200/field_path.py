@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from ._lib import FL_MASK_AWARE_NORM, FL_NO_NORM, FlTraj, check, load, stream_ptr
-from .mesh_utils import MeshPlan, PatchTable
+from .mesh_utils import MeshPlan
 
 
 @dataclass(frozen=True)

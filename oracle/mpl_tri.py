@@ -15,7 +15,6 @@ validated with ValueError; the C++ triangulation (orientation fix, neighbours) i
 construction here (matplotlib: lazily, same result).
 """
 import ctypes
-import os
 
 import numpy as np
 
