@@ -12,6 +12,7 @@ namespace {
 
 constexpr int NACC = 6;          // state ch0..2, diff ch0..2
 constexpr int CHUNK_T = 64;      // frames per CTA chunk
+constexpr int DEPTH = 2;         // frames ahead of the one being accumulated
 
 struct Agg { double n, mean, m2; };
 
@@ -40,18 +41,18 @@ __device__ __forceinline__ Agg warp_merge(Agg a) {
 }
 
 // grid: x = pixel tiles (256 pixels each over L*ppx), y = frame chunks.  The loop is bound by memory latency, not by
-// arithmetic: four CTAs per SM (<= 64 registers: the shifts are kept as the fp32 numbers they are) and the loads of the
-// frame after next are issued before the current pair is accumulated.
+// arithmetic: three CTAs per SM (the shifts are kept as the fp32 numbers they are) and the loads of DEPTH frames are in
+// flight while the current pair is accumulated.
 __global__ void __launch_bounds__(256, 4) k_stats_partial(const float* __restrict__ states, const uint8_t* __restrict__ mask,
                                                           int T, int L, int ppx, double* __restrict__ partials) {
     const long npix = (long)L * ppx;
     const long pix = (long)blockIdx.x * 256 + threadIdx.x;
     const int t_begin = blockIdx.y * CHUNK_T;              // pairs (t, t+1) for t in [t_begin, t_end)
     const int t_end = min(T - 1, t_begin + CHUNK_T);
-    // per-thread running sums around a per-thread shift (first accepted sample), fp64
+    // per-thread running sums in fp64; the state sums are taken around a per-thread shift (the first frame's value)
     double cnt[2] = {0.0, 0.0};
     float shift_f[NACC];
-    double s1[NACC], s2[NACC];
+    double s1[NACC], s2[NACC], ks[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int a = 0; a < NACC; ++a) { shift_f[a] = 0.f; s1[a] = 0.0; s2[a] = 0.0; }
     if (pix < npix && t_begin < t_end) {
@@ -59,41 +60,49 @@ __global__ void __launch_bounds__(256, 4) k_stats_partial(const float* __restric
         const size_t fstride = (size_t)L * 3 * ppx, mstride = (size_t)L * ppx;
         const float* sp = states + ((size_t)t_begin * L + l) * 3 * ppx + k;          // channel c at sp[c * ppx]
         const uint8_t* mp = mask + ((size_t)t_begin * L + l) * ppx + k;
-        // three frame buffers rotate through the roles (previous, current, being loaded) with the loop unrolled three
-        // times, so no register move has to wait for the load in flight
-        float f0[3], f1[3], f2[3] = {0.f, 0.f, 0.f};
-        uint8_t m1, m2 = 1, m0 = 1;
+        // DEPTH + 1 frame buffers rotate through the roles (previous, current, DEPTH - 1 frames in flight) with the loop
+        // unrolled DEPTH + 1 times, so the buffer indices are compile-time (registers) and no move waits for a load:
+        // (a deeper ring was measured: no gain, the loop is bound by issue slots and the conversion unit, not by latency)
+        float fb[DEPTH + 1][3];
+        uint8_t mb[DEPTH + 1];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { f0[c] = __ldg(sp + (size_t)c * ppx); f1[c] = __ldg(sp + fstride + (size_t)c * ppx); }
-        m1 = __ldg(mp + mstride);
-        bool first = true;
-        auto fetch = [&](float (&dst)[3], uint8_t& mdst, int t) {       // frame t + 2, needed by the next step
-            if (t + 1 < t_end) {
+        for (int i = 0; i <= DEPTH; ++i) { fb[i][0] = fb[i][1] = fb[i][2] = 0.f; mb[i] = 1; }
 #pragma unroll
-                for (int c = 0; c < 3; ++c) dst[c] = __ldg(sp + 2 * fstride + (size_t)c * ppx);
-                mdst = __ldg(mp + 2 * mstride);
+        for (int i = 0; i < DEPTH; ++i) {                  // frames t_begin .. t_begin + DEPTH - 1
+            if (t_begin + i <= t_end) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) fb[i][c] = __ldg(sp + (size_t)i * fstride + (size_t)c * ppx);
+                mb[i] = __ldg(mp + (size_t)i * mstride);
             }
-            sp += fstride; mp += mstride;
-        };
-        auto accumulate = [&](const float (&prev)[3], const float (&cur)[3], uint8_t mcur) {
-            if (!mcur) {                                    // masks[1:] (simple_dataloader.py:100)
+        }
+        // shift of the state sums: this thread's first frame (masked or not, it is a finite number near the data);
+        // the differences are centred on zero and need none
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float dvf = __fsub_rn(cur[c], prev[c]);
-                    if (first) { shift_f[c] = prev[c]; shift_f[3 + c] = dvf; }
-                    const double a = (double)prev[c] - (double)shift_f[c], b = (double)dvf - (double)shift_f[3 + c];
-                    s1[c] += a; s2[c] += a * a;
-                    s1[3 + c] += b; s2[3 + c] += b * b;
-                }
-                first = false;
-                cnt[0] += 1.0;
-            }
-        };
+        for (int c = 0; c < 3; ++c) { ks[c] = (double)fb[0][c]; shift_f[c] = fb[0][c]; }
         int t = t_begin;
-        while (true) {
-            fetch(f2, m2, t); accumulate(f0, f1, m1); if (++t >= t_end) break;
-            fetch(f0, m0, t); accumulate(f1, f2, m2); if (++t >= t_end) break;
-            fetch(f1, m1, t); accumulate(f2, f0, m0); if (++t >= t_end) break;
+        while (t < t_end) {
+#pragma unroll
+            for (int s = 0; s <= DEPTH; ++s) {
+                if (t < t_end) {
+                    const int ld = (s + DEPTH) % (DEPTH + 1), cu = (s + 1) % (DEPTH + 1);
+                    if (t + DEPTH <= t_end) {               // frame t + DEPTH goes where frame t - 1 was
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) fb[ld][c] = __ldg(sp + (size_t)DEPTH * fstride + (size_t)c * ppx);
+                        mb[ld] = __ldg(mp + (size_t)DEPTH * mstride);
+                    }
+                    if (!mb[cu]) {                          // masks[1:] (simple_dataloader.py:100)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const double a = (double)fb[s][c] - ks[c], b = (double)__fsub_rn(fb[cu][c], fb[s][c]);
+                            s1[c] += a; s2[c] += a * a;
+                            s1[3 + c] += b; s2[3 + c] += b * b;
+                        }
+                        cnt[0] += 1.0;
+                    }
+                    sp += fstride; mp += mstride;
+                    ++t;
+                }
+            }
         }
     }
     double shift[NACC];
