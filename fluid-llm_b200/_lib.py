@@ -13,6 +13,7 @@ FL_FLIP_Y = 1
 FL_MASK_AWARE_NORM = 2
 FL_NO_NORM = 4
 FL_FORCE_GATHER = 8
+FL_FORCE_STAGED = 16
 
 
 class FlTraj(ctypes.Structure):
@@ -20,7 +21,9 @@ class FlTraj(ctypes.Structure):
                 ("d_idx_slot", c_void_p), ("d_node_slot", c_void_p),
                 ("d_states", c_void_p), ("d_mask", c_void_p),
                 ("n_nodes", c_int32), ("t0", c_int32), ("interval", c_int32), ("n_frames", c_int32),
-                ("vel_stride", c_int32), ("prs_stride", c_int32)]
+                ("vel_stride", c_int32), ("prs_stride", c_int32),
+                ("d_idx_tile", c_void_p), ("d_tile_nodes", c_void_p), ("d_tile_desc", c_void_p), ("d_tile_patches", c_void_p),
+                ("n_tiles", c_int32), ("max_tile_nodes", c_int32)]
 
 
 class FluidGridError(RuntimeError):

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfluidgrid.so")
-SOURCES = ["fl_api.cu", "fl_locate.cu", "fl_interp.cu", "fl_dynamic.cu", "fl_patch.cu", "fl_stats.cu", "fl_embed.cu"]
+SOURCES = ["fl_api.cu", "fl_locate.cu", "fl_interp.cu", "fl_tiled.cu", "fl_dynamic.cu", "fl_patch.cu", "fl_stats.cu", "fl_embed.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--use_fast_math=false", "-fmad=true", "-Xcompiler", "-fvisibility=default"]
 
@@ -32,7 +32,7 @@ def sources():
 def needs_build() -> bool:
     if not os.path.exists(OUT):
         return True
-    deps = sources() + [os.path.join(CSRC, "fl_common.cuh"), os.path.join(CSRC, "fl_geom.cuh"), os.path.join(HERE, "..", "include", "fluidgrid.h"),
+    deps = sources() + [os.path.join(CSRC, "fl_common.cuh"), os.path.join(CSRC, "fl_geom.cuh"), os.path.join(CSRC, "fl_interp.cuh"), os.path.join(HERE, "..", "include", "fluidgrid.h"),
                         os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps)
 

@@ -9,7 +9,7 @@
 // to fp32.  Here the same point value is the fp64 barycentric sum w0*z0 + w1*z1 + w2*z2 (weights
 // fp64, from the static table), rounded once to fp32, then (v - mean) and / std in fp32 with
 // IEEE division, i.e. the same two roundings as simple_dataloader.py:213-214.
-#include "fl_geom.cuh"
+#include "fl_interp.cuh"
 #include <string.h>
 #include <stdlib.h>
 #include <math.h>
@@ -17,6 +17,10 @@
 using flg::NormConst;
 using flg::interp3;
 using flg::finite_f;
+using fli::StagedConst;
+using fli::norm_fast;
+using fli::norm_fast2;
+using fli::pack2;
 
 namespace {
 
@@ -108,33 +112,6 @@ __global__ void k_to_grid(const FlCellIdx* __restrict__ idx, const FlCellW* __re
 // ------------------------------------------------------------------------------------------
 constexpr int ST_THREADS = 512;
 constexpr int NP = 4;        // pixels per thread
-
-struct StagedConst {
-    float mean[3], stdv[3], rcp[3];
-    int fast_div;        // 1: Markstein division valid for these constants
-};
-
-// (x - mean) / std, correctly rounded: q = d*r, then one Markstein step with the exact remainder
-__device__ __forceinline__ float norm_fast(float x, float mean, float stdv, float rcp) {
-    float d = __fsub_rn(x, mean);
-    float q = __fmul_rn(d, rcp);
-    float e = __fmaf_rn(-q, stdv, d);
-    return __fmaf_rn(e, rcp, q);
-}
-// two pixels at once on the packed fp32 pipe (FADD2 / FMUL2 / FFMA2): same roundings as norm_fast
-__device__ __forceinline__ unsigned long long pack2(float a, float b) {
-    return ((unsigned long long)__float_as_uint(b) << 32) | __float_as_uint(a);
-}
-__device__ __forceinline__ void norm_fast2(float& x0, float& x1, unsigned long long nm, unsigned long long ns, unsigned long long rc) {
-    const unsigned long long x = pack2(x0, x1);
-    unsigned long long d, q, e, y;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(x), "l"(nm));
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(d), "l"(rc));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(e) : "l"(q), "l"(ns), "l"(d));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(y) : "l"(e), "l"(rc), "l"(q));
-    x0 = __uint_as_float((unsigned)y);
-    x1 = __uint_as_float((unsigned)(y >> 32));
-}
 
 template <bool CHECKED>
 __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned char* __restrict__ s_nodes, int slot_b,
@@ -294,24 +271,19 @@ k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int grou
     }
 }
 
-// host: is (x - mean) / std safe for the reciprocal + Markstein path?
-bool fast_div_ok(const float* mean, const float* stdv) {
-    for (int c = 0; c < 3; ++c) {
-        float s = fabsf(stdv[c]), m = fabsf(mean[c]);
-        uint32_t bits;
-        memcpy(&bits, &s, 4);
-        if (!(s >= 9.5367431640625e-07f && s <= 1048576.f)) return false;        // 2^-20 .. 2^20
-        if ((bits & 0x007fffffu) == 0x007fffffu) return false;                     // Markstein's excluded significand
-        if (!(m >= 9.094947017729282e-13f && m <= 1.152921504606847e18f)) return false;  // 2^-40 .. 2^60, non-zero
-    }
-    return true;
-}
-
 int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int max_frames, int n_patches, int px, int py,
                   const float* h_mean, const float* h_std, unsigned flags, cudaStream_t st) {
     NormConst nc;
     for (int c = 0; c < 3; ++c) { nc.mean[c] = h_mean ? h_mean[c] : 0.f; nc.stdv[c] = h_std ? h_std[c] : 1.f; }
     const int ppx = px * py;
+    // ---- tiled path (fl_tiled.cu): the descriptors carry a tile plan ----
+    if (h_trajs && !(flags & (FL_FORCE_GATHER | FL_FORCE_STAGED))) {
+        StagedConst sc;
+        for (int c = 0; c < 3; ++c) { sc.mean[c] = nc.mean[c]; sc.stdv[c] = nc.stdv[c]; sc.rcp[c] = 1.0f / nc.stdv[c]; }
+        sc.fast_div = (flags & FL_NO_NORM) ? 1 : (fli::fast_div_ok(nc.mean, nc.stdv) ? 1 : 0);
+        const int rc = fli::launch_tiled(d_trajs, h_trajs, n_traj, max_frames, n_patches, px, py, sc, flags, st);
+        if (rc != 1) return rc;          // 1 = no tile plan / does not fit: fall through
+    }
     // ---- staged path: needs the host copy of the descriptors to check strides / alignment ----
     if (h_trajs && ppx % 128 == 0 && !(flags & FL_FORCE_GATHER)) {
         bool ok = true;
@@ -333,7 +305,7 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
         if (TF >= 1) {
             StagedConst sc;
             for (int c = 0; c < 3; ++c) { sc.mean[c] = nc.mean[c]; sc.stdv[c] = nc.stdv[c]; sc.rcp[c] = 1.0f / nc.stdv[c]; }
-            sc.fast_div = (flags & FL_NO_NORM) ? 1 : (fast_div_ok(nc.mean, nc.stdv) ? 1 : 0);
+            sc.fast_div = (flags & FL_NO_NORM) ? 1 : (fli::fast_div_ok(nc.mean, nc.stdv) ? 1 : 0);
             const int gpt = (max_frames + TF - 1) / TF;
             const long n_items = (long)gpt * n_traj;
             const size_t smem = (size_t)TF * frame_bytes;
@@ -364,6 +336,19 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
 
 }  // namespace
 
+// host: is (x - mean) / std safe for the reciprocal + Markstein path?
+bool fli::fast_div_ok(const float* mean, const float* stdv) {
+    for (int c = 0; c < 3; ++c) {
+        float s = fabsf(stdv[c]), m = fabsf(mean[c]);
+        uint32_t bits;
+        memcpy(&bits, &s, 4);
+        if (!(s >= 9.5367431640625e-07f && s <= 1048576.f)) return false;        // 2^-20 .. 2^20
+        if ((bits & 0x007fffffu) == 0x007fffffu) return false;                     // Markstein's excluded significand
+        if (!(m >= 9.094947017729282e-13f && m <= 1.152921504606847e18f)) return false;  // 2^-40 .. 2^60, non-zero
+    }
+    return true;
+}
+
 static int check_trajs(const char* who, const FlTraj* h_trajs, int n_traj, int* max_frames) {
     FL_REQUIRE(h_trajs, FL_E_ARG, "%s: null descriptor array", who);
     FL_REQUIRE(n_traj > 0 && n_traj <= 65535, FL_E_ARG, "%s: n_traj=%d out of range", who, n_traj);
@@ -380,6 +365,9 @@ static int check_trajs(const char* who, const FlTraj* h_trajs, int n_traj, int* 
         FL_REQUIRE((uintptr_t)t.d_velocity % 8 == 0 && (uintptr_t)t.d_idx % 16 == 0 && (uintptr_t)t.d_w % 16 == 0 &&
                        t.vel_stride % 2 == 0,
                    FL_E_ALIGN, "%s: trajectory %d: velocity must be 8-byte aligned with an even stride, tables 16-byte aligned", who, i);
+        FL_REQUIRE((long long)t.interval * t.vel_stride < 0x7fffffffLL, FL_E_ARG, "%s: trajectory %d: interval * vel_stride overflows", who, i);
+        FL_REQUIRE((t.d_idx_slot == nullptr) == (t.d_node_slot == nullptr), FL_E_ARG,
+                   "%s: trajectory %d: d_idx_slot and d_node_slot must be given together", who, i);
         mf = t.n_frames > mf ? t.n_frames : mf;
     }
     *max_frames = mf;

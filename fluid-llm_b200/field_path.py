@@ -106,7 +106,7 @@ class TrajBatch:
     """Pre-built launch descriptors for a fixed batch (descriptor array already on the device), so
     the steady-state call is exactly one kernel launch and no host->device traffic."""
 
-    def __init__(self, trajs, tables, t0s, interval, n_frames, want_mask=True, use_slots=None, out=None):
+    def __init__(self, trajs, tables, t0s, interval, n_frames, want_mask=True, use_slots=None, out=None, tile_patches=None):
         if use_slots is None:
             use_slots = os.environ.get("FLUIDGRID_SLOTS", "1") != "0"
         if not (len(trajs) == len(tables) == len(t0s)) or not trajs:
@@ -134,22 +134,33 @@ class TrajBatch:
         else:
             self.states = torch.empty((self.n_traj, self.n_frames, L, 3, px, py), dtype=torch.float32, device=dev)
             self.mask = torch.empty((self.n_traj, self.n_frames, L, px, py), dtype=torch.uint8, device=dev) if want_mask else None
+        # tile plans (csrc/fl_tiled.cu): one split of the patch grid for the whole batch, sized for its largest mesh
+        ppx = px * py
+        self.tile_plans = None
+        if ppx in (128, 256) and tile_patches != 0:
+            tp = int(tile_patches) if tile_patches else max(tables, key=lambda t: t.n_nodes).default_tile_patches()
+            self.tile_plans = [tab.tile_plan(tp) for tab in tables]
         arr = (FlTraj * self.n_traj)()
         for i, (tr, tab, t0) in enumerate(zip(trajs, tables, t0s)):
+            tpl = self.tile_plans[i] if self.tile_plans else None
             arr[i] = FlTraj(tr.vel_buf.data_ptr(), tr.prs_buf.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(),
                             tab.idx_slot.data_ptr() if use_slots and tab.idx_slot is not None else 0,
                             tr.plan.node_slot_d.data_ptr() if use_slots and tab.idx_slot is not None else 0,
                             self.states[i].data_ptr(), self.mask[i].data_ptr() if want_mask else 0,
-                            tr.plan.n_nodes, int(t0), int(interval), self.n_frames, tr.vel_stride, tr.prs_stride)
+                            tr.plan.n_nodes, int(t0), int(interval), self.n_frames, tr.vel_stride, tr.prs_stride,
+                            tpl.idx_tile.data_ptr() if tpl else 0, tpl.tile_nodes.data_ptr() if tpl else 0,
+                            tpl.tile_desc.data_ptr() if tpl else 0, tpl.tile_patches.data_ptr() if tpl else 0,
+                            tpl.n_tiles if tpl else 0, tpl.max_tile_nodes if tpl else 0)
         self.host_desc = arr
         raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
         self.desc = torch.from_numpy(raw).to(dev)
         self._keep = (trajs, tables)   # keep the device buffers alive
 
-    def run(self, personality: Personality, normalize=True, means=None, stds=None, force_gather=False):
+    def run(self, personality: Personality, normalize=True, means=None, stds=None, force_gather=False, force_staged=False):
         """Enqueue the fused kernel on the current stream; returns (states, mask) device tensors."""
         flags = (FL_MASK_AWARE_NORM if personality.mask_aware_norm else 0) | (0 if normalize else FL_NO_NORM)
         flags |= _lib.FL_FORCE_GATHER if force_gather else 0
+        flags |= _lib.FL_FORCE_STAGED if force_staged else 0
         m = (ctypes.c_float * 3)(*(means if means is not None else personality.means))
         s = (ctypes.c_float * 3)(*(stds if stds is not None else personality.stds))
         tab = self.tab0
@@ -161,13 +172,14 @@ class TrajBatch:
 
 
 def interp_patchify(traj: DeviceTrajectory, step_num: int, seq_len: int, seq_interval: int, patch_size,
-                    personality: Personality, normalize=True, means=None, stds=None, force_gather=False):
+                    personality: Personality, normalize=True, means=None, stds=None, force_gather=False, force_staged=False,
+                    tile_patches=None):
     """One trajectory, frames step_num, step_num+interval, ... -> (states (T,L,3,px,py) f32,
     mask (T,L,px,py) u8, table)."""
     _lib.require_cuda()
     tab = traj.plan.patch_table(patch_size, personality.crop_patches, personality.flip_y)
-    batch = TrajBatch([traj], [tab], [step_num], seq_interval, seq_len)
-    states, mask = batch.run(personality, normalize, means, stds, force_gather)
+    batch = TrajBatch([traj], [tab], [step_num], seq_interval, seq_len, tile_patches=tile_patches)
+    states, mask = batch.run(personality, normalize, means, stds, force_gather, force_staged)
     return states[0], mask[0], tab
 
 

@@ -9,6 +9,7 @@ moves arrays and keeps the reference's argument checks and error behaviour.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 from functools import lru_cache
@@ -66,14 +67,116 @@ def grid_pos(x_min, x_max, y_min, y_max, grid_res, numpy_semantics=None):
             np.ascontiguousarray(np.broadcast_to(ay[None, :], (nx, ny))))
 
 
+SMEM_BYTES = 227 * 1024        # shared memory one CTA can have on sm_100a
+TILE_WARPS = 16                # warps of the tiled kernel's CTA (csrc/fl_tiled.cu)
+
+
+def serpentine_patches(n_bx, n_by):
+    """Patch ids l = bx * n_by + by along a serpentine through the patch grid (up column 0, down column 1, ...):
+    consecutive runs of this order are spatially compact sets of patches."""
+    l = np.arange(n_bx * n_by, dtype=np.int32).reshape(n_bx, n_by)
+    l[1::2] = l[1::2, ::-1]
+    return l.reshape(-1)
+
+
+def tile_sizes(n_patches, tp):
+    """Split n_patches into runs of tp (the last one shorter)."""
+    sizes = [tp] * (n_patches // tp)
+    if n_patches % tp:
+        sizes.append(n_patches % tp)
+    return sizes
+
+
+def choose_tile_patches(n_patches, n_nodes, ppx, max_frames=16):
+    """Patches per tile for the tiled kernel.  Small tiles stage few nodes (so more frames fit in shared memory per
+    work item and the per-pixel table records are amortised over more frames) but repeat the nodes on tile borders;
+    the chunk count of a tile (128 pixels each) should fill the CTA's 16 warps evenly."""
+    env = os.environ.get("FLUIDGRID_TILE_PATCHES")
+    if env:
+        return max(1, min(int(env), n_patches))
+    wpp = max(1, ppx // 128)
+    ring = (TILE_WARPS // wpp) * 2 * ppx * 13
+    stage = (SMEM_BYTES - 256 - ring) // 2
+    best, best_cost = n_patches, None
+    cands = sorted(set([n_patches] + list(range(8 // wpp * wpp or 1, n_patches, 8))))
+    for tp in cands:
+        nodes_in = n_nodes * tp / n_patches
+        s_est = nodes_in + 5.0 * np.sqrt(max(nodes_in, 1.0)) + 8       # nodes of the tile + the ring of nodes around it
+        tf = min(max_frames, int(stage // (16 * s_est)))
+        if tf < 2:
+            continue
+        slots = sum(-(-(t * wpp) // TILE_WARPS) * TILE_WARPS for t in tile_sizes(n_patches, tp))
+        balance = n_patches * wpp / slots
+        halo = s_est / max(nodes_in, 1.0)
+        # per pixel-frame: 1 (the frame loop) + table set-up per item / frames + node staging share
+        cost = (1.0 + 0.8 / tf + 0.15 * (halo - 1.0)) / balance
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = tp, cost
+    return best
+
+
+class TilePlan:
+    """The patch table split into tiles for csrc/fl_tiled.cu (FlTraj::d_idx_tile, d_tile_*)."""
+
+    def __init__(self, idx_tile, tile_nodes, tile_desc, tile_patches, n_tiles, max_tile_nodes, tp):
+        self.idx_tile, self.tile_nodes, self.tile_desc, self.tile_patches = idx_tile, tile_nodes, tile_desc, tile_patches
+        self.n_tiles, self.max_tile_nodes, self.tp = n_tiles, max_tile_nodes, tp
+
+
 class PatchTable:
     """The static table re-ordered into output-pixel order for one dataset personality.
     `idx_slot` is the same table with node ids replaced by the plan's shared-memory slots."""
 
-    def __init__(self, idx, w, n_bx, n_by, px, py, idx_slot=None):
+    def __init__(self, idx, w, n_bx, n_by, px, py, idx_slot=None, n_nodes=0):
         self.idx, self.w, self.n_bx, self.n_by, self.px, self.py = idx, w, n_bx, n_by, px, py
         self.idx_slot = idx_slot
         self.n_patches = n_bx * n_by
+        self.n_nodes = n_nodes
+        self._tile_plans = {}
+
+    def default_tile_patches(self):
+        return choose_tile_patches(self.n_patches, self.n_nodes, self.px * self.py)
+
+    def tile_plan(self, tp=None) -> TilePlan:
+        """Tiles = runs of `tp` patches along the serpentine; per tile the sorted list of the nodes its pixels touch,
+        and the table with node ids replaced by 16 * (position in that list).  Index bookkeeping only (one sort of
+        3 * pixels keys on the device); built once per table and tile size."""
+        tp = int(tp) if tp else self.default_tile_patches()
+        plan = self._tile_plans.get(tp)
+        if plan is not None:
+            return plan
+        dev = self.idx.device
+        L, ppx, N = self.n_patches, self.px * self.py, max(int(self.n_nodes), 1)
+        order = serpentine_patches(self.n_bx, self.n_by)
+        sizes = tile_sizes(L, tp)
+        n_tiles = len(sizes)
+        patch_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        tile_of_patch = np.empty(L, dtype=np.int64)
+        tile_of_patch[order] = np.repeat(np.arange(n_tiles), sizes)
+        with (torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()):
+            tile_px = torch.from_numpy(tile_of_patch).to(dev).repeat_interleave(ppx)            # tile of every output pixel
+            inside = self.idx[:, 3] >= 0
+            sentinel = n_tiles * N
+            key = torch.where(inside.unsqueeze(1), tile_px.unsqueeze(1) * N + self.idx[:, :3].long(),
+                              torch.full((1, 1), sentinel, dtype=torch.int64, device=dev))
+            uniq, inv = torch.unique(key.reshape(-1), return_inverse=True)                    # sorted: tile-major, node ids ascending
+            n_valid = int((uniq < sentinel).sum().item())
+            u_tile = uniq[:n_valid] // N
+            counts = torch.bincount(u_tile, minlength=n_tiles)
+            node_off = torch.cumsum(counts, 0) - counts
+            local = (inv.reshape(-1, 3) - node_off[tile_px].unsqueeze(1)) * 16                  # byte offset of the node's record
+            idx_tile = torch.cat([torch.where(inside.unsqueeze(1), local, torch.zeros_like(local)).to(torch.int32),
+                                  self.idx[:, 3:4]], dim=1).contiguous()
+            tile_nodes = (uniq[:n_valid] % N).to(torch.int32).contiguous()
+            if tile_nodes.numel() == 0:
+                tile_nodes = torch.zeros(4, dtype=torch.int32, device=dev)
+            desc = torch.stack([node_off, counts, torch.from_numpy(patch_off[:-1]).to(dev),
+                                torch.from_numpy(np.asarray(sizes, dtype=np.int64)).to(dev)], dim=1).to(torch.int32).contiguous()
+            tile_patches = torch.from_numpy(order).to(dev)
+            max_nodes = int(counts.max().item()) if n_tiles else 0
+        plan = TilePlan(idx_tile, tile_nodes, desc, tile_patches, n_tiles, max_nodes, tp)
+        self._tile_plans[tp] = plan
+        return plan
 
 
 def morton_slots(pos32, n_padded):
@@ -209,7 +312,7 @@ class MeshPlan:
                 inside = (idx[:, 3] >= 0).unsqueeze(1)
                 slots = self.node_slot_d[idx[:, :3].clamp(min=0, max=self.n_nodes - 1).long()]
                 idx_slot = torch.cat([torch.where(inside, slots, idx[:, :3]), idx[:, 3:4]], dim=1).contiguous()
-            tab = PatchTable(idx, w, nbx.value, nby.value, px, py, idx_slot)
+            tab = PatchTable(idx, w, nbx.value, nby.value, px, py, idx_slot, self.n_nodes)
             self._tables[key] = tab
         return tab
 

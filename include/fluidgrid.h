@@ -32,13 +32,14 @@ extern "C" {
 #define FL_E_WORKSPACE (-3)/* workspace too small */
 #define FL_E_ALIGN (-4)    /* pointer not aligned as documented */
 
-#define FL_ABI_VERSION 6
+#define FL_ABI_VERSION 7
 
 /* personality flags of fl_plan_patch_table / fl_interp_patchify */
 #define FL_FLIP_Y 1u          /* airfoil_ds.py:80  -- y axis reversed after padding */
 #define FL_MASK_AWARE_NORM 2u /* airfoil_ds.py:236-242 -- masked pixels stay 0, others normalised */
 #define FL_NO_NORM 4u         /* normalize=False */
-#define FL_FORCE_GATHER 8u    /* testing: never pick the staged kernel */
+#define FL_FORCE_GATHER 8u    /* testing: always the gather-from-global kernel */
+#define FL_FORCE_STAGED 16u   /* testing: ignore the tile plan (whole-mesh staged kernel, or the gather kernel) */
 
 /* One grid cell of the static per-mesh table (the product's own intermediate; the reference
  * recomputes the plane coefficients of every triangle per channel per frame instead,
@@ -101,6 +102,14 @@ typedef struct FlTraj {
     int32_t n_nodes, t0, interval, n_frames;
     int32_t vel_stride;        /* floats between consecutive frames of d_velocity (>= 2*n_nodes) */
     int32_t prs_stride;        /* floats between consecutive frames of d_pressure (>= n_nodes)   */
+    /* optional tile plan of the patch table (all NULL / 0 = none): the output patches are split into tiles, each with the
+     * list of mesh nodes its pixels touch, so that only a tile's nodes are staged in shared memory -- meshes of any size
+     * run the shared-memory kernel.  Every trajectory of a call must use the same split of the patches into tiles. */
+    const FlCellIdx* d_idx_tile;   /* [L*px*py] d_idx with node ids replaced by 16 * (slot of the node in its tile's list) */
+    const int32_t* d_tile_nodes;   /* the tiles' node lists, one after the other (node ids ascending inside a tile) */
+    const int32_t* d_tile_desc;    /* [n_tiles][4] = {first entry in d_tile_nodes, nodes, first entry in d_tile_patches, patches} */
+    const int32_t* d_tile_patches; /* the tiles' patch ids l, one after the other */
+    int32_t n_tiles, max_tile_nodes;
 } FlTraj;
 /* prs_stride a multiple of 4, vel_stride >= 2 * prs_stride, 16-byte aligned bases and pad floats
  * that are readable and finite select the staged kernel: whole frames are staged in shared memory

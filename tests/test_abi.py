@@ -22,13 +22,14 @@ def test_library_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/fluidgrid.h but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES and the header disagree"
-    assert lib.fl_abi_version() == 6
+    assert lib.fl_abi_version() == 7
 
 
 def test_struct_layout_matches_header():
     from fluid_llm_b200._lib import FlTraj
-    assert ctypes.sizeof(FlTraj) == 8 * 8 + 6 * 4
+    assert ctypes.sizeof(FlTraj) == 8 * 8 + 6 * 4 + 4 * 8 + 2 * 4 == 128
     assert FlTraj.n_nodes.offset == 64 and FlTraj.prs_stride.offset == 84
+    assert FlTraj.d_idx_tile.offset == 88 and FlTraj.n_tiles.offset == 120 and FlTraj.max_tile_nodes.offset == 124
 
 
 def test_argument_errors_without_a_device(lib):
