@@ -1,29 +1,32 @@
-// fl_tiled.cu -- the per-step kernel, tiled form: gather -> fp64 FMA -> fp32 -> mask -> normalise -> patchify for meshes
-// of ANY size out of shared memory.
+// fl_tiled.cu -- the per-step kernel, tiled and warp-specialised: gather -> fp64 FMA -> fp32 -> mask -> normalise ->
+// patchify for meshes of ANY size out of shared memory.
 //
 // Same work and the same arithmetic as k_interp_patchify_staged (fl_interp.cu; replaces simple_dataloader.py:104-152,
 // 166-216 / airfoil_ds.py:71-139,216-244 of the reference), reorganised around what ncu showed to bound that kernel
 // (profiles/README.md): the L1/shared data pipe carried the gathers AND 12 scalar global stores per 4 pixel-frames, the
 // conversion unit 9 fp32->fp64 conversions per pixel-frame, and staging was serialised behind a CTA-wide barrier.
 //
-//   tiles     the output patches are split into tiles (runs of patches along a serpentine through the patch grid); a
-//             tile's node list holds exactly the mesh nodes its pixels touch (FlTraj::d_tile_*), and the table carries
-//             tile-local slots.  A work item = one tile x TF consecutive selected frames of one trajectory, so shared
-//             memory holds TF x (nodes of ONE tile) records whatever the size of the mesh.
-//   records   16 bytes per node and frame, ALREADY in fp64 form: the high words of (double)u, (double)v, (double)p and
-//             one word with the three non-zero bits of each low word (a float widened to double has 29 zero bits at the
-//             bottom).  A vertex costs one LDS.128 + three PRMT instead of one LDS.128 + two F2F.F64.F32: the conversion
-//             unit only sees the three results per pixel-frame.
-//   staging   double buffered and spread over the compute loop: while a warp works through the TF frames of a chunk,
-//             each of its threads loads one node of the NEXT item per frame iteration (issued before the gathers,
-//             written to the other buffer after the stores), so the global-load latency hides behind the arithmetic and
-//             the only CTA-wide barrier is the buffer swap.
-//   output    results go to a per-patch shared-memory tile ([3][px*py] floats + px*py mask bytes, conflict-free
-//             STS.32) and leave as ONE bulk copy (cp.async.bulk shared -> global, 3 KB) per frame and patch, issued by
-//             one thread of the warps that share the patch; two tiles per patch group, so the copy of frame f overlaps
-//             the arithmetic of frame f+1.  No global store goes through the LSU.
+//   tiles      the output patches are split into tiles (runs of patches along a serpentine through the patch grid); a
+//              tile's node list holds exactly the mesh nodes its pixels touch (FlTraj::d_tile_*), and the table carries
+//              tile-local slots.  A work item = one tile x TF consecutive selected frames of one trajectory, so shared
+//              memory holds TF x (nodes of ONE tile) records whatever the size of the mesh.
+//   records    16 bytes per node and frame with u and v ALREADY in fp64 form: their high words plus one word with the
+//              three non-zero bits of each low word (a float widened to double has 29 zero bits at the bottom), and p
+//              as fp32.  A vertex costs one LDS.128 + two PRMT (written in place next to the high words) + one
+//              F2F.F64.F32 instead of one LDS.128 + two F2F: half the load on the conversion unit per vertex.
+//   producers  the last warps of the CTA only stage: they walk the CTA's items, load the tile's nodes frame by frame
+//              (several frames in flight per thread), convert, write the records of item k into buffer k & 1 and arrive
+//              on its `full` mbarrier; they wait on `empty` before overwriting a buffer.
+//   consumers  the other warps never meet at a CTA-wide barrier.  The (item, patch) units of the CTA form one sequence
+//              and are dealt round-robin to the patch groups (the warps that share a patch), so a group that is ahead
+//              simply starts on the next item as soon as its buffer is full; every consumer warp arrives on `empty`
+//              when it is done with an item.
+//   output     results go to a per-group shared-memory tile ([3][px*py] floats + px*py mask bytes, conflict-free
+//              STS.32) and leave as ONE bulk copy (cp.async.bulk shared -> global, 3 KB) per frame and patch, issued by
+//              one thread of the group; two tiles per group, so the copy of frame f overlaps the arithmetic of frame
+//              f+1.  No global store goes through the LSU.
 // HBM traffic per frame: 12 P (+ P mask) written, 12 x (sum of the tiles' node counts) read (= 12 N plus the halo
-// nodes shared by neighbouring tiles, most of which hit L2 because the tiles of a frame group run at the same time).
+// nodes shared by neighbouring tiles, part of which hit L2 because the tiles of a frame group run at the same time).
 #include "fl_interp.cuh"
 #include <stdlib.h>
 
@@ -39,7 +42,9 @@ constexpr int TL_THREADS = 512;
 constexpr int TL_WARPS = TL_THREADS / 32;
 constexpr int NP = 4;                        // pixels per thread and chunk; a chunk = 128 consecutive output pixels
 constexpr int SMEM_TOTAL = 227 * 1024;
-constexpr int ITEM_WORDS = 32;               // decoded work item kept in shared memory (two of them)
+constexpr int ITEM_BYTES = 128;              // decoded work item kept in shared memory (two of them)
+constexpr int HEAD_BYTES = 2 * ITEM_BYTES + 128;   // items + mbarriers
+constexpr int STAGE_BATCH = 8;               // frames a producer thread keeps in flight
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
@@ -48,19 +53,24 @@ __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t b
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void group_sync(int id, int nthreads) {
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void mb_init(uint32_t bar, unsigned n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(n) : "memory"); }
+__device__ __forceinline__ void mb_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mb_wait(uint32_t bar, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nTL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TL_DONE;\nbra TL_WAIT;\nTL_DONE:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts32u(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
 }
 __device__ __forceinline__ float2 ldg_stream2(const float* p) {
     float2 r;
@@ -73,54 +83,71 @@ __device__ __forceinline__ float ldg_stream1(const float* p) {
     return r;
 }
 
-// node record: {hi(p), hi(u), low-word bits, hi(v)}; the three bytes of `bits` hold the top byte of the low words
+// node record {bits, hi(u), p, hi(v)}: u and v already widened to fp64 (high words; byte 0 / 1 of `bits` = the top byte of
+// their low words, whose other 29 bits are zero for a widened float), p still fp32
 __device__ __forceinline__ uint4 make_record(float u, float v, float p) {
-    const double du = (double)u, dv = (double)v, dp = (double)p;
-    const uint32_t bits = ((uint32_t)__double2loint(du) >> 24) | (((uint32_t)__double2loint(dv) >> 24) << 8) |
-                          (((uint32_t)__double2loint(dp) >> 24) << 16);
-    return make_uint4((uint32_t)__double2hiint(dp), (uint32_t)__double2hiint(du), bits, (uint32_t)__double2hiint(dv));
+    const double du = (double)u, dv = (double)v;
+    const uint32_t bits = ((uint32_t)__double2loint(du) >> 24) | (((uint32_t)__double2loint(dv) >> 24) << 8);
+    return make_uint4(bits, (uint32_t)__double2hiint(du), __float_as_uint(p), (uint32_t)__double2hiint(dv));
 }
-__device__ __forceinline__ double rec_u(const uint4& a) { return __hiloint2double((int)a.y, (int)__byte_perm(a.z, 0u, 0x0444)); }
-__device__ __forceinline__ double rec_v(const uint4& a) { return __hiloint2double((int)a.w, (int)__byte_perm(a.z, 0u, 0x1444)); }
-__device__ __forceinline__ double rec_p(const uint4& a) { return __hiloint2double((int)a.x, (int)__byte_perm(a.z, 0u, 0x2444)); }
+// one 128-bit gather -> the three doubles.  Written on the 64-bit halves so that u and v are completed IN PLACE (one PRMT
+// each writes the low word next to the high word that is already there); p takes the one F2F.F64.F32.
+__device__ __forceinline__ void load_record(uint32_t addr, double& u, double& v, double& p) {
+    unsigned long long A, B;        // A = {bits, hi(u)}, B = {p as float, hi(v)}
+    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(A), "=l"(B) : "r"(addr));
+    const uint32_t bits = (uint32_t)A;
+    p = (double)__uint_as_float((uint32_t)B);
+    v = __longlong_as_double((long long)((B & 0xffffffff00000000ull) | __byte_perm(bits, 0u, 0x1444)));
+    u = __longlong_as_double((long long)((A & 0xffffffff00000000ull) | __byte_perm(bits, 0u, 0x0444)));
+}
 
-// A decoded work item (tile x frame group of one trajectory), written to shared memory by one warp.
-struct Item {
+// A decoded work item (tile x frame group of one trajectory), written to shared memory by a producer thread.
+struct alignas(128) Item {
     const float* vel;        // node fields at the item's first selected frame
     const float* prs;
-    int vstep, pstep;        // floats between selected frames (interval * stride)
     const int* nodes;        // the tile's node list
     const int* patches;      // the tile's patch ids
     const int4* idx;         // table with tile-local slots * 16
     const double2* w;
     float* states;           // output at the item's first frame
     uint8_t* mask;           // or NULL
-    int n_nodes, n_patches, nf, valid;
+    const int4* qslots;      // per quad (4 consecutive node ids) the tile touches: the slots of its 4 nodes (-1: not a node of this tile)
+    const int* quads;        // the quads' ids (node id / 4), ascending
+    int vstep, pstep;        // floats between selected frames (interval * stride)
+    int n_nodes, n_patches, nf;
+    int q_cnt, q_max;        // quads of the tile (0: stage node by node); q_max = the largest quad id + 1
+    int bad;                 // 1: non-finite / huge node values (or constants unfit for the fast division): checked path
 };
-static_assert(sizeof(Item) <= ITEM_WORDS * 4, "Item does not fit its shared-memory slot");
+static_assert(sizeof(Item) == ITEM_BYTES, "Item must fill its shared-memory slot");
 
 struct TiledArgs {
     const FlTraj* trajs;
     int n_items, groups, n_tiles, TF, n_patches, slot_rec;   // slot_rec: records per staged frame
     StagedConst sc;
     unsigned flags;
+    unsigned dbg;     // development ablations (FLUIDGRID_DBG): 1 no proxy fence, 2 no bulk copies, 4 producers stage nothing, 8 no group barrier, 16 no L2 prefetch, 32 node-by-node staging, 64 consumers compute nothing
 };
 
 __device__ __forceinline__ void decode_item(const TiledArgs& a, int item, int ppx, Item* out) {
     Item it;
-    it.valid = item < a.n_items;
-    if (!it.valid) { it.nf = 0; it.n_nodes = 0; it.n_patches = 0; *out = it; return; }
     const int tile = item % a.n_tiles;
     const int jg = item / a.n_tiles;
     const int g = jg % a.groups, j = jg / a.groups;
     const FlTraj tr = a.trajs[j];
     const int fbeg = g * a.TF;
     it.nf = max(0, min(a.TF, tr.n_frames - fbeg));
-    const int4 d = __ldg((const int4*)tr.d_tile_desc + tile);
+    const int4 d = __ldg((const int4*)tr.d_tile_desc + 2 * tile), e = __ldg((const int4*)tr.d_tile_desc + 2 * tile + 1);
     it.nodes = tr.d_tile_nodes + d.x;
     it.n_nodes = it.nf > 0 ? d.y : 0;
     it.patches = tr.d_tile_patches + d.z;
     it.n_patches = it.nf > 0 ? d.w : 0;
+    // coalesced quad staging needs 16-byte aligned frames whose pitch covers whole quads (the padded layout of the host package)
+    const bool quads = tr.d_tile_qslots && tr.vel_stride % 4 == 0 && tr.prs_stride % 4 == 0 && ((uintptr_t)tr.d_velocity % 16 == 0) &&
+                       ((uintptr_t)tr.d_pressure % 16 == 0) && 4 * e.z <= tr.prs_stride && 8 * e.z <= tr.vel_stride;
+    it.q_max = e.z;
+    it.q_cnt = quads && it.nf > 0 ? e.y : 0;
+    it.qslots = (const int4*)tr.d_tile_qslots + e.x;
+    it.quads = tr.d_tile_quads + e.x;
     const long long t = (long long)tr.t0 + (long long)fbeg * tr.interval;
     it.vel = tr.d_velocity + t * tr.vel_stride;
     it.prs = tr.d_pressure + t * tr.prs_stride;
@@ -130,6 +157,7 @@ __device__ __forceinline__ void decode_item(const TiledArgs& a, int item, int pp
     it.w = (const double2*)tr.d_w;
     it.states = tr.d_states + (size_t)fbeg * a.n_patches * 3 * ppx;
     it.mask = tr.d_mask ? tr.d_mask + (size_t)fbeg * a.n_patches * ppx : nullptr;
+    it.bad = a.sc.fast_div ? 0 : 1;
     *out = it;
 }
 
@@ -143,38 +171,155 @@ struct Scan {
     __device__ __forceinline__ int bad() const { return !(nanacc == 0.f) || amax > 1.0e30f; }
 };
 
-// stage node `s` of item `nx` for all its frames (not overlapped: prologue, warps without a chunk, left-over nodes)
-__device__ __forceinline__ void stage_node_all_frames(const Item* nxs, int s, uint32_t sbuf, int slot_rec, int f0, Scan& sc) {
-    const int n = __ldg(nxs->nodes + s);
-    const int vstep = nxs->vstep, pstep = nxs->pstep, nf = nxs->nf;
-    const float* vp = nxs->vel + 2 * (size_t)n + (size_t)f0 * vstep;
-    const float* pp = nxs->prs + (size_t)n + (size_t)f0 * pstep;
-    uint32_t dst = sbuf + ((uint32_t)f0 * slot_rec + s) * 16u;
-    for (int f = f0; f < nf; ++f, vp += vstep, pp += pstep, dst += slot_rec * 16u) {
-        const float2 va = ldg_stream2(vp);
-        const float pa = ldg_stream1(pp);
-        sc.add(va.x, va.y, pa);
-        sts128(dst, make_record(va.x, va.y, pa));
+// ---- producer warps -------------------------------------------------------------------------------------------------
+// nodes `s` and `s2` of the item (s2 < 0: none), all their frames, the loads of STAGE_BATCH frames of both in flight at once
+__device__ __forceinline__ void stage_nodes(const Item* it, int s, int s2, uint32_t sbuf, int slot_rec, Scan& sc) {
+    const bool two = s2 >= 0;
+    const int n = __ldg(it->nodes + s), n2 = two ? __ldg(it->nodes + s2) : 0;
+    const int vstep = it->vstep, pstep = it->pstep, nf = it->nf;
+    const float* vp = it->vel + 2 * (size_t)n;
+    const float* pp = it->prs + (size_t)n;
+    const float* vq = it->vel + 2 * (size_t)n2;
+    const float* pq = it->prs + (size_t)n2;
+    uint32_t dst = sbuf + (uint32_t)s * 16u, dst2 = sbuf + (uint32_t)(two ? s2 : 0) * 16u;
+    for (int f0 = 0; f0 < nf; f0 += STAGE_BATCH) {
+        float2 v[STAGE_BATCH], v2[STAGE_BATCH];
+        float p[STAGE_BATCH], p2[STAGE_BATCH];
+#pragma unroll
+        for (int i = 0; i < STAGE_BATCH; ++i)
+            if (f0 + i < nf) {
+                v[i] = ldg_stream2(vp + (size_t)i * vstep);
+                p[i] = ldg_stream1(pp + (size_t)i * pstep);
+                if (two) { v2[i] = ldg_stream2(vq + (size_t)i * vstep); p2[i] = ldg_stream1(pq + (size_t)i * pstep); }
+            }
+        vp += (size_t)STAGE_BATCH * vstep; pp += (size_t)STAGE_BATCH * pstep;
+        vq += (size_t)STAGE_BATCH * vstep; pq += (size_t)STAGE_BATCH * pstep;
+#pragma unroll
+        for (int i = 0; i < STAGE_BATCH; ++i)
+            if (f0 + i < nf) {
+                sc.add(v[i].x, v[i].y, p[i]);
+                sts128(dst, make_record(v[i].x, v[i].y, p[i]));
+                dst += (uint32_t)slot_rec * 16u;
+                if (two) {
+                    sc.add(v2[i].x, v2[i].y, p2[i]);
+                    sts128(dst2, make_record(v2[i].x, v2[i].y, p2[i]));
+                    dst2 += (uint32_t)slot_rec * 16u;
+                }
+            }
     }
 }
 
-// One chunk (128 output pixels of one patch) x the item's frames, with the staging of one node of the next item folded into
-// the frame loop.  WPP = warps per patch (ppx / 128); the WPP warps of a patch group share two output tiles.
+// Coalesced form: the tile's nodes lie in q_cnt quads of 4 consecutive node ids (listed ascending, so runs of nodes are runs
+// of quads); a thread takes one quad x 4 frames (two 128-bit loads of velocities and one of pressures per frame,
+// consecutive threads on consecutive list entries) and writes the records of the nodes the tile uses to their slots.
+__device__ __forceinline__ float4 ldg_stream4f(const float* p) { return fl_ldg_stream4((const float4*)p); }
+__device__ __forceinline__ void stage_quads(const Item* it, int ptid, int PT, uint32_t sbuf, int slot_rec, Scan& sc) {
+    constexpr int FB = 4;
+    const int qc = it->q_cnt, nf = it->nf, vstep = it->vstep, pstep = it->pstep;
+    const int nfb = (nf + FB - 1) / FB;
+    const float* vel = it->vel;
+    const float* prs = it->prs;
+    const int4* qs = it->qslots;
+    const int* qid = it->quads;
+    int u = ptid;
+    int4 sl_n = make_int4(-1, -1, -1, -1);
+    int q_n = 0;
+    if (u < qc * nfb) { const int e = u % qc; sl_n = __ldg(qs + e); q_n = __ldg(qid + e); }
+    for (; u < qc * nfb; u += PT) {
+        const int fb = u / qc;
+        const int f0 = fb * FB;
+        const int4 sl = sl_n;
+        const int q = q_n;
+        if (u + PT < qc * nfb) { const int e = (u + PT) % qc; sl_n = __ldg(qs + e); q_n = __ldg(qid + e); }   // next entry: off the critical path
+        const float* vp = vel + (size_t)f0 * vstep + 8 * (size_t)q;
+        const float* pp = prs + (size_t)f0 * pstep + 4 * (size_t)q;
+        float4 va[FB], vb[FB], pq[FB];
+#pragma unroll
+        for (int i = 0; i < FB; ++i)
+            if (f0 + i < nf) {
+                va[i] = ldg_stream4f(vp + (size_t)i * vstep);
+                vb[i] = ldg_stream4f(vp + (size_t)i * vstep + 4);
+                pq[i] = ldg_stream4f(pp + (size_t)i * pstep);
+            }
+        uint32_t dst = sbuf + (uint32_t)f0 * slot_rec * 16u;
+#pragma unroll
+        for (int i = 0; i < FB; ++i)
+            if (f0 + i < nf) {
+                if (sl.x >= 0) { sc.add(va[i].x, va[i].y, pq[i].x); sts128(dst + 16u * sl.x, make_record(va[i].x, va[i].y, pq[i].x)); }
+                if (sl.y >= 0) { sc.add(va[i].z, va[i].w, pq[i].y); sts128(dst + 16u * sl.y, make_record(va[i].z, va[i].w, pq[i].y)); }
+                if (sl.z >= 0) { sc.add(vb[i].x, vb[i].y, pq[i].z); sts128(dst + 16u * sl.z, make_record(vb[i].x, vb[i].y, pq[i].z)); }
+                if (sl.w >= 0) { sc.add(vb[i].z, vb[i].w, pq[i].w); sts128(dst + 16u * sl.w, make_record(vb[i].z, vb[i].w, pq[i].w)); }
+                dst += (uint32_t)slot_rec * 16u;
+            }
+    }
+}
+
+// Ask L2 for the node fields item `item` will stage: per frame the span of the tile's node ids (the list is ascending), one
+// bulk prefetch for the velocities and one for the pressures.  Thread i of the producers takes frame i.  The spans are
+// clipped to whole 16-byte units inside the frame, so nothing outside the caller's arrays is touched.
+__device__ __forceinline__ void prefetch_item(const TiledArgs& a, int item, int ptid) {
+    if (item >= a.n_items || ptid >= a.TF) return;
+    const int tile = item % a.n_tiles;
+    const int jg = item / a.n_tiles;
+    const int g = jg % a.groups, j = jg / a.groups;
+    const FlTraj* tr = a.trajs + j;
+    const int f = g * a.TF + ptid;
+    if (f >= tr->n_frames) return;
+    const int4 d = __ldg((const int4*)tr->d_tile_desc + 2 * tile);
+    if (d.y < 1) return;
+    const int n0 = __ldg(tr->d_tile_nodes + d.x), n1 = __ldg(tr->d_tile_nodes + d.x + d.y - 1) + 1;     // [n0, n1)
+    const long long t = (long long)tr->t0 + (long long)f * tr->interval;
+    const uintptr_t v0 = ((uintptr_t)(tr->d_velocity + t * tr->vel_stride + 2 * (size_t)n0) + 15) & ~(uintptr_t)15;
+    const uintptr_t v1 = (uintptr_t)(tr->d_velocity + t * tr->vel_stride + 2 * (size_t)n1) & ~(uintptr_t)15;
+    const uintptr_t p0 = ((uintptr_t)(tr->d_pressure + t * tr->prs_stride + (size_t)n0) + 15) & ~(uintptr_t)15;
+    const uintptr_t p1 = (uintptr_t)(tr->d_pressure + t * tr->prs_stride + (size_t)n1) & ~(uintptr_t)15;
+    if (v1 > v0) l2_prefetch_bulk((const void*)v0, (uint32_t)(v1 - v0));
+    if (p1 > p0) l2_prefetch_bulk((const void*)p0, (uint32_t)(p1 - p0));
+}
+
+template <int PROD_WARPS>
+__device__ __forceinline__ void producer_loop(const TiledArgs& a, Item* s_items, uint32_t bar_full, uint32_t bar_empty, uint32_t stage0,
+                                              uint32_t stage_bytes, int ppx) {
+    constexpr int PT = PROD_WARPS * 32;
+    const int ptid = threadIdx.x;          // the producers are the first warps of the CTA
+    int k = 0;
+    if (!(a.dbg & 16u)) prefetch_item(a, blockIdx.x, ptid);
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
+        const int b = k & 1;
+        if (!(a.dbg & 16u)) prefetch_item(a, item + gridDim.x, ptid);      // the next item's fields are in L2 by the time its buffer is free
+        if (k >= 2) mb_wait(bar_empty + 8u * b, ((k >> 1) - 1) & 1);       // every consumer warp is done with item k - 2
+        if (ptid == 0) decode_item(a, item, ppx, &s_items[b]);
+        named_sync(15, PT);
+        const Item* it = &s_items[b];
+        Scan scan;
+        const int S = it->n_nodes;
+        if (!(a.dbg & 4u) || k < 2) {
+            if (it->q_cnt > 0 && !(a.dbg & 32u)) stage_quads(it, ptid, PT, stage0 + (uint32_t)b * stage_bytes, a.slot_rec, scan);
+            else for (int s = ptid; s < S; s += PT) stage_nodes(it, s, -1, stage0 + (uint32_t)b * stage_bytes, a.slot_rec, scan);
+        }
+        if (__any_sync(0xffffffffu, scan.bad()) && (threadIdx.x & 31) == 0) atomicOr(&s_items[b].bad, 1);
+        mb_arrive(bar_full + 8u * b);           // release: the records (and the bad flag) are visible to whoever waits
+    }
+}
+
+// ---- consumer warps -------------------------------------------------------------------------------------------------
+// One chunk (128 output pixels of one patch) x the item's frames.  WPP = warps per patch (ppx / 128); the WPP warps of a
+// patch group share two output tiles and the named barrier 1 + group.
 template <bool CHECKED, int WPP>
-__device__ __forceinline__ void chunk_frames(const Item* cs, const Item* nxs, int chunk, uint32_t stage_cur, uint32_t stage_nxt,
-                                             int job, uint32_t ring, int& parity, const TiledArgs& a, Scan& scan) {
+__device__ __forceinline__ void chunk_frames(const Item* cs, int unit, uint32_t stage_cur, uint32_t tile0, int group, int& parity,
+                                             const TiledArgs& a) {
     constexpr int ppx = 128 * WPP;
     constexpr uint32_t TILE_BYTES = ppx * 13;       // [3][ppx] floats + ppx mask bytes
-    const int lane_id = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sub = WPP == 1 ? 0 : (chunk % WPP);
+    const int lane_id = threadIdx.x & 31;
+    const int sub = WPP == 1 ? 0 : ((threadIdx.x >> 5) % WPP);       // the producer warps come in pairs, so parity is kept
     const bool leader = sub == 0 && lane_id == 0;
-    const int bar_id = 1 + warp / WPP;
+    const int bar_id = 1 + group;
     const bool mask_aware = a.flags & FL_MASK_AWARE_NORM, no_norm = a.flags & FL_NO_NORM;
     // pixel of this lane inside a group of 32 adjacent pixels (2 patch rows x 16): the 8 lanes of a quarter-warp (one
     // LDS.128 wavefront) take a compact 2 x 4 block, which touches fewer distinct nodes than a 1 x 8 strip
     const int lane = ((lane_id >> 2) & 1) * 16 + (lane_id >> 3) * 4 + (lane_id & 3);
-    // the items live in shared memory (uniform reads); only what the frame loop needs is kept in registers
-    const int patch = __ldg(cs->patches + chunk / WPP);
+    // the item lives in shared memory (uniform reads); only what the frame loop needs is kept in registers
+    const int patch = __ldg(cs->patches + unit);
     const int o = patch * ppx + sub * 128 + lane;
     const int4* idx_tab = cs->idx;
     const double2* w_tab = cs->w;
@@ -208,11 +353,10 @@ __device__ __forceinline__ void chunk_frames(const Item* cs, const Item* nxs, in
     };
     const bool want_mask = cs->mask != nullptr;
     const int nf = cs->nf;
-    // the patch group's two output tiles; element (c, pixel k of the patch) at c * ppx + k, mask bytes behind the floats
-    const uint32_t tile0 = ring + (uint32_t)(warp / WPP) * 2u * TILE_BYTES;
+    // element (c, pixel k of the patch) of a tile at c * ppx + k, mask bytes behind the floats
     const uint32_t my_f = (uint32_t)(sub * 128 + lane) * 4u, my_m = 3u * ppx * 4u + (uint32_t)(sub * 128 + 4 * lane_id);
     if (leader) bulk_wait_read0();                    // both tiles are free (this thread issued every copy that read them)
-    if (WPP > 1) group_sync(bar_id, 32 * WPP); else __syncwarp();
+    if (WPP > 1) named_sync(bar_id, 32 * WPP); else __syncwarp();
     if (!CHECKED && want_mask) {
         const unsigned mw = mask_word(mbits);
         sts32u(tile0 + my_m, mw);
@@ -225,35 +369,24 @@ __device__ __forceinline__ void chunk_frames(const Item* cs, const Item* nxs, in
         ns[c] = pack2(-a.sc.stdv[c], -a.sc.stdv[c]);
         rc[c] = pack2(a.sc.rcp[c], a.sc.rcp[c]);
     }
-    // staging job of this thread: node `job` of the next item, one frame per iteration
-    const bool job_ok = job < nxs->n_nodes;
-    const float* vp = nullptr;
-    const float* pp = nullptr;
-    uint32_t sdst = stage_nxt + (uint32_t)job * 16u;
-    if (job_ok) {
-        const int n = __ldg(nxs->nodes + job);
-        vp = nxs->vel + 2 * (size_t)n;
-        pp = nxs->prs + (size_t)n;
-    }
-    const int vstep = nxs->vstep, pstep = nxs->pstep;
-    const int nf_stage = job_ok ? min(nf, nxs->nf) : 0;
+    // leader only: where this patch's block of the item's first frame goes
+    float* gst = cs->states + (size_t)patch * (3 * ppx);
+    uint8_t* gmk = want_mask ? cs->mask + (size_t)patch * ppx : nullptr;
+    const size_t gst_step = (size_t)a.n_patches * (3 * ppx), gmk_step = (size_t)a.n_patches * ppx;
     uint32_t nb = stage_cur;
 #pragma unroll 1
     for (int f = 0; f < nf; ++f, nb += a.slot_rec * 16u) {
-        float2 sva = make_float2(0.f, 0.f);
-        float spa = 0.f;
-        const bool do_stage = f < nf_stage;
-        if (do_stage) { sva = ldg_stream2(vp); spa = ldg_stream1(pp); vp += vstep; pp += pstep; }
         float res[3][NP];
         unsigned fm = mbits;
 #pragma unroll
         for (int r = 0; r < NP; ++r) {
-            const uint4 a0 = lds128(nb + ov[r][0]);   // one 128-bit gather per vertex
-            const uint4 a1 = lds128(nb + ov[r][1]);
-            const uint4 a2 = lds128(nb + ov[r][2]);
-            res[0][r] = (float)fma(w2[r], rec_u(a2), fma(w1[r], rec_u(a1), w0[r] * rec_u(a0)));
-            res[1][r] = (float)fma(w2[r], rec_v(a2), fma(w1[r], rec_v(a1), w0[r] * rec_v(a0)));
-            res[2][r] = (float)fma(w2[r], rec_p(a2), fma(w1[r], rec_p(a1), w0[r] * rec_p(a0)));
+            double u0, v0, p0, u1, v1, p1, u2, v2, p2;
+            load_record(nb + ov[r][0], u0, v0, p0);   // one 128-bit gather per vertex
+            load_record(nb + ov[r][1], u1, v1, p1);
+            load_record(nb + ov[r][2], u2, v2, p2);
+            res[0][r] = (float)fma(w2[r], u2, fma(w1[r], u1, w0[r] * u0));
+            res[1][r] = (float)fma(w2[r], v2, fma(w1[r], v1, w0[r] * v0));
+            res[2][r] = (float)fma(w2[r], p2, fma(w1[r], p1, w0[r] * p0));
             if (CHECKED) {
                 if (!finite_f(res[2][r])) fm |= 1u << (8 * r);           // pressure mask only (simple_dataloader.py:114,119)
 #pragma unroll
@@ -290,70 +423,69 @@ __device__ __forceinline__ void chunk_frames(const Item* cs, const Item* nxs, in
 #pragma unroll
             for (int r = 0; r < NP; ++r) sts32(tile + my_f + (uint32_t)(c * ppx + 32 * r) * 4u, res[c][r]);
         if (CHECKED && want_mask) sts32u(tile + my_m, mask_word(fm));
-        fence_async_smem();                            // generic-proxy writes -> visible to the bulk copy
+        if (!(a.dbg & 1u)) fence_async_smem();         // generic-proxy writes -> visible to the bulk copy
         if (leader) bulk_wait_read0();                 // the previous frame's copy has left the other tile
-        if (WPP > 1) group_sync(bar_id, 32 * WPP); else __syncwarp();
-        if (leader) {
-            const size_t fp = (size_t)f * a.n_patches + patch;       // (frame, patch) block of the item's output
-            bulk_store(cs->states + fp * (3 * ppx), tile, 3u * ppx * 4u);
-            if (want_mask) bulk_store(cs->mask + fp * ppx, tile + 3u * ppx * 4u, ppx);
+        if (!(a.dbg & 8u)) { if (WPP > 1) named_sync(bar_id, 32 * WPP); else __syncwarp(); }
+        if (leader && !(a.dbg & 2u)) {
+            bulk_store(gst, tile, 3u * ppx * 4u);
+            if (want_mask) bulk_store(gmk, tile + 3u * ppx * 4u, ppx);
             bulk_commit();
         }
+        gst += gst_step;
+        gmk += gmk_step;
         parity ^= 1;
-        if (do_stage) {
-            scan.add(sva.x, sva.y, spa);
-            sts128(sdst, make_record(sva.x, sva.y, spa));
-            sdst += a.slot_rec * 16u;
-        }
     }
-    // frames of the next item beyond this item's frame count (a short last group followed by a full one)
-    if (job_ok && nxs->nf > nf_stage) stage_node_all_frames(nxs, job, stage_nxt, a.slot_rec, nf_stage, scan);
 }
 
-template <int WPP>
-__global__ void __launch_bounds__(TL_THREADS, 1) k_interp_patchify_tiled(TiledArgs a) {
-    constexpr int ppx = 128 * WPP;
-    constexpr uint32_t TILE_BYTES = ppx * 13;
-    constexpr uint32_t RING_BYTES = (TL_WARPS / WPP) * 2 * TILE_BYTES;
-    extern __shared__ __align__(128) unsigned char fl_smem[];
-    Item* s_items = (Item*)fl_smem;                                   // [2]
-    const uint32_t ring = smem_u32(fl_smem) + 2 * ITEM_WORDS * 4;
-    const uint32_t stage0 = ring + RING_BYTES;
-    const uint32_t stage_bytes = (uint32_t)a.TF * a.slot_rec * 16u;
-    const int warp = threadIdx.x >> 5;
-    int cur = 0, parity = 0;
-    Scan scan;
-    // prologue: decode and stage the first item (not overlapped)
-    if (threadIdx.x == 0) decode_item(a, blockIdx.x, ppx, &s_items[0]);
-    __syncthreads();
-    for (int s = threadIdx.x; s < s_items[0].n_nodes; s += TL_THREADS) stage_node_all_frames(&s_items[0], s, stage0, a.slot_rec, 0, scan);
-    if (threadIdx.x == 0) decode_item(a, blockIdx.x + gridDim.x, ppx, &s_items[1]);
-    int bad = __syncthreads_or(scan.bad() || !a.sc.fast_div);
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-        const Item* it = &s_items[cur];
-        const Item* nx = &s_items[cur ^ 1];
-        const uint32_t stage_cur = stage0 + (uint32_t)cur * stage_bytes, stage_nxt = stage0 + (uint32_t)(cur ^ 1) * stage_bytes;
-        const int n_chunks = it->n_patches * WPP;
-        const int rounds = (n_chunks + TL_WARPS - 1) / TL_WARPS;
-        scan = Scan();
-        for (int round = 0; round < rounds; ++round) {
-            const int chunk = round * TL_WARPS + warp;
-            const int job = round * TL_THREADS + threadIdx.x;
-            if (chunk < n_chunks) {
-                if (bad) chunk_frames<true, WPP>(it, nx, chunk, stage_cur, stage_nxt, job, ring, parity, a, scan);
-                else chunk_frames<false, WPP>(it, nx, chunk, stage_cur, stage_nxt, job, ring, parity, a, scan);
-            } else if (job < nx->n_nodes) {
-                stage_node_all_frames(nx, job, stage_nxt, a.slot_rec, 0, scan);
-            }
+template <int WPP, int PROD_WARPS>
+__device__ __forceinline__ void consumer_loop(const TiledArgs& a, const Item* s_items, uint32_t bar_full, uint32_t bar_empty, uint32_t ring,
+                                              uint32_t stage0, uint32_t stage_bytes) {
+    constexpr int CONS_WARPS = TL_WARPS - PROD_WARPS;
+    constexpr int N_GROUPS = CONS_WARPS / WPP;
+    constexpr uint32_t TILE_BYTES = 128 * WPP * 13;
+    const int warp = (threadIdx.x >> 5) - PROD_WARPS, group = warp / WPP;
+    const uint32_t tile0 = ring + (uint32_t)group * 2u * TILE_BYTES;
+    int next_unit = group, unit_base = 0, parity = 0, k = 0;
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
+        const int b = k & 1;
+        mb_wait(bar_full + 8u * b, (k >> 1) & 1);                          // the producers have staged item k
+        const Item* it = &s_items[b];
+        const int np = it->n_patches, bad = it->bad;
+        const uint32_t stage_cur = stage0 + (uint32_t)b * stage_bytes;
+        for (; next_unit < unit_base + np; next_unit += N_GROUPS) {
+            if (a.dbg & 64u) continue;
+            if (bad) chunk_frames<true, WPP>(it, next_unit - unit_base, stage_cur, tile0, group, parity, a);
+            else chunk_frames<false, WPP>(it, next_unit - unit_base, stage_cur, tile0, group, parity, a);
         }
-        for (int s = rounds * TL_THREADS + threadIdx.x; s < nx->n_nodes; s += TL_THREADS)
-            stage_node_all_frames(nx, s, stage_nxt, a.slot_rec, 0, scan);
-        __syncthreads();       // every warp is done with s_items[cur] and with the gathers out of stage_cur
-        if (threadIdx.x == 0) decode_item(a, item + 2 * gridDim.x, ppx, &s_items[cur]);
-        bad = __syncthreads_or(scan.bad() || !a.sc.fast_div);
-        cur ^= 1;
+        unit_base += np;
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mb_arrive(bar_empty + 8u * b);          // this warp no longer reads buffer b / item slot b
     }
     bulk_wait_read0();         // no bulk copy may still be reading shared memory when the CTA exits
+}
+
+template <int WPP, int PROD_WARPS>
+__global__ void __launch_bounds__(TL_THREADS, 1) k_interp_patchify_tiled(TiledArgs a) {
+    constexpr int ppx = 128 * WPP;
+    constexpr int CONS_WARPS = TL_WARPS - PROD_WARPS;
+    constexpr uint32_t TILE_BYTES = ppx * 13;
+    constexpr uint32_t RING_BYTES = (CONS_WARPS / WPP) * 2 * TILE_BYTES;
+    extern __shared__ __align__(128) unsigned char fl_smem[];
+    Item* s_items = (Item*)fl_smem;                                   // [2]
+    const uint32_t base = smem_u32(fl_smem);
+    const uint32_t bar_full = base + 2 * ITEM_BYTES, bar_empty = bar_full + 16;     // [2] each
+    const uint32_t ring = base + HEAD_BYTES;
+    const uint32_t stage0 = ring + ((RING_BYTES + 127u) & ~127u);
+    const uint32_t stage_bytes = (uint32_t)a.TF * a.slot_rec * 16u;
+    if (threadIdx.x == 0) {
+        mb_init(bar_full, PROD_WARPS * 32);
+        mb_init(bar_full + 8, PROD_WARPS * 32);
+        mb_init(bar_empty, CONS_WARPS);
+        mb_init(bar_empty + 8, CONS_WARPS);
+    }
+    __syncthreads();
+    if ((threadIdx.x >> 5) < PROD_WARPS) producer_loop<PROD_WARPS>(a, s_items, bar_full, bar_empty, stage0, stage_bytes, ppx);
+    else consumer_loop<WPP, PROD_WARPS>(a, s_items, bar_full, bar_empty, ring, stage0, stage_bytes);
 }
 
 }  // namespace
@@ -375,8 +507,13 @@ int fli::launch_tiled(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, 
         max_nodes = t.max_tile_nodes > max_nodes ? t.max_tile_nodes : max_nodes;
     }
     const int slot_rec = max_nodes > 0 ? max_nodes : 1;
-    const size_t ring = (size_t)(TL_WARPS / wpp) * 2 * ppx * 13;
-    const size_t fixed = 2 * ITEM_WORDS * 4 + ring;
+    // producer warps: two keep up with the meshes of the reference's data sets (a node per ~9 pixels); denser meshes get four
+    const double nodes_per_pixel = (double)slot_rec * n_tiles / ((double)n_patches * ppx);
+    int prod_warps = nodes_per_pixel > 0.2 ? 4 : 2;
+    if (const char* e = getenv("FLUIDGRID_PROD_WARPS")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 6) prod_warps = v; }
+    const int cons_warps = TL_WARPS - prod_warps;
+    const size_t ring = fl_align_up((size_t)(cons_warps / wpp) * 2 * ppx * 13, 128);
+    const size_t fixed = HEAD_BYTES + ring;
     long TF = ((long)SMEM_TOTAL - (long)fixed) / 2 / (16L * slot_rec);
     if (TF > 16) TF = 16;
     if (TF > max_frames) TF = max_frames;
@@ -394,17 +531,24 @@ int fli::launch_tiled(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, 
     a.slot_rec = slot_rec;
     a.sc = sc;
     a.flags = flags;
+    a.dbg = 0;
+    if (const char* e = getenv("FLUIDGRID_DBG")) a.dbg = (unsigned)atol(e);
     const size_t smem = fixed + 2 * (size_t)TF * slot_rec * 16;
     const int grid = n_items < FL_SM_COUNT ? (int)n_items : FL_SM_COUNT;      // one persistent CTA per SM
-    if (wpp == 2) {
-        static FlOncePerDevice attr;
-        if (attr.first_use()) FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_tiled<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        k_interp_patchify_tiled<2><<<grid, TL_THREADS, smem, st>>>(a);
-    } else {
-        static FlOncePerDevice attr;
-        if (attr.first_use()) FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-        k_interp_patchify_tiled<1><<<grid, TL_THREADS, smem, st>>>(a);
-    }
+#define FL_TILED_LAUNCH(W, P)                                                                                                   \
+    do {                                                                                                                        \
+        static FlOncePerDevice attr;                                                                                            \
+        if (attr.first_use())                                                                                                   \
+            FL_CUDA(cudaFuncSetAttribute(k_interp_patchify_tiled<W, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL)); \
+        k_interp_patchify_tiled<W, P><<<grid, TL_THREADS, smem, st>>>(a);                                                        \
+    } while (0)
+    if (wpp == 2 && prod_warps == 2) FL_TILED_LAUNCH(2, 2);
+    else if (wpp == 2 && prod_warps == 4) FL_TILED_LAUNCH(2, 4);
+    else if (wpp == 2) FL_TILED_LAUNCH(2, 6);
+    else if (prod_warps == 2) FL_TILED_LAUNCH(1, 2);
+    else if (prod_warps == 4) FL_TILED_LAUNCH(1, 4);
+    else FL_TILED_LAUNCH(1, 6);
+#undef FL_TILED_LAUNCH
     FL_LAUNCH_CHECK();
     return FL_OK;
 }

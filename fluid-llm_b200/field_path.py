@@ -150,6 +150,7 @@ class TrajBatch:
                             tr.plan.n_nodes, int(t0), int(interval), self.n_frames, tr.vel_stride, tr.prs_stride,
                             tpl.idx_tile.data_ptr() if tpl else 0, tpl.tile_nodes.data_ptr() if tpl else 0,
                             tpl.tile_desc.data_ptr() if tpl else 0, tpl.tile_patches.data_ptr() if tpl else 0,
+                            tpl.tile_quads.data_ptr() if tpl else 0, tpl.tile_qslots.data_ptr() if tpl else 0,
                             tpl.n_tiles if tpl else 0, tpl.max_tile_nodes if tpl else 0)
         self.host_desc = arr
         raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()

@@ -118,8 +118,9 @@ def choose_tile_patches(n_patches, n_nodes, ppx, max_frames=16):
 class TilePlan:
     """The patch table split into tiles for csrc/fl_tiled.cu (FlTraj::d_idx_tile, d_tile_*)."""
 
-    def __init__(self, idx_tile, tile_nodes, tile_desc, tile_patches, n_tiles, max_tile_nodes, tp):
+    def __init__(self, idx_tile, tile_nodes, tile_desc, tile_patches, tile_quads, tile_qslots, n_tiles, max_tile_nodes, tp):
         self.idx_tile, self.tile_nodes, self.tile_desc, self.tile_patches = idx_tile, tile_nodes, tile_desc, tile_patches
+        self.tile_quads, self.tile_qslots = tile_quads, tile_qslots
         self.n_tiles, self.max_tile_nodes, self.tp = n_tiles, max_tile_nodes, tp
 
 
@@ -167,14 +168,31 @@ class PatchTable:
             local = (inv.reshape(-1, 3) - node_off[tile_px].unsqueeze(1)) * 16                  # byte offset of the node's record
             idx_tile = torch.cat([torch.where(inside.unsqueeze(1), local, torch.zeros_like(local)).to(torch.int32),
                                   self.idx[:, 3:4]], dim=1).contiguous()
-            tile_nodes = (uniq[:n_valid] % N).to(torch.int32).contiguous()
+            node_u = uniq[:n_valid] % N
+            tile_nodes = node_u.to(torch.int32).contiguous()
+            # per tile the quads (4 consecutive node ids) that hold its nodes, and per quad the slots of its nodes
+            NQ = (N + 3) // 4 + 1
+            qkey = u_tile * NQ + node_u // 4
+            uq, qinv = torch.unique(qkey, return_inverse=True)
+            q_tile = uq // NQ
+            tile_quads = (uq % NQ).to(torch.int32).contiguous()
+            q_cnt = torch.bincount(q_tile, minlength=n_tiles)
+            q_off = torch.cumsum(q_cnt, 0) - q_cnt
+            q_max = torch.zeros(n_tiles, dtype=torch.int64, device=dev).scatter_reduce(0, q_tile, uq % NQ + 1, "amax", include_self=True)
+            qslots = torch.full((max(int(uq.numel()), 1) * 4,), -1, dtype=torch.int32, device=dev)
+            if n_valid:
+                local_u = torch.arange(n_valid, device=dev) - node_off[u_tile]
+                qslots[qinv * 4 + node_u % 4] = local_u.to(torch.int32)
+            if tile_quads.numel() == 0:
+                tile_quads = torch.zeros(4, dtype=torch.int32, device=dev)
             if tile_nodes.numel() == 0:
                 tile_nodes = torch.zeros(4, dtype=torch.int32, device=dev)
             desc = torch.stack([node_off, counts, torch.from_numpy(patch_off[:-1]).to(dev),
-                                torch.from_numpy(np.asarray(sizes, dtype=np.int64)).to(dev)], dim=1).to(torch.int32).contiguous()
+                                torch.from_numpy(np.asarray(sizes, dtype=np.int64)).to(dev),
+                                q_off, q_cnt, q_max, torch.zeros_like(q_off)], dim=1).to(torch.int32).contiguous()
             tile_patches = torch.from_numpy(order).to(dev)
             max_nodes = int(counts.max().item()) if n_tiles else 0
-        plan = TilePlan(idx_tile, tile_nodes, desc, tile_patches, n_tiles, max_nodes, tp)
+        plan = TilePlan(idx_tile, tile_nodes, desc, tile_patches, tile_quads, qslots.view(-1, 4), n_tiles, max_nodes, tp)
         self._tile_plans[tp] = plan
         return plan
 

@@ -107,8 +107,12 @@ typedef struct FlTraj {
      * run the shared-memory kernel.  Every trajectory of a call must use the same split of the patches into tiles. */
     const FlCellIdx* d_idx_tile;   /* [L*px*py] d_idx with node ids replaced by 16 * (slot of the node in its tile's list) */
     const int32_t* d_tile_nodes;   /* the tiles' node lists, one after the other (node ids ascending inside a tile) */
-    const int32_t* d_tile_desc;    /* [n_tiles][4] = {first entry in d_tile_nodes, nodes, first entry in d_tile_patches, patches} */
+    const int32_t* d_tile_desc;    /* [n_tiles][8] = {first entry in d_tile_nodes, nodes, first entry in d_tile_patches, patches,
+                                      first entry in d_tile_quads / d_tile_qslots, quads, largest quad id + 1, 0} */
     const int32_t* d_tile_patches; /* the tiles' patch ids l, one after the other */
+    const int32_t* d_tile_quads;   /* optional: per tile the quads (node id / 4, ascending) that hold its nodes, one list after the other */
+    const int32_t* d_tile_qslots;  /* with d_tile_quads: [quads][4] the slots of each quad's 4 nodes (-1: not used by the tile); lets the
+                                      kernel stage with coalesced 128-bit loads when the frames are 16-byte aligned and padded to quads */
     int32_t n_tiles, max_tile_nodes;
 } FlTraj;
 /* prs_stride a multiple of 4, vel_stride >= 2 * prs_stride, 16-byte aligned bases and pad floats

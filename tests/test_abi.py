@@ -27,9 +27,9 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_layout_matches_header():
     from fluid_llm_b200._lib import FlTraj
-    assert ctypes.sizeof(FlTraj) == 8 * 8 + 6 * 4 + 4 * 8 + 2 * 4 == 128
+    assert ctypes.sizeof(FlTraj) == 8 * 8 + 6 * 4 + 6 * 8 + 2 * 4 == 144
     assert FlTraj.n_nodes.offset == 64 and FlTraj.prs_stride.offset == 84
-    assert FlTraj.d_idx_tile.offset == 88 and FlTraj.n_tiles.offset == 120 and FlTraj.max_tile_nodes.offset == 124
+    assert FlTraj.d_idx_tile.offset == 88 and FlTraj.n_tiles.offset == 136 and FlTraj.max_tile_nodes.offset == 140
 
 
 def test_argument_errors_without_a_device(lib):

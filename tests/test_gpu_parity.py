@@ -306,7 +306,8 @@ def test_c_abi_called_directly_as_integration_md_shows():
                     ("n_nodes", ctypes.c_int32), ("t0", ctypes.c_int32), ("interval", ctypes.c_int32), ("n_frames", ctypes.c_int32),
                     ("vel_stride", ctypes.c_int32), ("prs_stride", ctypes.c_int32),
                     ("d_idx_tile", ctypes.c_void_p), ("d_tile_nodes", ctypes.c_void_p), ("d_tile_desc", ctypes.c_void_p),
-                    ("d_tile_patches", ctypes.c_void_p), ("n_tiles", ctypes.c_int32), ("max_tile_nodes", ctypes.c_int32)]
+                    ("d_tile_patches", ctypes.c_void_p), ("d_tile_quads", ctypes.c_void_p), ("d_tile_qslots", ctypes.c_void_p),
+                    ("n_tiles", ctypes.c_int32), ("max_tile_nodes", ctypes.c_int32)]
 
     lib.fl_interp_patchify.restype = ctypes.c_int
     lib.fl_interp_patchify.argtypes = [ctypes.POINTER(FlTraj), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -319,7 +320,7 @@ def test_c_abi_called_directly_as_integration_md_shows():
     mask = torch.empty((seq_len, tab.n_patches, 16, 16), dtype=torch.uint8, device="cuda")
     traj = FlTraj(vel.data_ptr(), prs.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(), None, None,
                   states.data_ptr(), mask.data_ptr(), N, step, interval, seq_len, vel.stride(0), prs.stride(0),
-                  None, None, None, None, 0, 0)      # no tile plan: the library picks the staged / gather kernel
+                  None, None, None, None, None, None, 0, 0)      # no tile plan: the library picks the staged / gather kernel
     mean = (ctypes.c_float * 3)(0.823, 0.0005865, 0.04763)
     std = (ctypes.c_float * 3)(0.275, 0.275, 0.275)
     rc = lib.fl_interp_patchify(ctypes.byref(traj), 1, tab.n_patches, 16, 16, mean, std, 0,

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--tiles", default="0,8,16,24,32,48")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--tf", default="")
+    ap.add_argument("--prod", default="", help="comma-separated FLUIDGRID_PROD_WARPS values (2 or 4)")
+    ap.add_argument("--dbg", default="", help="comma-separated FLUIDGRID_DBG values (development ablations; results are wrong)")
     args = ap.parse_args()
     import torch
     import fluid_llm_b200
@@ -42,7 +44,14 @@ def main():
     peak, _ = bench.measured_peak()
     ref = None
     tfs = [int(x) for x in args.tf.split(",")] if args.tf else [0]
-    for tp in [int(x) for x in args.tiles.split(",")]:
+    dbgs = [int(x) for x in args.dbg.split(",")] if args.dbg else [0]
+    prods = [int(x) for x in args.prod.split(",")] if args.prod else [0]
+    for tp, dbg, prod in [(int(x), d, pw) for x in args.tiles.split(",") for d in dbgs for pw in prods]:
+        os.environ["FLUIDGRID_DBG"] = str(dbg)
+        if prod:
+            os.environ["FLUIDGRID_PROD_WARPS"] = str(prod)
+        else:
+            os.environ.pop("FLUIDGRID_PROD_WARPS", None)
         for tf in tfs:
             if tf:
                 os.environ["FLUIDGRID_TF"] = str(tf)
@@ -64,7 +73,7 @@ def main():
             if ref is None:
                 ref = chk
             tpl = batch.tile_plans[0] if batch.tile_plans else None
-            print(json.dumps({"workload": args.workload, "tile_patches": tp, "tf_cap": tf, "n_tiles": tpl.n_tiles if tpl else 0,
+            print(json.dumps({"workload": args.workload, "tile_patches": tp, "tf_cap": tf, "dbg": dbg, "prod_warps": prod, "n_tiles": tpl.n_tiles if tpl else 0,
                               "max_tile_nodes": tpl.max_tile_nodes if tpl else 0, "ms": round(ms, 4),
                               "frames_per_s": round(len(trajs) * w["T"] / ms * 1e3), "roofline_frac": round(algo / ms / 1e6 / peak, 4),
                               "same_bits_as_first": chk == ref}), flush=True)
