@@ -23,7 +23,7 @@ class FlTraj(ctypes.Structure):
                 ("n_nodes", c_int32), ("t0", c_int32), ("interval", c_int32), ("n_frames", c_int32),
                 ("vel_stride", c_int32), ("prs_stride", c_int32),
                 ("d_idx_tile", c_void_p), ("d_tile_nodes", c_void_p), ("d_tile_desc", c_void_p), ("d_tile_patches", c_void_p),
-                ("d_tile_quads", c_void_p), ("d_tile_qslots", c_void_p), ("n_tiles", c_int32), ("max_tile_nodes", c_int32)]
+                ("d_tile_quads", c_void_p), ("d_tile_qslots", c_void_p), ("n_tiles", c_int32), ("max_tile_nodes", c_int32), ("max_tile_patches", c_int32), ("reserved_", c_int32)]
 
 
 class FluidGridError(RuntimeError):

@@ -186,6 +186,11 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
                     for (int c = 0; c < 3; ++c) if (!finite_f(res[c][r])) res[c][r] = 0.f;
                 }
             }
+            if (mbits) {       // outside the mesh the weights are 0 and the sum is +-0: the reference stores +0.0 (mesh_utils.py:89)
+#pragma unroll
+                for (int r = 0; r < NP; ++r)
+                    if ((mbits >> (8 * r)) & 1u) { res[0][r] = 0.f; res[1][r] = 0.f; res[2][r] = 0.f; }
+            }
             if (!no_norm) {
                 if (CHECKED) {
 #pragma unroll

@@ -17,10 +17,10 @@
 //   producers  the last warps of the CTA only stage: they walk the CTA's items, load the tile's nodes frame by frame
 //              (several frames in flight per thread), convert, write the records of item k into buffer k & 1 and arrive
 //              on its `full` mbarrier; they wait on `empty` before overwriting a buffer.
-//   consumers  the other warps never meet at a CTA-wide barrier.  The (item, patch) units of the CTA form one sequence
-//              and are dealt round-robin to the patch groups (the warps that share a patch), so a group that is ahead
-//              simply starts on the next item as soon as its buffer is full; every consumer warp arrives on `empty`
-//              when it is done with an item.
+//   consumers  the other warps never meet at a CTA-wide barrier.  A tile has as many patches as the CTA has patch groups
+//              (the warps that share a patch), and a CTA works through (trajectory, tile, run of frame groups) units:
+//              a group reads the table records of ITS patch once per unit and keeps them in registers for every frame of
+//              the run, waits on `full` for each frame group and arrives on `empty` when it is done with it.
 //   output     results go to a per-group shared-memory tile ([3][px*py] floats + px*py mask bytes, conflict-free
 //              STS.32) and leave as ONE bulk copy (cp.async.bulk shared -> global, 3 KB) per frame and patch, issued by
 //              one thread of the group; two tiles per group, so the copy of frame f overlaps the arithmetic of frame
@@ -63,9 +63,6 @@ __device__ __forceinline__ void mb_wait(uint32_t bar, unsigned parity) {
         "{\n.reg .pred p;\nTL_WAIT:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra TL_DONE;\nbra TL_WAIT;\nTL_DONE:\n}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 __device__ __forceinline__ void sts32u(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
@@ -122,17 +119,15 @@ static_assert(sizeof(Item) == ITEM_BYTES, "Item must fill its shared-memory slot
 
 struct TiledArgs {
     const FlTraj* trajs;
-    int n_items, groups, n_tiles, TF, n_patches, slot_rec;   // slot_rec: records per staged frame
+    int n_units, fchunks, gpc, groups, n_tiles, TF, n_patches, slot_rec;
+    // unit = (trajectory, run `c` of gpc frame groups, tile); groups = frame groups per trajectory; slot_rec = records per staged frame
     StagedConst sc;
     unsigned flags;
     unsigned dbg;     // development ablations (FLUIDGRID_DBG): 1 no proxy fence, 2 no bulk copies, 4 producers stage nothing, 8 no group barrier, 16 no L2 prefetch, 32 node-by-node staging, 64 consumers compute nothing
 };
 
-__device__ __forceinline__ void decode_item(const TiledArgs& a, int item, int ppx, Item* out) {
+__device__ __forceinline__ void decode_item(const TiledArgs& a, int j, int tile, int g, int ppx, Item* out) {
     Item it;
-    const int tile = item % a.n_tiles;
-    const int jg = item / a.n_tiles;
-    const int g = jg % a.groups, j = jg / a.groups;
     const FlTraj tr = a.trajs[j];
     const int fbeg = g * a.TF;
     it.nf = max(0, min(a.TF, tr.n_frames - fbeg));
@@ -213,68 +208,58 @@ __device__ __forceinline__ void stage_nodes(const Item* it, int s, int s2, uint3
 // of quads); a thread takes one quad x 4 frames (two 128-bit loads of velocities and one of pressures per frame,
 // consecutive threads on consecutive list entries) and writes the records of the nodes the tile uses to their slots.
 __device__ __forceinline__ float4 ldg_stream4f(const float* p) { return fl_ldg_stream4((const float4*)p); }
+
+// one quad x FB frames in registers
+template <int FB>
+struct QuadBatch {
+    float4 va[FB], vb[FB], pq[FB];
+    int4 sl;
+    int f0;
+};
+template <int FB>
+__device__ __forceinline__ void quad_load(QuadBatch<FB>& qb, const Item* it, int u, int qc) {
+    const int fb = u / qc, e = u - fb * qc;
+    qb.f0 = fb * FB;
+    qb.sl = __ldg(it->qslots + e);
+    const int q = __ldg(it->quads + e);
+    const int vstep = it->vstep, pstep = it->pstep, nf = it->nf;
+    const float* vp = it->vel + (size_t)qb.f0 * vstep + 8 * (size_t)q;
+    const float* pp = it->prs + (size_t)qb.f0 * pstep + 4 * (size_t)q;
+#pragma unroll
+    for (int i = 0; i < FB; ++i)
+        if (qb.f0 + i < nf) {
+            qb.va[i] = ldg_stream4f(vp + (size_t)i * vstep);
+            qb.vb[i] = ldg_stream4f(vp + (size_t)i * vstep + 4);
+            qb.pq[i] = ldg_stream4f(pp + (size_t)i * pstep);
+        }
+}
+template <int FB>
+__device__ __forceinline__ void quad_store(const QuadBatch<FB>& qb, int nf, uint32_t sbuf, int slot_rec, Scan& sc) {
+    uint32_t dst = sbuf + (uint32_t)qb.f0 * slot_rec * 16u;
+    const int4 sl = qb.sl;
+#pragma unroll
+    for (int i = 0; i < FB; ++i)
+        if (qb.f0 + i < nf) {
+            if (sl.x >= 0) { sc.add(qb.va[i].x, qb.va[i].y, qb.pq[i].x); sts128(dst + 16u * sl.x, make_record(qb.va[i].x, qb.va[i].y, qb.pq[i].x)); }
+            if (sl.y >= 0) { sc.add(qb.va[i].z, qb.va[i].w, qb.pq[i].y); sts128(dst + 16u * sl.y, make_record(qb.va[i].z, qb.va[i].w, qb.pq[i].y)); }
+            if (sl.z >= 0) { sc.add(qb.vb[i].x, qb.vb[i].y, qb.pq[i].z); sts128(dst + 16u * sl.z, make_record(qb.vb[i].x, qb.vb[i].y, qb.pq[i].z)); }
+            if (sl.w >= 0) { sc.add(qb.vb[i].z, qb.vb[i].w, qb.pq[i].w); sts128(dst + 16u * sl.w, make_record(qb.vb[i].z, qb.vb[i].w, qb.pq[i].w)); }
+            dst += (uint32_t)slot_rec * 16u;
+        }
+}
+// Coalesced form: the tile's nodes lie in q_cnt quads of 4 consecutive node ids (listed ascending, so runs of nodes are runs
+// of quads); a thread takes one quad x FB frames at a time (two 128-bit loads of velocities and one of pressures per frame,
+// consecutive threads on consecutive list entries) and writes the records of the nodes the tile uses to their slots.
+// (Two batches in flight per thread -- loads of the next issued before the current is converted -- spill at 128 registers.)
 __device__ __forceinline__ void stage_quads(const Item* it, int ptid, int PT, uint32_t sbuf, int slot_rec, Scan& sc) {
     constexpr int FB = 4;
-    const int qc = it->q_cnt, nf = it->nf, vstep = it->vstep, pstep = it->pstep;
-    const int nfb = (nf + FB - 1) / FB;
-    const float* vel = it->vel;
-    const float* prs = it->prs;
-    const int4* qs = it->qslots;
-    const int* qid = it->quads;
-    int u = ptid;
-    int4 sl_n = make_int4(-1, -1, -1, -1);
-    int q_n = 0;
-    if (u < qc * nfb) { const int e = u % qc; sl_n = __ldg(qs + e); q_n = __ldg(qid + e); }
-    for (; u < qc * nfb; u += PT) {
-        const int fb = u / qc;
-        const int f0 = fb * FB;
-        const int4 sl = sl_n;
-        const int q = q_n;
-        if (u + PT < qc * nfb) { const int e = (u + PT) % qc; sl_n = __ldg(qs + e); q_n = __ldg(qid + e); }   // next entry: off the critical path
-        const float* vp = vel + (size_t)f0 * vstep + 8 * (size_t)q;
-        const float* pp = prs + (size_t)f0 * pstep + 4 * (size_t)q;
-        float4 va[FB], vb[FB], pq[FB];
-#pragma unroll
-        for (int i = 0; i < FB; ++i)
-            if (f0 + i < nf) {
-                va[i] = ldg_stream4f(vp + (size_t)i * vstep);
-                vb[i] = ldg_stream4f(vp + (size_t)i * vstep + 4);
-                pq[i] = ldg_stream4f(pp + (size_t)i * pstep);
-            }
-        uint32_t dst = sbuf + (uint32_t)f0 * slot_rec * 16u;
-#pragma unroll
-        for (int i = 0; i < FB; ++i)
-            if (f0 + i < nf) {
-                if (sl.x >= 0) { sc.add(va[i].x, va[i].y, pq[i].x); sts128(dst + 16u * sl.x, make_record(va[i].x, va[i].y, pq[i].x)); }
-                if (sl.y >= 0) { sc.add(va[i].z, va[i].w, pq[i].y); sts128(dst + 16u * sl.y, make_record(va[i].z, va[i].w, pq[i].y)); }
-                if (sl.z >= 0) { sc.add(vb[i].x, vb[i].y, pq[i].z); sts128(dst + 16u * sl.z, make_record(vb[i].x, vb[i].y, pq[i].z)); }
-                if (sl.w >= 0) { sc.add(vb[i].z, vb[i].w, pq[i].w); sts128(dst + 16u * sl.w, make_record(vb[i].z, vb[i].w, pq[i].w)); }
-                dst += (uint32_t)slot_rec * 16u;
-            }
+    const int qc = it->q_cnt, nf = it->nf;
+    const int total = qc * ((nf + FB - 1) / FB);
+    for (int u = ptid; u < total; u += PT) {
+        QuadBatch<FB> qb;
+        quad_load(qb, it, u, qc);
+        quad_store(qb, nf, sbuf, slot_rec, sc);
     }
-}
-
-// Ask L2 for the node fields item `item` will stage: per frame the span of the tile's node ids (the list is ascending), one
-// bulk prefetch for the velocities and one for the pressures.  Thread i of the producers takes frame i.  The spans are
-// clipped to whole 16-byte units inside the frame, so nothing outside the caller's arrays is touched.
-__device__ __forceinline__ void prefetch_item(const TiledArgs& a, int item, int ptid) {
-    if (item >= a.n_items || ptid >= a.TF) return;
-    const int tile = item % a.n_tiles;
-    const int jg = item / a.n_tiles;
-    const int g = jg % a.groups, j = jg / a.groups;
-    const FlTraj* tr = a.trajs + j;
-    const int f = g * a.TF + ptid;
-    if (f >= tr->n_frames) return;
-    const int4 d = __ldg((const int4*)tr->d_tile_desc + 2 * tile);
-    if (d.y < 1) return;
-    const int n0 = __ldg(tr->d_tile_nodes + d.x), n1 = __ldg(tr->d_tile_nodes + d.x + d.y - 1) + 1;     // [n0, n1)
-    const long long t = (long long)tr->t0 + (long long)f * tr->interval;
-    const uintptr_t v0 = ((uintptr_t)(tr->d_velocity + t * tr->vel_stride + 2 * (size_t)n0) + 15) & ~(uintptr_t)15;
-    const uintptr_t v1 = (uintptr_t)(tr->d_velocity + t * tr->vel_stride + 2 * (size_t)n1) & ~(uintptr_t)15;
-    const uintptr_t p0 = ((uintptr_t)(tr->d_pressure + t * tr->prs_stride + (size_t)n0) + 15) & ~(uintptr_t)15;
-    const uintptr_t p1 = (uintptr_t)(tr->d_pressure + t * tr->prs_stride + (size_t)n1) & ~(uintptr_t)15;
-    if (v1 > v0) l2_prefetch_bulk((const void*)v0, (uint32_t)(v1 - v0));
-    if (p1 > p0) l2_prefetch_bulk((const void*)p0, (uint32_t)(p1 - p0));
 }
 
 template <int PROD_WARPS>
@@ -283,31 +268,55 @@ __device__ __forceinline__ void producer_loop(const TiledArgs& a, Item* s_items,
     constexpr int PT = PROD_WARPS * 32;
     const int ptid = threadIdx.x;          // the producers are the first warps of the CTA
     int k = 0;
-    if (!(a.dbg & 16u)) prefetch_item(a, blockIdx.x, ptid);
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
-        const int b = k & 1;
-        if (!(a.dbg & 16u)) prefetch_item(a, item + gridDim.x, ptid);      // the next item's fields are in L2 by the time its buffer is free
-        if (k >= 2) mb_wait(bar_empty + 8u * b, ((k >> 1) - 1) & 1);       // every consumer warp is done with item k - 2
-        if (ptid == 0) decode_item(a, item, ppx, &s_items[b]);
-        named_sync(15, PT);
-        const Item* it = &s_items[b];
-        Scan scan;
-        const int S = it->n_nodes;
-        if (!(a.dbg & 4u) || k < 2) {
-            if (it->q_cnt > 0 && !(a.dbg & 32u)) stage_quads(it, ptid, PT, stage0 + (uint32_t)b * stage_bytes, a.slot_rec, scan);
-            else for (int s = ptid; s < S; s += PT) stage_nodes(it, s, -1, stage0 + (uint32_t)b * stage_bytes, a.slot_rec, scan);
+    for (int unit = blockIdx.x; unit < a.n_units; unit += gridDim.x) {
+        const int tile = unit % a.n_tiles, jc = unit / a.n_tiles;
+        const int c = jc % a.fchunks, j = jc / a.fchunks;
+        const int g1 = min(a.groups, (c + 1) * a.gpc);
+        for (int g = c * a.gpc; g < g1; ++g, ++k) {
+            const int b = k & 1;
+            if (k >= 2) mb_wait(bar_empty + 8u * b, ((k >> 1) - 1) & 1);       // every consumer warp is done with item k - 2
+            if (ptid == 0) decode_item(a, j, tile, g, ppx, &s_items[b]);
+            named_sync(15, PT);
+            const Item* it = &s_items[b];
+            Scan scan;
+            const int S = it->n_nodes;
+            if (!(a.dbg & 4u) || k < 2) {
+                if (it->q_cnt > 0 && !(a.dbg & 32u)) stage_quads(it, ptid, PT, stage0 + (uint32_t)b * stage_bytes, a.slot_rec, scan);
+                else for (int s = ptid; s < S; s += PT) stage_nodes(it, s, -1, stage0 + (uint32_t)b * stage_bytes, a.slot_rec, scan);
+            }
+            if (__any_sync(0xffffffffu, scan.bad()) && (threadIdx.x & 31) == 0) atomicOr(&s_items[b].bad, 1);
+            mb_arrive(bar_full + 8u * b);           // release: the records (and the bad flag) are visible to whoever waits
         }
-        if (__any_sync(0xffffffffu, scan.bad()) && (threadIdx.x & 31) == 0) atomicOr(&s_items[b].bad, 1);
-        mb_arrive(bar_full + 8u * b);           // release: the records (and the bad flag) are visible to whoever waits
     }
 }
 
 // ---- consumer warps -------------------------------------------------------------------------------------------------
-// One chunk (128 output pixels of one patch) x the item's frames.  WPP = warps per patch (ppx / 128); the WPP warps of a
-// patch group share two output tiles and the named barrier 1 + group.
+// What a thread keeps in registers for its 4 pixels of its group's patch, for all frames of a unit
+struct PixelRegs {
+    uint32_t ov[NP][3];        // byte offsets of the three vertices' records inside a staged frame
+    double w0[NP], w1[NP], w2[NP];
+    unsigned mbits;            // byte r = 1 if pixel r is outside the mesh
+};
+
+// mask bytes in pixel order: lane j returns the four bytes of pixels 4j..4j+3 of the warp's 128 pixels
+__device__ __forceinline__ unsigned mask_word(unsigned bits) {
+    const int lane_id = threadIdx.x & 31;
+    unsigned word = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = 4 * (lane_id & 7) + i;                                         // position inside the 32-pixel group
+        const int src = (((q >> 2) & 3) << 3) | (((q >> 4) & 1) << 2) | (q & 3);     // inverse of the lane permutation
+        const unsigned m = __shfl_sync(0xffffffffu, bits, src);
+        word |= ((m >> (8 * (lane_id >> 3))) & 1u) << (8 * i);
+    }
+    return word;
+}
+
+// The frames of one item for the group's patch.  WPP = warps per patch (ppx / 128); the WPP warps of a patch group share
+// two output tiles and the named barrier 1 + group.
 template <bool CHECKED, int WPP>
-__device__ __forceinline__ void chunk_frames(const Item* cs, int unit, uint32_t stage_cur, uint32_t tile0, int group, int& parity,
-                                             const TiledArgs& a) {
+__device__ __forceinline__ void run_frames(const PixelRegs& px, const Item* cs, int patch, uint32_t stage_cur, uint32_t tile0, int group,
+                                           int& parity, const TiledArgs& a) {
     constexpr int ppx = 128 * WPP;
     constexpr uint32_t TILE_BYTES = ppx * 13;       // [3][ppx] floats + ppx mask bytes
     const int lane_id = threadIdx.x & 31;
@@ -315,53 +324,11 @@ __device__ __forceinline__ void chunk_frames(const Item* cs, int unit, uint32_t 
     const bool leader = sub == 0 && lane_id == 0;
     const int bar_id = 1 + group;
     const bool mask_aware = a.flags & FL_MASK_AWARE_NORM, no_norm = a.flags & FL_NO_NORM;
-    // pixel of this lane inside a group of 32 adjacent pixels (2 patch rows x 16): the 8 lanes of a quarter-warp (one
-    // LDS.128 wavefront) take a compact 2 x 4 block, which touches fewer distinct nodes than a 1 x 8 strip
     const int lane = ((lane_id >> 2) & 1) * 16 + (lane_id >> 3) * 4 + (lane_id & 3);
-    // the item lives in shared memory (uniform reads); only what the frame loop needs is kept in registers
-    const int patch = __ldg(cs->patches + unit);
-    const int o = patch * ppx + sub * 128 + lane;
-    const int4* idx_tab = cs->idx;
-    const double2* w_tab = cs->w;
-    uint32_t ov[NP][3];
-    double w0[NP], w1[NP], w2[NP];
-    unsigned mbits = 0;     // byte r = 1 if pixel r is outside the mesh
-#pragma unroll
-    for (int r = 0; r < NP; ++r) {
-        const int4 id = __ldg(idx_tab + o + 32 * r);
-        const double2 ww = __ldg(w_tab + o + 32 * r);
-        const bool out = id.w < 0;
-        mbits |= out ? (1u << (8 * r)) : 0u;
-        w1[r] = out ? 0.0 : ww.x;
-        w2[r] = out ? 0.0 : ww.y;
-        w0[r] = out ? 0.0 : 1.0 - ww.x - ww.y;
-        ov[r][0] = out ? 0u : (uint32_t)id.x;        // already 16 * slot
-        ov[r][1] = out ? 0u : (uint32_t)id.y;
-        ov[r][2] = out ? 0u : (uint32_t)id.z;
-    }
-    // mask bytes in pixel order: lane j holds the four bytes of pixels 4j..4j+3 of the chunk (static on the unchecked path)
-    auto mask_word = [&](unsigned bits) {
-        unsigned word = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int q = 4 * (lane_id & 7) + i;                                         // position inside the 32-pixel group
-            const int src = (((q >> 2) & 3) << 3) | (((q >> 4) & 1) << 2) | (q & 3);     // inverse of the lane permutation
-            const unsigned m = __shfl_sync(0xffffffffu, bits, src);
-            word |= ((m >> (8 * (lane_id >> 3))) & 1u) << (8 * i);
-        }
-        return word;
-    };
     const bool want_mask = cs->mask != nullptr;
     const int nf = cs->nf;
     // element (c, pixel k of the patch) of a tile at c * ppx + k, mask bytes behind the floats
     const uint32_t my_f = (uint32_t)(sub * 128 + lane) * 4u, my_m = 3u * ppx * 4u + (uint32_t)(sub * 128 + 4 * lane_id);
-    if (leader) bulk_wait_read0();                    // both tiles are free (this thread issued every copy that read them)
-    if (WPP > 1) named_sync(bar_id, 32 * WPP); else __syncwarp();
-    if (!CHECKED && want_mask) {
-        const unsigned mw = mask_word(mbits);
-        sts32u(tile0 + my_m, mw);
-        sts32u(tile0 + TILE_BYTES + my_m, mw);
-    }
     unsigned long long nm[3], ns[3], rc[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -377,21 +344,26 @@ __device__ __forceinline__ void chunk_frames(const Item* cs, int unit, uint32_t 
 #pragma unroll 1
     for (int f = 0; f < nf; ++f, nb += a.slot_rec * 16u) {
         float res[3][NP];
-        unsigned fm = mbits;
+        unsigned fm = px.mbits;
 #pragma unroll
         for (int r = 0; r < NP; ++r) {
             double u0, v0, p0, u1, v1, p1, u2, v2, p2;
-            load_record(nb + ov[r][0], u0, v0, p0);   // one 128-bit gather per vertex
-            load_record(nb + ov[r][1], u1, v1, p1);
-            load_record(nb + ov[r][2], u2, v2, p2);
-            res[0][r] = (float)fma(w2[r], u2, fma(w1[r], u1, w0[r] * u0));
-            res[1][r] = (float)fma(w2[r], v2, fma(w1[r], v1, w0[r] * v0));
-            res[2][r] = (float)fma(w2[r], p2, fma(w1[r], p1, w0[r] * p0));
+            load_record(nb + px.ov[r][0], u0, v0, p0);   // one 128-bit gather per vertex
+            load_record(nb + px.ov[r][1], u1, v1, p1);
+            load_record(nb + px.ov[r][2], u2, v2, p2);
+            res[0][r] = (float)fma(px.w2[r], u2, fma(px.w1[r], u1, px.w0[r] * u0));
+            res[1][r] = (float)fma(px.w2[r], v2, fma(px.w1[r], v1, px.w0[r] * v0));
+            res[2][r] = (float)fma(px.w2[r], p2, fma(px.w1[r], p1, px.w0[r] * p0));
             if (CHECKED) {
                 if (!finite_f(res[2][r])) fm |= 1u << (8 * r);           // pressure mask only (simple_dataloader.py:114,119)
 #pragma unroll
                 for (int c = 0; c < 3; ++c) if (!finite_f(res[c][r])) res[c][r] = 0.f;   // mesh_utils.py:89, per channel
             }
+        }
+        if (px.mbits) {        // outside the mesh the weights are 0 and the sum is +-0: the reference stores +0.0 (mesh_utils.py:89)
+#pragma unroll
+            for (int r = 0; r < NP; ++r)
+                if ((px.mbits >> (8 * r)) & 1u) { res[0][r] = 0.f; res[1][r] = 0.f; res[2][r] = 0.f; }
         }
         if (!no_norm) {
             if (CHECKED) {
@@ -440,26 +412,71 @@ __device__ __forceinline__ void chunk_frames(const Item* cs, int unit, uint32_t 
 template <int WPP, int PROD_WARPS>
 __device__ __forceinline__ void consumer_loop(const TiledArgs& a, const Item* s_items, uint32_t bar_full, uint32_t bar_empty, uint32_t ring,
                                               uint32_t stage0, uint32_t stage_bytes) {
-    constexpr int CONS_WARPS = TL_WARPS - PROD_WARPS;
-    constexpr int N_GROUPS = CONS_WARPS / WPP;
-    constexpr uint32_t TILE_BYTES = 128 * WPP * 13;
+    constexpr int ppx = 128 * WPP;
+    constexpr uint32_t TILE_BYTES = ppx * 13;
+    const int lane_id = threadIdx.x & 31;
     const int warp = (threadIdx.x >> 5) - PROD_WARPS, group = warp / WPP;
+    const int sub = WPP == 1 ? 0 : (warp % WPP);
+    const bool leader = sub == 0 && lane_id == 0;
+    const int lane = ((lane_id >> 2) & 1) * 16 + (lane_id >> 3) * 4 + (lane_id & 3);
     const uint32_t tile0 = ring + (uint32_t)group * 2u * TILE_BYTES;
-    int next_unit = group, unit_base = 0, parity = 0, k = 0;
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++k) {
-        const int b = k & 1;
-        mb_wait(bar_full + 8u * b, (k >> 1) & 1);                          // the producers have staged item k
-        const Item* it = &s_items[b];
-        const int np = it->n_patches, bad = it->bad;
-        const uint32_t stage_cur = stage0 + (uint32_t)b * stage_bytes;
-        for (; next_unit < unit_base + np; next_unit += N_GROUPS) {
-            if (a.dbg & 64u) continue;
-            if (bad) chunk_frames<true, WPP>(it, next_unit - unit_base, stage_cur, tile0, group, parity, a);
-            else chunk_frames<false, WPP>(it, next_unit - unit_base, stage_cur, tile0, group, parity, a);
+    const uint32_t my_m = 3u * ppx * 4u + (uint32_t)(sub * 128 + 4 * lane_id);
+    int parity = 0, k = 0;
+    for (int unit = blockIdx.x; unit < a.n_units; unit += gridDim.x) {
+        const int tile = unit % a.n_tiles, jc = unit / a.n_tiles;
+        const int c = jc % a.fchunks, j = jc / a.fchunks;
+        const int g1 = min(a.groups, (c + 1) * a.gpc);
+        // ---- once per unit: the table records of this group's patch (the tile has at most one patch per group) ----
+        const FlTraj* tr = a.trajs + j;
+        const int4 d = __ldg((const int4*)tr->d_tile_desc + 2 * tile);
+        const bool has = group < d.w;
+        const int patch = has ? __ldg(tr->d_tile_patches + d.z + group) : 0;
+        const bool want_mask = tr->d_mask != nullptr;
+        PixelRegs px;
+        px.mbits = 0;
+        if (has) {
+            const int4* idx_tab = (const int4*)tr->d_idx_tile;
+            const double2* w_tab = (const double2*)tr->d_w;
+            const int o = patch * ppx + sub * 128 + lane;
+#pragma unroll
+            for (int r = 0; r < NP; ++r) {
+                const int4 id = __ldg(idx_tab + o + 32 * r);
+                const double2 ww = __ldg(w_tab + o + 32 * r);
+                const bool out = id.w < 0;
+                px.mbits |= out ? (1u << (8 * r)) : 0u;
+                px.w1[r] = out ? 0.0 : ww.x;
+                px.w2[r] = out ? 0.0 : ww.y;
+                px.w0[r] = out ? 0.0 : 1.0 - ww.x - ww.y;
+                px.ov[r][0] = out ? 0u : (uint32_t)id.x;        // already 16 * slot
+                px.ov[r][1] = out ? 0u : (uint32_t)id.y;
+                px.ov[r][2] = out ? 0u : (uint32_t)id.z;
+            }
         }
-        unit_base += np;
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mb_arrive(bar_empty + 8u * b);          // this warp no longer reads buffer b / item slot b
+        bool mask_stale = true;       // the tiles' mask bytes are not this patch's static mask (new patch, or a checked item ran)
+        for (int g = c * a.gpc; g < g1; ++g, ++k) {
+            const int b = k & 1;
+            mb_wait(bar_full + 8u * b, (k >> 1) & 1);                          // the producers have staged item k
+            const Item* it = &s_items[b];
+            if (has && it->nf > 0 && !(a.dbg & 64u)) {
+                const uint32_t stage_cur = stage0 + (uint32_t)b * stage_bytes;
+                if (it->bad) {
+                    run_frames<true, WPP>(px, it, patch, stage_cur, tile0, group, parity, a);
+                    mask_stale = true;
+                } else {
+                    if (mask_stale && want_mask) {
+                        if (leader) bulk_wait_read0();            // both tiles are free (this thread issued every copy that read them)
+                        if (WPP > 1) named_sync(1 + group, 32 * WPP); else __syncwarp();
+                        const unsigned mw = mask_word(px.mbits);
+                        sts32u(tile0 + my_m, mw);
+                        sts32u(tile0 + TILE_BYTES + my_m, mw);
+                        mask_stale = false;
+                    }
+                    run_frames<false, WPP>(px, it, patch, stage_cur, tile0, group, parity, a);
+                }
+            }
+            __syncwarp();
+            if (lane_id == 0) mb_arrive(bar_empty + 8u * b);          // this warp no longer reads buffer b / item slot b
+        }
     }
     bulk_wait_read0();         // no bulk copy may still be reading shared memory when the CTA exits
 }
@@ -495,22 +512,26 @@ int fli::launch_tiled(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, 
     const int ppx = px * py;
     if (!h_trajs || (ppx != 128 && ppx != 256)) return 1;
     const int wpp = ppx / 128;
-    int n_tiles = h_trajs[0].n_tiles, max_nodes = 0;
+    int n_tiles = h_trajs[0].n_tiles, max_nodes = 0, max_tile_patches = 0;
     for (int i = 0; i < n_traj; ++i) {
         const FlTraj& t = h_trajs[i];
         if (!t.d_idx_tile || !t.d_tile_nodes || !t.d_tile_desc || !t.d_tile_patches || t.n_tiles < 1) return 1;
         FL_REQUIRE(t.n_tiles == n_tiles, FL_E_ARG, "fl_interp_patchify: trajectory %d has %d tiles, trajectory 0 has %d", i, t.n_tiles, n_tiles);
-        FL_REQUIRE(t.max_tile_nodes >= 0, FL_E_ARG, "fl_interp_patchify: trajectory %d: negative max_tile_nodes", i);
-        FL_REQUIRE((uintptr_t)t.d_idx_tile % 16 == 0 && (uintptr_t)t.d_tile_desc % 16 == 0 && (uintptr_t)t.d_states % 16 == 0 &&
-                       (t.d_mask == nullptr || (uintptr_t)t.d_mask % 16 == 0),
-                   FL_E_ALIGN, "fl_interp_patchify: trajectory %d: tile tables and outputs must be 16-byte aligned", i);
+        FL_REQUIRE(t.max_tile_nodes >= 0 && t.max_tile_patches >= 1, FL_E_ARG, "fl_interp_patchify: trajectory %d: bad tile sizes", i);
+        FL_REQUIRE((uintptr_t)t.d_idx_tile % 16 == 0 && (uintptr_t)t.d_tile_desc % 16 == 0, FL_E_ALIGN,
+                   "fl_interp_patchify: trajectory %d: tile tables must be 16-byte aligned", i);
+        // the bulk copies write 16-byte aligned blocks; outputs placed otherwise go to the other kernels
+        if ((uintptr_t)t.d_states % 16 != 0 || (t.d_mask != nullptr && (uintptr_t)t.d_mask % 16 != 0)) return 1;
         max_nodes = t.max_tile_nodes > max_nodes ? t.max_tile_nodes : max_nodes;
+        max_tile_patches = t.max_tile_patches > max_tile_patches ? t.max_tile_patches : max_tile_patches;
     }
     const int slot_rec = max_nodes > 0 ? max_nodes : 1;
-    // producer warps: two keep up with the meshes of the reference's data sets (a node per ~9 pixels); denser meshes get four
-    const double nodes_per_pixel = (double)slot_rec * n_tiles / ((double)n_patches * ppx);
-    int prod_warps = nodes_per_pixel > 0.2 ? 4 : 2;
-    if (const char* e = getenv("FLUIDGRID_PROD_WARPS")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 6) prod_warps = v; }
+    // a tile has one patch per patch group of consumer warps; whatever warps that leaves are producers (the host sizes the
+    // tiles: 7 patches of 256 pixels -> 14 consumer + 2 producer warps, 6 -> 12 + 4 for meshes with many nodes per pixel)
+    int prod_warps = 0;
+    for (int pw = 2; pw <= 6; pw += 2)
+        if ((TL_WARPS - pw) / wpp >= max_tile_patches) prod_warps = pw;      // the most producers the tile size leaves room for
+    if (!prod_warps) return 1;     // more patches per tile than patch groups: not a plan for this kernel
     const int cons_warps = TL_WARPS - prod_warps;
     const size_t ring = fl_align_up((size_t)(cons_warps / wpp) * 2 * ppx * 13, 128);
     const size_t fixed = HEAD_BYTES + ring;
@@ -523,9 +544,14 @@ int fli::launch_tiled(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, 
     a.trajs = d_trajs;
     a.groups = (max_frames + (int)TF - 1) / (int)TF;
     a.n_tiles = n_tiles;
-    const long n_items = (long)a.groups * n_tiles * n_traj;
-    FL_REQUIRE(n_items < 0x7fffffffL - 2 * FL_SM_COUNT, FL_E_ARG, "fl_interp_patchify: too many work items (%ld)", n_items);
-    a.n_items = (int)n_items;
+    // a unit = (trajectory, run of gpc frame groups, tile): long runs amortise the per-unit table reads, enough units keep every SM busy
+    long fchunks = 1;
+    while (fchunks < a.groups && (long)n_traj * n_tiles * fchunks < 8L * FL_SM_COUNT && (a.groups + fchunks) / (fchunks + 1) >= 4) ++fchunks;
+    a.gpc = (int)((a.groups + fchunks - 1) / fchunks);
+    a.fchunks = (a.groups + a.gpc - 1) / a.gpc;
+    const long n_units = (long)n_traj * a.fchunks * n_tiles;
+    FL_REQUIRE(n_units < 0x7fffffffL - 2 * FL_SM_COUNT, FL_E_ARG, "fl_interp_patchify: too many work units (%ld)", n_units);
+    a.n_units = (int)n_units;
     a.TF = (int)TF;
     a.n_patches = n_patches;
     a.slot_rec = slot_rec;
@@ -534,7 +560,7 @@ int fli::launch_tiled(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, 
     a.dbg = 0;
     if (const char* e = getenv("FLUIDGRID_DBG")) a.dbg = (unsigned)atol(e);
     const size_t smem = fixed + 2 * (size_t)TF * slot_rec * 16;
-    const int grid = n_items < FL_SM_COUNT ? (int)n_items : FL_SM_COUNT;      // one persistent CTA per SM
+    const int grid = n_units < FL_SM_COUNT ? (int)n_units : FL_SM_COUNT;      // one persistent CTA per SM
 #define FL_TILED_LAUNCH(W, P)                                                                                                   \
     do {                                                                                                                        \
         static FlOncePerDevice attr;                                                                                            \

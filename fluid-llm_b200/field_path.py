@@ -36,6 +36,9 @@ CYLINDER = Personality("cylinder", False, 0, False, (0.823, 0.0005865, 0.04763),
 AIRFOIL = Personality("airfoil", True, 1, True, (170.1, -1.183, 9.935e+04), (50.0, 50.0, 6197.0))
 
 
+STAGED_MAX_NODES = 4800     # 3 frames x 16 bytes x nodes = the 227 KB of shared memory of one SM
+
+
 def shard_range(n_items: int, rank: int, world: int):
     """Contiguous block of trajectories owned by `rank` (sizes differ by at most one).  Trajectories are
     independent, so this is the whole multi-GPU story of the per-frame path: no data-path collective."""
@@ -137,8 +140,15 @@ class TrajBatch:
         # tile plans (csrc/fl_tiled.cu): one split of the patch grid for the whole batch, sized for its largest mesh
         ppx = px * py
         self.tile_plans = None
-        if ppx in (128, 256) and tile_patches != 0:
-            tp = int(tile_patches) if tile_patches else max(tables, key=lambda t: t.n_nodes).default_tile_patches()
+        # (tile_patches: None = tiles only where whole frames of the mesh do not fit shared memory at >= 3 frames per work
+        # item -- measured on B200 the whole-mesh staged kernel is the faster one below that, profiles/README.md; 0 = never;
+        # n > 0 = tiles of n patches)
+        biggest = max(tables, key=lambda t: t.n_nodes)
+        if tile_patches is None and os.environ.get("FLUIDGRID_TILE_PATCHES"):
+            tile_patches = int(os.environ["FLUIDGRID_TILE_PATCHES"])
+        want_tiles = tile_patches is not None and tile_patches > 0 or (tile_patches is None and biggest.n_nodes > STAGED_MAX_NODES)
+        if ppx in (128, 256) and want_tiles:
+            tp = int(tile_patches) if tile_patches else biggest.default_tile_patches()
             self.tile_plans = [tab.tile_plan(tp) for tab in tables]
         arr = (FlTraj * self.n_traj)()
         for i, (tr, tab, t0) in enumerate(zip(trajs, tables, t0s)):
@@ -151,7 +161,7 @@ class TrajBatch:
                             tpl.idx_tile.data_ptr() if tpl else 0, tpl.tile_nodes.data_ptr() if tpl else 0,
                             tpl.tile_desc.data_ptr() if tpl else 0, tpl.tile_patches.data_ptr() if tpl else 0,
                             tpl.tile_quads.data_ptr() if tpl else 0, tpl.tile_qslots.data_ptr() if tpl else 0,
-                            tpl.n_tiles if tpl else 0, tpl.max_tile_nodes if tpl else 0)
+                            tpl.n_tiles if tpl else 0, tpl.max_tile_nodes if tpl else 0, min(tpl.tp, tab.n_patches) if tpl else 0, 0)
         self.host_desc = arr
         raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
         self.desc = torch.from_numpy(raw).to(dev)

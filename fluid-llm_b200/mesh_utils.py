@@ -67,8 +67,6 @@ def grid_pos(x_min, x_max, y_min, y_max, grid_res, numpy_semantics=None):
             np.ascontiguousarray(np.broadcast_to(ay[None, :], (nx, ny))))
 
 
-SMEM_BYTES = 227 * 1024        # shared memory one CTA can have on sm_100a
-TILE_WARPS = 16                # warps of the tiled kernel's CTA (csrc/fl_tiled.cu)
 
 
 def serpentine_patches(n_bx, n_by):
@@ -87,32 +85,13 @@ def tile_sizes(n_patches, tp):
     return sizes
 
 
-def choose_tile_patches(n_patches, n_nodes, ppx, max_frames=16):
-    """Patches per tile for the tiled kernel.  Small tiles stage few nodes (so more frames fit in shared memory per
-    work item and the per-pixel table records are amortised over more frames) but repeat the nodes on tile borders;
-    the chunk count of a tile (128 pixels each) should fill the CTA's 16 warps evenly."""
-    env = os.environ.get("FLUIDGRID_TILE_PATCHES")
-    if env:
-        return max(1, min(int(env), n_patches))
+def choose_tile_patches(n_patches, n_nodes, ppx):
+    """Patches per tile for the tiled kernel (csrc/fl_tiled.cu): one patch per patch group of consumer warps, i.e.
+    14 consumer warps / (ppx / 128) warps per patch with two producer warps, or 12 / (ppx / 128) with four producer
+    warps for meshes with many nodes per output pixel (their staging needs more threads)."""
     wpp = max(1, ppx // 128)
-    ring = (TILE_WARPS // wpp) * 2 * ppx * 13
-    stage = (SMEM_BYTES - 256 - ring) // 2
-    best, best_cost = n_patches, None
-    cands = sorted(set([n_patches] + list(range(8 // wpp * wpp or 1, n_patches, 8))))
-    for tp in cands:
-        nodes_in = n_nodes * tp / n_patches
-        s_est = nodes_in + 5.0 * np.sqrt(max(nodes_in, 1.0)) + 8       # nodes of the tile + the ring of nodes around it
-        tf = min(max_frames, int(stage // (16 * s_est)))
-        if tf < 2:
-            continue
-        slots = sum(-(-(t * wpp) // TILE_WARPS) * TILE_WARPS for t in tile_sizes(n_patches, tp))
-        balance = n_patches * wpp / slots
-        halo = s_est / max(nodes_in, 1.0)
-        # per pixel-frame: 1 (the frame loop) + table set-up per item / frames + node staging share
-        cost = (1.0 + 0.8 / tf + 0.15 * (halo - 1.0)) / balance
-        if best_cost is None or cost < best_cost - 1e-9:
-            best, best_cost = tp, cost
-    return best
+    dense = n_nodes > 0.2 * n_patches * ppx
+    return max(1, min((12 if dense else 14) // wpp, n_patches))
 
 
 class TilePlan:

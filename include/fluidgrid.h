@@ -114,6 +114,7 @@ typedef struct FlTraj {
     const int32_t* d_tile_qslots;  /* with d_tile_quads: [quads][4] the slots of each quad's 4 nodes (-1: not used by the tile); lets the
                                       kernel stage with coalesced 128-bit loads when the frames are 16-byte aligned and padded to quads */
     int32_t n_tiles, max_tile_nodes;
+    int32_t max_tile_patches, reserved_;   /* patches of the largest tile: at most 7 (px*py = 256) or 14 (128), one per patch group */
 } FlTraj;
 /* prs_stride a multiple of 4, vel_stride >= 2 * prs_stride, 16-byte aligned bases and pad floats
  * that are readable and finite select the staged kernel: whole frames are staged in shared memory

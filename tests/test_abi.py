@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_layout_matches_header():
     from fluid_llm_b200._lib import FlTraj
-    assert ctypes.sizeof(FlTraj) == 8 * 8 + 6 * 4 + 6 * 8 + 2 * 4 == 144
+    assert ctypes.sizeof(FlTraj) == 8 * 8 + 6 * 4 + 6 * 8 + 4 * 4 == 152
     assert FlTraj.n_nodes.offset == 64 and FlTraj.prs_stride.offset == 84
     assert FlTraj.d_idx_tile.offset == 88 and FlTraj.n_tiles.offset == 136 and FlTraj.max_tile_nodes.offset == 140
 

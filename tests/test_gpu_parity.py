@@ -11,6 +11,20 @@ from helpers import PATCH, oracle_ds_get, personality_of, tie_mesh, trajectory
 pytestmark = pytest.mark.gpu
 
 
+KERNELS = ["staged", "gather", "tiled"]
+
+
+def _kernel_args(kernel, ppx=256):
+    """interp_patchify / TrajBatch arguments that force one of the three per-step kernels (csrc/fl_interp.cu, fl_tiled.cu)."""
+    return {"staged": dict(tile_patches=0), "gather": dict(tile_patches=0, force_gather=True),
+            "tiled": dict(tile_patches=14 * 128 // ppx)}[kernel]
+
+
+def _same_bits(a, b):
+    """bitwise equality of two float32 arrays (array_equal would accept -0.0 for +0.0)"""
+    return np.array_equal(np.ascontiguousarray(a).view(np.int32), np.ascontiguousarray(b).view(np.int32))
+
+
 def _plan(kind, sem="1.26", res=238):
     from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
     from fluid_llm_b200.mesh_utils import MeshPlan
@@ -114,9 +128,9 @@ def test_to_grid_nonfinite_values_are_masked():
 
 @pytest.mark.parametrize("kind", ["cylinder", "airfoil", "eagle"])
 @pytest.mark.parametrize("normalize", [True, False])
-@pytest.mark.parametrize("force_gather", [False, True], ids=["staged", "gather"])
-def test_interp_patchify_matches_oracle(kind, normalize, force_gather):
-    """states / mask of the fused kernel == the oracle's unfold+normalise pipeline, bit for bit
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_interp_patchify_matches_oracle(kind, normalize, kernel):
+    """states / mask of the fused kernels == the oracle's unfold+normalise pipeline, bit for bit, signed zeros included
     (north_star tolerance: 1e-6 relative; achieved: exact on these inputs)."""
     from fluid_llm_b200.field_path import AIRFOIL, CYLINDER, DeviceTrajectory, interp_patchify
     from fluid_llm_b200.airfoil_ds import crop_airfoil_mesh
@@ -128,7 +142,7 @@ def test_interp_patchify_matches_oracle(kind, normalize, force_gather):
         vel, prs = vel[:, nmask], prs[:, nmask]
     pers = AIRFOIL if kind == "airfoil" else CYLINDER
     states, mask, tab = interp_patchify(DeviceTrajectory(vel, prs, plan), 1, 3, 2, PATCH, pers, normalize=normalize,
-                                        force_gather=force_gather)
+                                        **_kernel_args(kernel))
     (_, _, _, _, _), extra = oracle_ds_get(kind, 1, 3, 2, normalize=normalize)
     assert (tab.n_bx, tab.n_by) == (extra["N_x_patch"], extra["N_y_patch"])
     assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
@@ -136,9 +150,11 @@ def test_interp_patchify_matches_oracle(kind, normalize, force_gather):
     assert s.shape == so.shape and s.dtype == so.dtype
     np.testing.assert_allclose(s, so, rtol=1e-6, atol=0)
     assert np.array_equal(s, so), f"{(s != so).sum()} of {s.size} values differ in the last bit"
+    assert _same_bits(s, so), "a signed zero differs from the reference's +0.0"
 
 
-def test_interp_patchify_batch_of_meshes():
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_interp_patchify_batch_of_meshes(kernel):
     """One launch over several trajectories with different meshes, different start frames."""
     from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, TrajBatch
     from fluid_llm_b200.mesh_utils import MeshPlan
@@ -149,8 +165,10 @@ def test_interp_patchify_batch_of_meshes():
         trajs.append(DeviceTrajectory(tr["velocity"], tr["pressure"], plan))
         tabs.append(plan.patch_table(PATCH))
         want.append(oracle_ds_get("cylinder", t0, 4, 1, mesh_seed=seed, field_seed=10 + seed)[1])
-    batch = TrajBatch(trajs, tabs, t0s, 1, 4)
-    states, mask = batch.run(CYLINDER)
+    ka = _kernel_args(kernel)
+    batch = TrajBatch(trajs, tabs, t0s, 1, 4, tile_patches=ka["tile_patches"])
+    assert (batch.tile_plans is not None) == (kernel == "tiled")
+    states, mask = batch.run(CYLINDER, force_gather=ka.get("force_gather", False))
     torch.cuda.synchronize()
     for i, ex in enumerate(want):
         assert np.array_equal(states[i].cpu().numpy(), ex["states"])
@@ -228,27 +246,51 @@ def test_nonfinite_node_values_take_the_checked_path(kind):
     pers = AIRFOIL if kind == "airfoil" else CYLINDER
     with np.errstate(all="ignore"):
         _, extra = P.ds_get(tr, 0, 5, 1, 238, PATCH, personality_of(kind), return_all=True)
-    for fg in (False, True):
-        states, mask, _ = interp_patchify(DeviceTrajectory(vel, prs, plan), 0, 5, 1, PATCH, pers, force_gather=fg)
-        assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
-        assert np.array_equal(states.cpu().numpy(), extra["states"])
+    for kernel in KERNELS:
+        states, mask, _ = interp_patchify(DeviceTrajectory(vel, prs, plan), 0, 5, 1, PATCH, pers, **_kernel_args(kernel))
+        assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool)), kernel
+        assert _same_bits(states.cpu().numpy(), extra["states"]), kernel
 
 
-def test_long_sequence_many_items():
-    """More frames than one staged work item holds, odd node count (padded frame pitch), interval 3."""
+@pytest.mark.parametrize("kernel", ["staged", "tiled"])
+def test_long_sequence_many_items(kernel):
+    """More frames than one work item holds (several frame groups per unit in the tiled kernel), odd node count (padded
+    frame pitch), interval 3."""
     from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
     from fluid_llm_b200.mesh_utils import MeshPlan
     tr = trajectory("cylinder", 64, 3, 7)
     plan = MeshPlan(tr["mesh_pos"], tr["cells"], 238)
-    states, mask, _ = interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 2, 20, 3, PATCH, CYLINDER)
+    states, mask, _ = interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 2, 20, 3, PATCH, CYLINDER,
+                                      **_kernel_args(kernel))
     _, extra = oracle_ds_get("cylinder", 2, 20, 3, T=64, mesh_seed=3, field_seed=7)
-    assert np.array_equal(states.cpu().numpy(), extra["states"])
+    assert _same_bits(states.cpu().numpy(), extra["states"])
     assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
 
 
-def test_big_mesh_gather_path_matches_oracle():
-    """BASELINE config 5 in miniature: a structured ~80k-triangle mesh on a 512-point grid.  The node arrays do
-    not fit the staged kernel's shared memory, so this exercises the gather-from-global kernel end to end."""
+def test_tiled_kernel_many_frame_groups_and_no_mask():
+    """The tiled kernel over 64 frames (4+ frame groups per unit, runs of groups split into units), with and without the
+    mask output, against the staged kernel's bits."""
+    from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, TrajBatch
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    tr = trajectory("cylinder", 64, 3, 7)
+    plan = MeshPlan(tr["mesh_pos"], tr["cells"], 238)
+    dt = DeviceTrajectory(tr["velocity"], tr["pressure"], plan)
+    tab = plan.patch_table(PATCH)
+    ref = TrajBatch([dt], [tab], [0], 1, 64, tile_patches=0)
+    rs, rm = ref.run(CYLINDER)
+    for tp in (7, 6, 5, 3):
+        for want_mask in (True, False):
+            b = TrajBatch([dt], [tab], [0], 1, 64, want_mask=want_mask, tile_patches=tp)
+            s, m = b.run(CYLINDER)
+            assert torch.equal(s.view(torch.int32), rs.view(torch.int32)), (tp, want_mask)
+            assert m is None or torch.equal(m, rm)
+    _, extra = oracle_ds_get("cylinder", 0, 64, 1, T=64, mesh_seed=3, field_seed=7)
+    assert _same_bits(rs[0].cpu().numpy(), extra["states"])
+
+
+def test_big_mesh_tiled_and_gather_paths_match_oracle():
+    """BASELINE config 5 in miniature: a structured ~80k-triangle mesh on a 512-point grid.  Whole frames of the node
+    arrays do not fit shared memory, so the default is the tiled kernel; the gather-from-global kernel is checked too."""
     from fluid_llm_b200 import synth
     from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
     from fluid_llm_b200.mesh_utils import MeshPlan
@@ -259,12 +301,16 @@ def test_big_mesh_gather_path_matches_oracle():
     assert (plan.nx, plan.ny) == tri_o.shape == (512, 256)
     assert np.array_equal(plan.tri_index, tri_o)
     assert np.array_equal(tri_o, mpl_tri.rule_find_many(triang, gx, gy, bucketed=True))
-    states, mask, tab = interp_patchify(DeviceTrajectory(vel, prs, plan), 0, 3, 1, PATCH, CYLINDER)
+    from fluid_llm_b200.field_path import TrajBatch
+    dt = DeviceTrajectory(vel, prs, plan)
+    assert TrajBatch([dt], [plan.patch_table(PATCH)], [0], 1, 3).tile_plans is not None      # the default picks tiles here
     tr = {"mesh_pos": pos, "cells": cells, "velocity": vel, "pressure": prs}
     _, extra = P.ds_get(tr, 0, 3, 1, 512, PATCH, "cylinder", return_all=True)
-    assert (tab.n_bx, tab.n_by) == (32, 16)
-    assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
-    assert np.array_equal(states.cpu().numpy(), extra["states"])
+    for kw in (dict(), dict(tile_patches=7), dict(tile_patches=0, force_gather=True)):
+        states, mask, tab = interp_patchify(dt, 0, 3, 1, PATCH, CYLINDER, **kw)
+        assert (tab.n_bx, tab.n_by) == (32, 16)
+        assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool)), kw
+        assert _same_bits(states.cpu().numpy(), extra["states"]), kw
 
 
 @pytest.mark.parametrize("patch", [(8, 8), (16, 8), (8, 16), (4, 8)])
@@ -273,11 +319,13 @@ def test_other_patch_sizes(patch):
     from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
     tr = trajectory("cylinder")
     plan, _, _ = _plan("cylinder")
-    states, mask, tab = interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 0, 3, 1, patch, CYLINDER)
     _, extra = P.ds_get(tr, 0, 3, 1, 238, patch, "cylinder", return_all=True)
-    assert (tab.n_bx, tab.n_by) == (extra["N_x_patch"], extra["N_y_patch"])
-    assert np.array_equal(states.cpu().numpy(), extra["states"])
-    assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool))
+    variants = [dict()] + ([dict(tile_patches=14), dict(tile_patches=9)] if patch[0] * patch[1] == 128 else [])
+    for kw in variants:        # 128-pixel patches also run the tiled kernel (one warp per patch)
+        states, mask, tab = interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 0, 3, 1, patch, CYLINDER, **kw)
+        assert (tab.n_bx, tab.n_by) == (extra["N_x_patch"], extra["N_y_patch"])
+        assert np.array_equal(states.cpu().numpy(), extra["states"]), kw
+        assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool)), kw
 
 
 def test_unsupported_patch_size_is_an_error():
@@ -307,7 +355,8 @@ def test_c_abi_called_directly_as_integration_md_shows():
                     ("vel_stride", ctypes.c_int32), ("prs_stride", ctypes.c_int32),
                     ("d_idx_tile", ctypes.c_void_p), ("d_tile_nodes", ctypes.c_void_p), ("d_tile_desc", ctypes.c_void_p),
                     ("d_tile_patches", ctypes.c_void_p), ("d_tile_quads", ctypes.c_void_p), ("d_tile_qslots", ctypes.c_void_p),
-                    ("n_tiles", ctypes.c_int32), ("max_tile_nodes", ctypes.c_int32)]
+                    ("n_tiles", ctypes.c_int32), ("max_tile_nodes", ctypes.c_int32),
+                    ("max_tile_patches", ctypes.c_int32), ("reserved_", ctypes.c_int32)]
 
     lib.fl_interp_patchify.restype = ctypes.c_int
     lib.fl_interp_patchify.argtypes = [ctypes.POINTER(FlTraj), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -320,7 +369,7 @@ def test_c_abi_called_directly_as_integration_md_shows():
     mask = torch.empty((seq_len, tab.n_patches, 16, 16), dtype=torch.uint8, device="cuda")
     traj = FlTraj(vel.data_ptr(), prs.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(), None, None,
                   states.data_ptr(), mask.data_ptr(), N, step, interval, seq_len, vel.stride(0), prs.stride(0),
-                  None, None, None, None, None, None, 0, 0)      # no tile plan: the library picks the staged / gather kernel
+                  None, None, None, None, None, None, 0, 0, 0, 0)      # no tile plan: the library picks the staged / gather kernel
     mean = (ctypes.c_float * 3)(0.823, 0.0005865, 0.04763)
     std = (ctypes.c_float * 3)(0.275, 0.275, 0.275)
     rc = lib.fl_interp_patchify(ctypes.byref(traj), 1, tab.n_patches, 16, 16, mean, std, 0,
@@ -336,8 +385,9 @@ def test_c_abi_called_directly_as_integration_md_shows():
     assert b"stride" in lib.fl_last_error()
 
 
-@pytest.mark.parametrize("kind,force_gather", [("cylinder", False), ("airfoil", False), ("eagle", False), ("cylinder", True)])
-def test_interp_patchify_writes_stay_inside_the_output_buffers(kind, force_gather):
+@pytest.mark.parametrize("kind,kernel", [("cylinder", "staged"), ("airfoil", "staged"), ("eagle", "staged"), ("cylinder", "gather"),
+                                         ("cylinder", "tiled"), ("airfoil", "tiled"), ("eagle", "tiled")])
+def test_interp_patchify_writes_stay_inside_the_output_buffers(kind, kernel):
     """Outputs placed inside guarded buffers (TrajBatch(out=...)): the staged and the gather kernel write every element of
     [n_traj, n_frames, L, ...] and nothing around it."""
     from fluid_llm_b200.field_path import AIRFOIL, CYLINDER, DeviceTrajectory, TrajBatch
@@ -357,8 +407,9 @@ def test_interp_patchify_writes_stay_inside_the_output_buffers(kind, force_gathe
     mbuf = torch.full((G + n + G,), 77, dtype=torch.uint8, device="cuda")
     states = sbuf[G:G + 3 * n].view(n_traj, T, L, 3, 16, 16)
     mask = mbuf[G:G + n].view(n_traj, T, L, 16, 16)
-    batch = TrajBatch(trajs, [tab, tab], [0, 1], 1, T, out=(states, mask))
-    batch.run(pers, force_gather=force_gather)
+    ka = _kernel_args(kernel)
+    batch = TrajBatch(trajs, [tab, tab], [0, 1], 1, T, out=(states, mask), tile_patches=ka["tile_patches"])
+    batch.run(pers, force_gather=ka.get("force_gather", False))
     torch.cuda.synchronize()
     assert bool((sbuf[:G] == 777.0).all()) and bool((sbuf[-G:] == 777.0).all())
     assert bool((mbuf[:G] == 77).all()) and bool((mbuf[-G:] == 77).all())
