@@ -44,6 +44,7 @@ SIGNATURES = {
                                    c_uint, c_void_p]),
     "fl_interp_patchify_dev": (c_int, [c_void_p, POINTER(FlTraj), c_int, c_int, c_int, c_int, POINTER(c_float),
                                        POINTER(c_float), c_uint, c_void_p]),
+    "fl_last_interp_kernel": (ctypes.c_char_p, []),
     "fl_to_grid": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "fl_interp_frames": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_int, POINTER(c_float), POINTER(c_float), c_uint, c_void_p, c_void_p, c_void_p]),

@@ -22,6 +22,8 @@ using fli::norm_fast;
 using fli::norm_fast2;
 using fli::pack2;
 
+static thread_local const char* g_last_kernel = "";     // what fl_interp_patchify last launched on this thread
+
 namespace {
 
 // Generic kernel: one CTA = one patch (px*py threads) x a chunk of frames of one trajectory.
@@ -287,6 +289,7 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
         for (int c = 0; c < 3; ++c) { sc.mean[c] = nc.mean[c]; sc.stdv[c] = nc.stdv[c]; sc.rcp[c] = 1.0f / nc.stdv[c]; }
         sc.fast_div = (flags & FL_NO_NORM) ? 1 : (fli::fast_div_ok(nc.mean, nc.stdv) ? 1 : 0);
         const int rc = fli::launch_tiled(d_trajs, h_trajs, n_traj, max_frames, n_patches, px, py, sc, flags, st);
+        if (rc == FL_OK) g_last_kernel = "k_interp_patchify_tiled";
         if (rc != 1) return rc;          // 1 = no tile plan / does not fit: fall through
     }
     // ---- staged path: needs the host copy of the descriptors to check strides / alignment ----
@@ -324,6 +327,7 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             k_interp_patchify_staged<<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift, slot_prs,
                                                                      sc, flags);
             FL_LAUNCH_CHECK();
+            g_last_kernel = "k_interp_patchify_staged";
             return FL_OK;
         }
     }
@@ -336,6 +340,7 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
     dim3 grid(n_patches, (max_frames + fpc - 1) / fpc, n_traj);
     k_interp_patchify_gather<<<grid, ppx, 0, st>>>(d_trajs, n_patches, ppx, fpc, nc, flags);
     FL_LAUNCH_CHECK();
+    g_last_kernel = "k_interp_patchify_gather";
     return FL_OK;
 }
 
@@ -378,6 +383,8 @@ static int check_trajs(const char* who, const FlTraj* h_trajs, int n_traj, int* 
     *max_frames = mf;
     return FL_OK;
 }
+
+extern "C" const char* fl_last_interp_kernel(void) { return g_last_kernel; }
 
 extern "C" int fl_interp_patchify_dev(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int n_patches, int px, int py,
                                       const float* h_mean, const float* h_std, unsigned flags, void* stream) {

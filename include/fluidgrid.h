@@ -128,6 +128,10 @@ int fl_interp_patchify(const FlTraj* h_trajs, int n_traj, int n_patches, int px,
 int fl_interp_patchify_dev(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int n_patches, int px, int py,
                            const float* h_mean, const float* h_std, unsigned flags, void* stream);
 
+/* which kernel the last fl_interp_patchify[_dev] call of this thread launched: "k_interp_patchify_tiled" (tile plan given),
+ * "k_interp_patchify_staged" (whole frames fit shared memory) or "k_interp_patchify_gather"; "" before the first call */
+const char* fl_last_interp_kernel(void);
+
 /* Plain-grid variant (no pad/patchify): replaces mesh_utils.to_grid (src/dataloader/mesh_utils.py:82-91)
  * for n_fields scalar node fields at once.  d_val f32[n_fields, n_nodes] -> d_data f32[n_fields, nx*ny],
  * d_mask u8[n_fields, nx*ny] (1 = outside mesh or non-finite). */

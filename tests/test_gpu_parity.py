@@ -416,3 +416,57 @@ def test_interp_patchify_writes_stay_inside_the_output_buffers(kind, kernel):
     assert not bool((states == 777.0).any()) and not bool((mask == 77).any())
     _, extra = oracle_ds_get(kind, 1, T, 1)
     assert np.array_equal(states[1].cpu().numpy(), extra["states"])
+
+
+def test_c5_full_size_1m_triangles():
+    """BASELINE config 5 at FULL size: ~1M triangles / ~0.5M nodes on a 2048 x 1024 grid (8192 patches), the tiled kernel.
+    Triangle ids against the stated rule evaluated on all 2M cells and against the trapezoid map (the restated matplotlib
+    trifinder) on a strided subset plus the boundary rows and columns; states and mask of two frames against the oracle's
+    plane interpolation + pad + unfold + normalise."""
+    from fluid_llm_b200 import synth
+    from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, TrajBatch
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    pos, cells = synth.make_mesh("big", 0)
+    assert len(cells) == 1_000_000 and len(pos) > 500_000
+    plan = MeshPlan(pos, cells, 2048)
+    assert (plan.nx, plan.ny) == (2048, 1024)
+    triang = mpl_tri.Triangulation(pos[:, 0], pos[:, 1], cells)
+    gx, gy = plan.grid_x, plan.grid_y
+    assert np.array_equal(gx, P.grid_pos(pos[:, 0].min(), pos[:, 0].max(), pos[:, 1].min(), pos[:, 1].max(), 2048)[0])
+    tri_rule = mpl_tri.rule_find_many(triang, gx, gy, bucketed=True)
+    assert np.array_equal(plan.tri_index, tri_rule)                       # all 2 097 152 cells
+    finder = triang.get_trifinder()                                       # trapezoid map over 1M triangles
+    sub = np.zeros(gx.shape, dtype=bool)
+    sub[::8, ::8] = True
+    sub[[0, -1], :] = True
+    sub[:, [0, -1]] = True                                               # the boundary cells sit exactly on boundary edges
+    assert np.array_equal(finder(gx[sub], gy[sub]), plan.tri_index[sub])
+    vel, prs = synth.make_fields("big", pos, 2, 1)
+    dt = DeviceTrajectory(vel, prs, plan)
+    tab = plan.patch_table(PATCH)
+    assert (tab.n_bx, tab.n_by) == (128, 64)
+    batch = TrajBatch([dt], [tab], [0], 1, 2)
+    assert batch.tile_plans is not None
+    states, mask = batch.run(CYLINDER)
+    import fluid_llm_b200
+    assert fluid_llm_b200.load().fl_last_interp_kernel() == b"k_interp_patchify_tiled"
+    seq = []
+    for t in range(2):
+        state, m = P.get_step(triang, tri_rule, gx, gy, vel, prs, t, PATCH)
+        seq.append(np.concatenate([state, m[None].astype(state.dtype)], axis=0))
+    patches = P.unfold_patches(np.stack(seq).astype(np.float32), PATCH)
+    want = np.ascontiguousarray(patches[:, :-1].transpose(0, 4, 1, 2, 3))
+    want_mask = np.ascontiguousarray(patches[:, -1].transpose(0, 3, 1, 2))
+    want = P.normalize(want, want_mask, "cylinder")
+    assert np.array_equal(mask[0].cpu().numpy().astype(bool), want_mask.astype(bool))
+    got = states[0].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=0)                  # north_star's tolerance, every value
+    # the reference rounds the fp64 plane a*x + b*y + c, the kernel the fp64 barycentric sum: the two fp64 values differ in
+    # their last bits, so a handful of the 12.6M fp32 roundings land on the other side (1 ulp); everything else is bit-equal
+    diff = got.view(np.int32) != want.view(np.int32)
+    assert diff.sum() <= 12, f"{diff.sum()} of {got.size} values differ in their bits"
+    assert np.all(np.abs(got.view(np.int32)[diff].astype(np.int64) - want.view(np.int32)[diff].astype(np.int64)) <= 1)
+    print(f"C5 full size: {int(diff.sum())} of {got.size} values differ by one ulp")
+    # the gather-from-global kernel agrees on the same table
+    s2, m2 = TrajBatch([dt], [tab], [0], 1, 2, tile_patches=0).run(CYLINDER, force_gather=True)
+    assert torch.equal(s2.view(torch.int32), states.view(torch.int32)) and torch.equal(m2, mask)
