@@ -37,7 +37,7 @@ class AirfoilDataset(_GpuFieldDataset):
     personality = AIRFOIL
 
     def _list_files(self):
-        return _natsorted([f for f in os.listdir(f"{self.load_dir}/") if f.endswith(('.pkl', '.fgt'))])
+        return _natsorted(self._one_per_stem())
 
     def _prepare_mesh(self, save_data):
         mask, pos, faces = crop_airfoil_mesh(save_data['mesh_pos'], save_data['cells'])

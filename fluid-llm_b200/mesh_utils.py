@@ -204,7 +204,12 @@ class MeshPlan:
     `x`, `y`, `triangles` are kept (host) because the reference's interpolator checks `z` against
     `triangulation.x.shape` (src/_triinterpolate.py:37-39)."""
 
-    def __init__(self, pos, faces, grid_res=238, numpy_semantics=None, device=None):
+    def __init__(self, pos, faces, grid_res=238, numpy_semantics=None, device=None, allow_degenerate=False):
+        """`allow_degenerate`: matplotlib's trapezoid-map trifinder is undefined on triangles of zero area (three colinear
+        nodes: their edges overlap, its map builder raises or loops), and its plane fit takes a pseudo-inverse branch there
+        (`calculate_plane_coefficients`); the data sets contain none.  By default such input raises ValueError like an
+        invalid triangulation does upstream; with allow_degenerate=True the rule locator treats the triangle like any
+        other and a grid point located in it gets the value of the triangle's first vertex (weights 0, 0)."""
         _lib.require_cuda()
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if dev.index is None:
@@ -228,6 +233,13 @@ class MeshPlan:
         if tri.shape[0] == 0:
             raise ValueError("triangles must be a (N, 3) int array with N >= 1")
         pos32 = np.ascontiguousarray(pos, dtype=F32)
+        p = pos32.astype(F64)[tri]                              # the same fp64 cross product as correct_triangles
+        area2 = (p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1]) - (p[:, 1, 1] - p[:, 0, 1]) * (p[:, 2, 0] - p[:, 0, 0])
+        self.n_degenerate = int((area2 == 0).sum())
+        if self.n_degenerate and not allow_degenerate:
+            raise ValueError(f"{self.n_degenerate} triangle(s) of zero area (first: triangle {int(np.argmax(area2 == 0))}): "
+                             "the triangulation is invalid for the trapezoid-map trifinder; pass allow_degenerate=True to "
+                             "locate with the stated rule anyway")
         self.x, self.y, self.triangles = pos32[:, 0].astype(F64), pos32[:, 1].astype(F64), tri
         self.n_nodes, self.n_cells = len(pos32), len(tri)
         self.numpy_semantics = numpy_semantics or default_numpy_semantics()
@@ -346,6 +358,12 @@ def to_grid(val, grid_x, grid_y, triang: MeshPlan, tri_index):
     if tuple(np.shape(grid_x)) != (triang.nx, triang.ny):
         raise ValueError(f"grid of shape {np.shape(grid_x)} does not belong to this mesh plan "
                          f"({triang.nx}, {triang.ny})")
+    # the reference interpolates with the tri_index it is handed (_triinterpolate.py:265-267); the plan's static table was
+    # built from the plan's own, so anything else is refused instead of being silently replaced
+    if tri_index is not triang._tri_index_host:
+        ti = tri_index.detach().cpu().numpy() if torch.is_tensor(tri_index) else np.asarray(tri_index)
+        if not np.array_equal(ti, triang.tri_index):
+            raise ValueError("tri_index differs from the one get_mesh_interpolation returned for this mesh plan")
     dev = triang.device
     with torch.cuda.device(dev):
         v = v.to(device=dev, dtype=torch.float32).reshape(-1, triang.n_nodes).contiguous()

@@ -79,16 +79,27 @@ class _GpuFieldDataset(Dataset):
         self.save_files = self._list_files()
         # simple_dataloader.py:45-56: probe file [1], step 20, for value ranges and the patch grid
         traj = self._load_step(self.save_files[1])
-        states, _, tab = interp_patchify(traj, 20, 1, 1, self.patch_size, self.personality, normalize=False)
+        # ... min / max over the whole padded frame, BEFORE the airfoil's ring crop (airfoil_ds.py:46-50): no crop here
+        full = Personality(self.personality.name, self.personality.flip_y, 0, self.personality.mask_aware_norm,
+                           self.personality.means, self.personality.stds)
+        states, _, _ = interp_patchify(traj, 20, 1, 1, self.patch_size, full, normalize=False)
         lo, hi = states[0].amin(dim=(0, 2, 3)).cpu().numpy(), states[0].amax(dim=(0, 2, 3)).cpu().numpy()
         self.ds_min_max = [(lo[0], hi[0]), (lo[1], hi[1]), (lo[2], hi[2])]
+        tab = traj.plan.patch_table(self.patch_size, self.personality.crop_patches, self.personality.flip_y)
         self.N_x_patch, self.N_y_patch = tab.n_bx, tab.n_by
         self.N_patch = self.N_x_patch * self.N_y_patch
 
     # -- file handling ----------------------------------------------------------------------
     def _list_files(self):
         # the reference's pickles, or the flat .fgt files of traj_store.py (same stems, converted once)
-        return sorted([f for f in os.listdir(f"{self.load_dir}/") if f.endswith(('.pkl', '.fgt'))])
+        return sorted(self._one_per_stem())
+
+    def _one_per_stem(self):
+        """A directory converted in place holds x.pkl AND x.fgt: one entry per trajectory (the .fgt), so __len__ and the
+        index -> trajectory map stay those of the reference's listing of the pickles."""
+        names = [f for f in os.listdir(f"{self.load_dir}/") if f.endswith(('.pkl', '.fgt'))]
+        fgt = {os.path.splitext(f)[0] for f in names if f.endswith('.fgt')}
+        return [f for f in names if f.endswith('.fgt') or os.path.splitext(f)[0] not in fgt]
 
     def _prepare_mesh(self, save_data):
         """-> (pos, faces, velocity, pressure) as the locate step should see them."""

@@ -113,3 +113,27 @@ def rollout_step(last_state, pred_diff_img, mask, ds_props: DSProps):
         check(load().fl_rollout_step(ptr(img_c), ptr(m), ptr(last_c), ptr(diffs), ptr(nxt), bs * T, ds_props.Nx_patch,
                                      ds_props.Ny_patch, C, px, py, stream_ptr()), "fl_rollout_step")
     return nxt, diffs
+
+
+def get_data_loader(config, mode="train", device=None, numpy_semantics=None):
+    """utils_model.py:9-45: config -> (DataLoader, DSProps), same dataset selection, same DSProps.
+
+    The datasets produce their samples on the GPU (one kernel launch per DataLoader batch through `__getitems__`), so the
+    loader runs in the calling process (`num_workers=0`, no pinning: nothing is on the host to pin) and the default
+    collate stacks device tensors.  `config['num_workers']` is accepted and ignored."""
+    from torch.utils.data import DataLoader
+    from .airfoil_ds import AirfoilDataset
+    from .simple_dataloader import MGNDataset
+    ds_name = config["load_dir"]
+    kw = dict(load_dir=f'{ds_name}/{mode}', resolution=config['resolution'], patch_size=config['patch_size'],
+              stride=config['stride'], seq_len=config['seq_len'], seq_interval=config['seq_interval'], mode=mode,
+              normalize=config['normalize_ds'], device=device, numpy_semantics=numpy_semantics)
+    if (ds_name == "./ds/MGN/cylinder_dataset") | (ds_name == "cylinder"):
+        ds = MGNDataset(**kw)
+    elif (ds_name == "./ds/MGN/airfoil_dataset") | (ds_name == "airfoil"):
+        ds = AirfoilDataset(**kw)
+    else:
+        raise ValueError(f"Invalid dataset {ds_name}")
+    dl = DataLoader(ds, batch_size=config['batch_size'], num_workers=0, shuffle=(mode == 'train'))
+    ds_props = DSProps(Nx_patch=ds.N_x_patch, Ny_patch=ds.N_y_patch, patch_size=ds.patch_size, seq_len=ds.seq_len - 1)
+    return dl, ds_props

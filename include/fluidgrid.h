@@ -60,10 +60,12 @@ int fl_device_count(void);
  * d_pos f32[n_nodes,2], d_cells i32[n_cells,3] (any winding), d_grid_ax f32[nx], d_grid_ay f32[ny]
  * (the axes of grid_pos, mesh_utils.py:64-79; cell (ix,iy) is at (ax[ix], ay[iy])).
  * Outputs, all [nx*ny] in the reference's [ix, iy] order (iy fastest):
- *   d_tri_index i32 -- bit-exact with TrapezoidMapTriFinder incl. its tie-breaks: a query on a
- *       mesh vertex -> lowest-index triangle listing it; on an edge -> the triangle above the
+ *   d_tri_index i32 -- the stated tie-break rule, which is what matplotlib 3.8.2's TrapezoidMapTriFinder computes as
+ *       restated in oracle/tri_oracle.cpp (matplotlib layer: restated, never executed -- it is not installed where this
+ *       was built): a query on a mesh vertex -> lowest-index triangle listing it; on an edge -> the triangle above the
  *       edge (left of the edge directed from its lexicographically smaller to larger end point),
- *       else the one below; else the containing triangle; -1 if none.
+ *       else the one below; else the containing triangle; -1 if none.  Bit-exact against that restatement, against an
+ *       independent brute-force evaluation of the rule and against an exact-rational one (oracle/exact_locator.py).
  *   d_cell_idx / d_cell_w -- the static table (may be NULL to skip).
  * Workspace: fl_locate_workspace_bytes(n_nodes, n_cells) bytes, 256-B aligned. */
 size_t fl_locate_workspace_bytes(int n_nodes, int n_cells);

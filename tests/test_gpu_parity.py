@@ -470,3 +470,53 @@ def test_c5_full_size_1m_triangles():
     # the gather-from-global kernel agrees on the same table
     s2, m2 = TrajBatch([dt], [tab], [0], 1, 2, tile_patches=0).run(CYLINDER, force_gather=True)
     assert torch.equal(s2.view(torch.int32), states.view(torch.int32)) and torch.equal(m2, mask)
+
+
+def test_locate_agrees_with_the_exact_rational_rule():
+    """CUDA triangle ids == the stated rule in exact rational arithmetic (oracle/exact_locator.py) on the tie mesh, where
+    every grid point sits on a vertex, an edge or in a hole."""
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    from oracle.exact_locator import exact_find_many
+    pos, tris = tie_mesh()
+    for res in (9, 17):
+        plan = MeshPlan(pos, tris, res, "1.26")
+        assert np.array_equal(plan.tri_index, exact_find_many(pos, tris, plan.grid_x, plan.grid_y)), res
+
+
+def test_zero_area_triangles_are_refused_or_follow_the_rule():
+    """A triangle of three colinear nodes makes matplotlib's trapezoid map invalid (overlapping edges) and its plane fit take
+    the pseudo-inverse branch.  MeshPlan refuses such a mesh by default; with allow_degenerate=True the ids follow the
+    stated rule (brute-force fp64 and exact rational evaluations agree) and a cell located in the degenerate triangle
+    gets its first vertex's value -- the documented divergence from calculate_plane_coefficients."""
+    from fluid_llm_b200.mesh_utils import MeshPlan, to_grid
+    from oracle.exact_locator import exact_find_many
+    pos, tris = tie_mesh()
+    idx = np.arange(25).reshape(5, 5)
+    flat = np.array([[idx[0, 0], idx[2, 0], idx[1, 0]]], dtype=np.int32)          # three nodes on the bottom boundary y = 0
+    bad = np.concatenate([flat, tris]).astype(np.int32)                           # lowest index: wins every tie it takes part in
+    with pytest.raises(ValueError, match="zero area"):
+        MeshPlan(pos, bad, 9)
+    plan = MeshPlan(pos, bad, 9, "1.26", allow_degenerate=True)
+    assert plan.n_degenerate == 1
+    triang = mpl_tri.Triangulation(pos[:, 0], pos[:, 1], bad)
+    rule = mpl_tri.rule_find_many(triang, plan.grid_x, plan.grid_y, bucketed=False)
+    assert np.array_equal(plan.tri_index, rule)
+    assert np.array_equal(plan.tri_index, exact_find_many(pos, bad, plan.grid_x, plan.grid_y))
+    z = np.linspace(1.0, 2.0, 25).astype(np.float32)
+    d, m = to_grid(z, plan.grid_x, plan.grid_y, plan, plan.tri_index)
+    d_o, m_o = P.to_grid(z, plan.grid_x, plan.grid_y, triang, rule)
+    in_flat = plan.tri_index == 0
+    assert np.array_equal(m, m_o) and np.array_equal(d[~in_flat], d_o[~in_flat])
+    assert np.all(d[in_flat] == z[flat[0, 0]])                                     # first vertex's value
+
+
+def test_to_grid_refuses_a_foreign_tri_index():
+    from fluid_llm_b200.mesh_utils import get_mesh_interpolation, to_grid
+    tr = trajectory("cylinder")
+    triang, tri_index, gx, gy = get_mesh_interpolation(tr["mesh_pos"], tr["cells"], 238)
+    val = tr["pressure"][0][:, 0]
+    to_grid(val, gx, gy, triang, tri_index.copy())                                  # an equal copy is fine
+    other = tri_index.copy()
+    other[10, 10] = (other[10, 10] + 1) % triang.n_cells
+    with pytest.raises(ValueError, match="tri_index differs"):
+        to_grid(val, gx, gy, triang, other)

@@ -243,3 +243,57 @@ def test_dynamic_synth_frames_are_valid_triangulations():
         pos = tr["mesh_pos"][t]
         triang = mpl_tri.Triangulation(pos[:, 0], pos[:, 1], triangles=tr["cells"][t])
         assert np.array_equal(triang.get_trifinder()(gx, gy), mpl_tri.rule_find_many(triang, gx, gy))
+
+
+def test_exact_rational_locator_agrees_with_both_fp64_locators():
+    """Third witness for the matplotlib layer (restated, never executed): the stated tie-break rule in exact rational
+    arithmetic == the trapezoid map == the brute-force fp64 rule, on the hand-built tie mesh (every grid point on a vertex,
+    an edge or in a hole) and on the boundary rows / columns of the data-set shaped meshes (grid points exactly on
+    boundary edges) plus a strided interior sample."""
+    from helpers import tie_mesh, trajectory
+    from oracle import mpl_tri
+    from oracle.exact_locator import exact_find_many
+    pos, tris = tie_mesh()
+    for res in (9, 5, 17, 33):
+        triang, tri_o, gx, gy = P.get_mesh_interpolation(pos, tris, res, "1.26")
+        e = exact_find_many(pos, tris, gx, gy)
+        assert np.array_equal(e, tri_o), res
+        assert np.array_equal(e, mpl_tri.rule_find_many(triang, gx, gy, bucketed=False)), res
+    for kind in ("cylinder", "airfoil", "eagle"):
+        tr = trajectory(kind)
+        pos, faces = tr["mesh_pos"], tr["cells"]
+        if kind == "airfoil":
+            _, pos, faces = P.airfoil_crop(pos, faces)
+        for sem in ("1.26", "2.x"):
+            triang, tri_o, gx, gy = P.get_mesh_interpolation(pos, faces, 238, sem)
+            sel = np.zeros(gx.shape, dtype=bool)
+            sel[[0, -1], :] = True
+            sel[:, [0, -1]] = True
+            sel[::17, ::13] = True
+            e = exact_find_many(pos, faces, gx[sel], gy[sel])
+            assert np.array_equal(e, tri_o[sel]), (kind, sem)
+            assert np.array_equal(e, mpl_tri.rule_find_many(triang, gx[sel], gy[sel], bucketed=True)), (kind, sem)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="needs /root/reference (development container only)")
+def test_reference_callers_reproduce_the_frozen_fixture_live():
+    """The reference's unmodified `_generate` / `gen_seq` (src/models/model.py:154-233), over the reference's own patch ops,
+    reproduce tests/golden/ref_callers.npz -- the fixture the GPU tests hold the drop-ins against is not stale."""
+    import hashlib
+    import torch
+    from oracle import make_golden, ref_callers
+    g = np.load(os.path.join(GOLDEN, "ref_callers.npz"))
+    R = ref_import.modules()
+    r = make_golden.ROLLOUT
+    props = R["ds_props"].DSProps(Nx_patch=r["Nx"], Ny_patch=r["Ny"], patch_size=(16, 16), seq_len=r["init_len"] + r["n_steps"])
+    Ref = ref_callers.reference_rollout_class(R["utils_model"].img_to_patch, R["utils_model"].patch_to_img)
+    m = Ref()
+    m.ds_props, m.max_ctx_len, m.forward_see_init = props, r["max_ctx_len"], ref_callers.stub_forward(props)
+    init, mask, pos = make_golden.rollout_inputs()
+    with torch.no_grad():
+        all_states, all_diffs = m._generate(init, mask, pos, r["n_steps"])
+        full = torch.cat([init, torch.zeros_like(all_states[:, r["init_len"]:])], dim=1)
+        img_s, img_d = m.gen_seq((full, None, None, mask, pos), r["n_steps"], start_state=r["init_len"])
+    assert np.array_equal(all_states.numpy(), g["ro_all_states"]) and np.array_equal(all_diffs.numpy(), g["ro_all_diffs"])
+    sha = [hashlib.sha256(np.ascontiguousarray(t.numpy()).tobytes()).hexdigest() for t in (img_s, img_d)]
+    assert sha == list(g["ro_img_sha256"])
