@@ -35,6 +35,7 @@ def crop_airfoil_mesh(pos, faces):
 class AirfoilDataset(_GpuFieldDataset):
     """Load a sequence of timesteps of one Airfoil trajectory (airfoil_ds.py:24)."""
     personality = AIRFOIL
+    ingest_airfoil_crop = True       # the ingest workers apply the node crop of _prepare_mesh
 
     def _list_files(self):
         return _natsorted(self._one_per_stem())

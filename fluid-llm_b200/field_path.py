@@ -90,6 +90,9 @@ class DeviceTrajectory:
             self.vel_buf = torch.empty((T, self.vel_stride), dtype=torch.float32, device=dev)
             self.prs_buf = torch.empty((T, self.prs_stride), dtype=torch.float32, device=dev)
             for name, src, dst in (("vel", vel_padded, self.vel_buf), ("prs", prs_padded, self.prs_buf)):
+                if torch.is_tensor(src):                          # already page-locked (ingest.PickleIngest slots)
+                    dst.copy_(src, non_blocking=True)
+                    continue
                 if pinned is not None:
                     h = pinned.get(name, src.shape)
                     h.numpy()[...] = src                      # page cache / disk -> pinned memory

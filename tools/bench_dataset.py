@@ -62,7 +62,28 @@ def main():
         return ds
 
     for d, name in ((d_pkl, "pickle"), (d_fgt, ".fgt  ")):
-        run(fresh(d, cache_size=0, window_loads=False), f"{name} cold (file -> plan -> upload -> kernel per sample)")
+        run(fresh(d, cache_size=0, window_loads=False, ingest_workers=0), f"{name} cold (file -> plan -> upload -> kernel per sample)")
+        if name == "pickle":
+            # the ingest pool: worker processes unpickle ahead into page-locked slots, the parent only copies and launches
+            dsp = fresh(d, cache_size=0, window_loads=False)
+            dsp.ds_get(0, 0)
+
+            def cold_pool(batch):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for i in range(0, len(order), batch):
+                    dsp.prefetch(order[i:i + 4 * batch])              # what a DataLoader's prefetch_factor does
+                    if batch == 1:
+                        dsp.ds_get(*order[i])
+                    else:
+                        dsp.ds_get_many(order[i:i + batch])
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                lab = f"{name} cold, ingest pool ({dsp._ingest.workers} processes), " + ("one sample per call" if batch == 1 else f"batches of {batch}")
+                print(f"{lab:58s} {args.samples / dt:9.1f} samples/s  {args.samples * args.seq_len / dt:10.1f} frames/s  {dt / args.samples * 1e3:8.2f} ms/sample")
+            cold_pool(1)
+            cold_pool(8)
+            dsp._ingest.close()
         if name.strip() == ".fgt":
             dsw = fresh(d, cache_size=0, window_loads=True)
             run(dsw, f"{name} window loads, first pass (12 mesh plans built on the way)")
