@@ -14,6 +14,8 @@ FL_MASK_AWARE_NORM = 2
 FL_NO_NORM = 4
 FL_FORCE_GATHER = 8
 FL_FORCE_STAGED = 16
+FL_FORCE_TILED = 32
+FL_FORCE_RING = 64
 
 
 class FlTraj(ctypes.Structure):

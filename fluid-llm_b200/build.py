@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfluidgrid.so")
-SOURCES = ["fl_api.cu", "fl_locate.cu", "fl_interp.cu", "fl_tiled.cu", "fl_dynamic.cu", "fl_patch.cu", "fl_stats.cu", "fl_embed.cu"]
+SOURCES = ["fl_api.cu", "fl_locate.cu", "fl_interp.cu", "fl_tiled.cu", "fl_ring.cu", "fl_dynamic.cu", "fl_patch.cu", "fl_stats.cu", "fl_embed.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "--use_fast_math=false", "-fmad=true", "-Xcompiler", "-fvisibility=default"]
 

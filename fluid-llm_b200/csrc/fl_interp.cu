@@ -288,7 +288,14 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
         StagedConst sc;
         for (int c = 0; c < 3; ++c) { sc.mean[c] = nc.mean[c]; sc.stdv[c] = nc.stdv[c]; sc.rcp[c] = 1.0f / nc.stdv[c]; }
         sc.fast_div = (flags & FL_NO_NORM) ? 1 : (fli::fast_div_ok(nc.mean, nc.stdv) ? 1 : 0);
-        const int rc = fli::launch_tiled(d_trajs, h_trajs, n_traj, max_frames, n_patches, px, py, sc, flags, st);
+        // the frame-ring kernel (fl_ring.cu) is an experiment that measured slower than the staged kernel on B200
+        // (profiles/README.md): it runs only when asked for (FL_FORCE_RING, or FLUIDGRID_RING=1 in the environment)
+        const char* ring_env = getenv("FLUIDGRID_RING");
+        const bool want_ring = (flags & FL_FORCE_RING) || (ring_env && atoi(ring_env) == 1);
+        int rc = want_ring && !(flags & FL_FORCE_TILED) ? fli::launch_ring(d_trajs, h_trajs, n_traj, max_frames, n_patches, px, py, sc, flags, st) : 1;
+        if (rc == FL_OK) g_last_kernel = "k_interp_patchify_ring";
+        if (rc != 1) return rc;          // 1 = not asked for / no tile plan / frames too large for the ring
+        rc = fli::launch_tiled(d_trajs, h_trajs, n_traj, max_frames, n_patches, px, py, sc, flags, st);
         if (rc == FL_OK) g_last_kernel = "k_interp_patchify_tiled";
         if (rc != 1) return rc;          // 1 = no tile plan / does not fit: fall through
     }

@@ -39,4 +39,8 @@ bool fast_div_ok(const float* mean, const float* stdv);
 int launch_tiled(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int max_frames, int n_patches, int px, int py,
                  const StagedConst& sc, unsigned flags, cudaStream_t st);
 
+// fl_ring.cu: the whole-frame ring kernel for meshes whose frames fit shared memory a few times over; same return convention
+int launch_ring(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int max_frames, int n_patches, int px, int py,
+                const StagedConst& sc, unsigned flags, cudaStream_t st);
+
 }  // namespace fli

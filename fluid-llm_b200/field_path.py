@@ -170,11 +170,13 @@ class TrajBatch:
         self.desc = torch.from_numpy(raw).to(dev)
         self._keep = (trajs, tables)   # keep the device buffers alive
 
-    def run(self, personality: Personality, normalize=True, means=None, stds=None, force_gather=False, force_staged=False):
+    def run(self, personality: Personality, normalize=True, means=None, stds=None, force_gather=False, force_staged=False,
+            force_ring=False):
         """Enqueue the fused kernel on the current stream; returns (states, mask) device tensors."""
         flags = (FL_MASK_AWARE_NORM if personality.mask_aware_norm else 0) | (0 if normalize else FL_NO_NORM)
         flags |= _lib.FL_FORCE_GATHER if force_gather else 0
         flags |= _lib.FL_FORCE_STAGED if force_staged else 0
+        flags |= _lib.FL_FORCE_RING if force_ring else 0          # experimental frame-ring kernel (csrc/fl_ring.cu)
         m = (ctypes.c_float * 3)(*(means if means is not None else personality.means))
         s = (ctypes.c_float * 3)(*(stds if stds is not None else personality.stds))
         tab = self.tab0
@@ -187,13 +189,13 @@ class TrajBatch:
 
 def interp_patchify(traj: DeviceTrajectory, step_num: int, seq_len: int, seq_interval: int, patch_size,
                     personality: Personality, normalize=True, means=None, stds=None, force_gather=False, force_staged=False,
-                    tile_patches=None):
+                    tile_patches=None, force_ring=False):
     """One trajectory, frames step_num, step_num+interval, ... -> (states (T,L,3,px,py) f32,
     mask (T,L,px,py) u8, table)."""
     _lib.require_cuda()
     tab = traj.plan.patch_table(patch_size, personality.crop_patches, personality.flip_y)
     batch = TrajBatch([traj], [tab], [step_num], seq_interval, seq_len, tile_patches=tile_patches)
-    states, mask = batch.run(personality, normalize, means, stds, force_gather, force_staged)
+    states, mask = batch.run(personality, normalize, means, stds, force_gather, force_staged, force_ring)
     return states[0], mask[0], tab
 
 

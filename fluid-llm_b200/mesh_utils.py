@@ -78,11 +78,10 @@ def serpentine_patches(n_bx, n_by):
 
 
 def tile_sizes(n_patches, tp):
-    """Split n_patches into runs of tp (the last one shorter)."""
-    sizes = [tp] * (n_patches // tp)
-    if n_patches % tp:
-        sizes.append(n_patches % tp)
-    return sizes
+    """Split n_patches into ceil(n_patches / tp) runs of nearly equal length (they differ by at most one patch)."""
+    n_tiles = max(1, -(-n_patches // tp))
+    base, extra = divmod(n_patches, n_tiles)
+    return [base + 1] * extra + [base] * (n_tiles - extra)
 
 
 def choose_tile_patches(n_patches, n_nodes, ppx):
@@ -133,6 +132,9 @@ class PatchTable:
         patch_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         tile_of_patch = np.empty(L, dtype=np.int64)
         tile_of_patch[order] = np.repeat(np.arange(n_tiles), sizes)
+        # inside a tile the patches are listed with ascending ids: runs of consecutive ids are contiguous blocks of a frame's
+        # output, which csrc/fl_ring.cu stores with one bulk copy each
+        order = np.concatenate([np.sort(order[patch_off[t]:patch_off[t + 1]]) for t in range(n_tiles)]).astype(order.dtype)
         with (torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()):
             tile_px = torch.from_numpy(tile_of_patch).to(dev).repeat_interleave(ppx)            # tile of every output pixel
             inside = self.idx[:, 3] >= 0

@@ -40,6 +40,9 @@ extern "C" {
 #define FL_NO_NORM 4u         /* normalize=False */
 #define FL_FORCE_GATHER 8u    /* testing: always the gather-from-global kernel */
 #define FL_FORCE_STAGED 16u   /* testing: ignore the tile plan (whole-mesh staged kernel, or the gather kernel) */
+#define FL_FORCE_TILED 32u    /* testing: with a tile plan, always the node-list kernel (fl_tiled.cu) */
+#define FL_FORCE_RING 64u     /* testing: with a tile plan of <= 6 patches (px*py = 256) per tile and frames that fit shared memory a few
+                                 times over, the experimental frame-ring kernel (fl_ring.cu); otherwise ignored */
 
 /* One grid cell of the static per-mesh table (the product's own intermediate; the reference
  * recomputes the plane coefficients of every triangle per channel per frame instead,

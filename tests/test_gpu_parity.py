@@ -11,13 +11,14 @@ from helpers import PATCH, oracle_ds_get, personality_of, tie_mesh, trajectory
 pytestmark = pytest.mark.gpu
 
 
-KERNELS = ["staged", "gather", "tiled"]
+KERNELS = ["staged", "gather", "tiled", "ring"]
 
 
 def _kernel_args(kernel, ppx=256):
-    """interp_patchify / TrajBatch arguments that force one of the three per-step kernels (csrc/fl_interp.cu, fl_tiled.cu)."""
+    """interp_patchify / TrajBatch arguments that force one of the per-step kernels (csrc/fl_interp.cu, fl_tiled.cu, and the
+    experimental fl_ring.cu)."""
     return {"staged": dict(tile_patches=0), "gather": dict(tile_patches=0, force_gather=True),
-            "tiled": dict(tile_patches=14 * 128 // ppx)}[kernel]
+            "tiled": dict(tile_patches=14 * 128 // ppx), "ring": dict(tile_patches=12 * 128 // ppx, force_ring=True)}[kernel]
 
 
 def _same_bits(a, b):
@@ -156,6 +157,7 @@ def test_interp_patchify_matches_oracle(kind, normalize, kernel):
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_interp_patchify_batch_of_meshes(kernel):
     """One launch over several trajectories with different meshes, different start frames."""
+    import fluid_llm_b200
     from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, TrajBatch
     from fluid_llm_b200.mesh_utils import MeshPlan
     trajs, tabs, t0s, want = [], [], [1, 0, 3], []
@@ -167,8 +169,9 @@ def test_interp_patchify_batch_of_meshes(kernel):
         want.append(oracle_ds_get("cylinder", t0, 4, 1, mesh_seed=seed, field_seed=10 + seed)[1])
     ka = _kernel_args(kernel)
     batch = TrajBatch(trajs, tabs, t0s, 1, 4, tile_patches=ka["tile_patches"])
-    assert (batch.tile_plans is not None) == (kernel == "tiled")
-    states, mask = batch.run(CYLINDER, force_gather=ka.get("force_gather", False))
+    assert (batch.tile_plans is not None) == (kernel in ("tiled", "ring"))
+    states, mask = batch.run(CYLINDER, force_gather=ka.get("force_gather", False), force_ring=ka.get("force_ring", False))
+    assert fluid_llm_b200.load().fl_last_interp_kernel().decode() == "k_interp_patchify_" + kernel
     torch.cuda.synchronize()
     for i, ex in enumerate(want):
         assert np.array_equal(states[i].cpu().numpy(), ex["states"])
@@ -252,7 +255,7 @@ def test_nonfinite_node_values_take_the_checked_path(kind):
         assert _same_bits(states.cpu().numpy(), extra["states"]), kernel
 
 
-@pytest.mark.parametrize("kernel", ["staged", "tiled"])
+@pytest.mark.parametrize("kernel", ["staged", "tiled", "ring"])
 def test_long_sequence_many_items(kernel):
     """More frames than one work item holds (several frame groups per unit in the tiled kernel), odd node count (padded
     frame pitch), interval 3."""
@@ -386,7 +389,7 @@ def test_c_abi_called_directly_as_integration_md_shows():
 
 
 @pytest.mark.parametrize("kind,kernel", [("cylinder", "staged"), ("airfoil", "staged"), ("eagle", "staged"), ("cylinder", "gather"),
-                                         ("cylinder", "tiled"), ("airfoil", "tiled"), ("eagle", "tiled")])
+                                         ("cylinder", "tiled"), ("airfoil", "tiled"), ("eagle", "tiled"), ("airfoil", "ring")])
 def test_interp_patchify_writes_stay_inside_the_output_buffers(kind, kernel):
     """Outputs placed inside guarded buffers (TrajBatch(out=...)): the staged and the gather kernel write every element of
     [n_traj, n_frames, L, ...] and nothing around it."""
@@ -409,7 +412,7 @@ def test_interp_patchify_writes_stay_inside_the_output_buffers(kind, kernel):
     mask = mbuf[G:G + n].view(n_traj, T, L, 16, 16)
     ka = _kernel_args(kernel)
     batch = TrajBatch(trajs, [tab, tab], [0, 1], 1, T, out=(states, mask), tile_patches=ka["tile_patches"])
-    batch.run(pers, force_gather=ka.get("force_gather", False))
+    batch.run(pers, force_gather=ka.get("force_gather", False), force_ring=ka.get("force_ring", False))
     torch.cuda.synchronize()
     assert bool((sbuf[:G] == 777.0).all()) and bool((sbuf[-G:] == 777.0).all())
     assert bool((mbuf[:G] == 77).all()) and bool((mbuf[-G:] == 77).all())

@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--tf", default="")
     ap.add_argument("--prod", default="", help="comma-separated FLUIDGRID_PROD_WARPS values (2 or 4)")
+    ap.add_argument("--ring", default="0", help="comma-separated FLUIDGRID_RING values (1: the experimental frame-ring kernel where it fits -- tiles of <= 6 patches --, 0: node-list kernel)")
+    ap.add_argument("--env", default="", help="extra environment for every variant, e.g. FLUIDGRID_RING_D=3,FLUIDGRID_RING_NT=4")
     ap.add_argument("--dbg", default="", help="comma-separated FLUIDGRID_DBG values (development ablations; results are wrong)")
     args = ap.parse_args()
     import torch
@@ -46,8 +48,12 @@ def main():
     tfs = [int(x) for x in args.tf.split(",")] if args.tf else [0]
     dbgs = [int(x) for x in args.dbg.split(",")] if args.dbg else [0]
     prods = [int(x) for x in args.prod.split(",")] if args.prod else [0]
-    for tp, dbg, prod in [(int(x), d, pw) for x in args.tiles.split(",") for d in dbgs for pw in prods]:
+    for kv in filter(None, args.env.split(",")):
+        os.environ[kv.split("=")[0]] = kv.split("=")[1]
+    rings = [int(x) for x in args.ring.split(",")]
+    for tp, dbg, prod, ring in [(int(x), d, pw, rg) for x in args.tiles.split(",") for d in dbgs for pw in prods for rg in rings]:
         os.environ["FLUIDGRID_DBG"] = str(dbg)
+        os.environ["FLUIDGRID_RING"] = str(ring)
         if prod:
             os.environ["FLUIDGRID_PROD_WARPS"] = str(prod)
         else:
@@ -73,7 +79,7 @@ def main():
             if ref is None:
                 ref = chk
             tpl = batch.tile_plans[0] if batch.tile_plans else None
-            print(json.dumps({"workload": args.workload, "tile_patches": tp, "tf_cap": tf, "dbg": dbg, "prod_warps": prod, "n_tiles": tpl.n_tiles if tpl else 0,
+            print(json.dumps({"workload": args.workload, "tile_patches": tp, "tf_cap": tf, "dbg": dbg, "prod_warps": prod, "kernel": fluid_llm_b200.load().fl_last_interp_kernel().decode(), "n_tiles": tpl.n_tiles if tpl else 0,
                               "max_tile_nodes": tpl.max_tile_nodes if tpl else 0, "ms": round(ms, 4),
                               "frames_per_s": round(len(trajs) * w["T"] / ms * 1e3), "roofline_frac": round(algo / ms / 1e6 / peak, 4),
                               "same_bits_as_first": chk == ref}), flush=True)
