@@ -52,8 +52,11 @@ SIGNATURES = {
                                  c_int, POINTER(c_float), POINTER(c_float), c_uint, c_void_p, c_void_p, c_void_p]),
     "fl_patch_to_img": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fl_img_to_patch": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "fl_rollout_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+    "fl_rollout_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_void_p]),
+    "fl_sample_assemble": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "fl_pos_add_ring": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_void_p]),
     "fl_grid2mesh": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                              c_double, c_double, c_void_p]),
     "fl_dyn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -185,6 +185,7 @@ k_gemm_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 __syncwarp();                                   // the previous tile's rows have been consumed
                 s_pos[3 * lane] = (short)p0; s_pos[3 * lane + 1] = (short)p1; s_pos[3 * lane + 2] = (short)p2;
+                __syncwarp();                                   // every lane reads other lanes' rows below
             }
             mb_wait(&tmem_full[buf], (j >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -295,7 +296,51 @@ int launch_gemm(const void* A, const void* B, int M, int N, int K, const Epilogu
     return FL_OK;
 }
 
+
+// out[r] = pre[src(r)] + ((x_emb[p0] + y_emb[p1]) + t_emb[p2]): the positional add of the second GEMM's epilogue on its own, over a
+// ring of cached pre-positional embeddings.  Row r = (b * c + j) * L + l of the output takes state (start + j) % ctx of the ring
+// [ctx][B][L][N].  One thread = 4 columns.
+__global__ void k_pos_add_ring(const float4* __restrict__ pre, const float* __restrict__ x_emb, const float* __restrict__ y_emb,
+                               const float* __restrict__ t_emb, const long long* __restrict__ ids, int max_x, int max_y, int max_t,
+                               float4* __restrict__ out, long rows, int n4, int B, int c, int L, int ctx, int start) {
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= rows * n4) return;
+    const long r = g / n4;
+    const int q = (int)(g - r * n4);
+    const int l = (int)(r % L);
+    const long bj = r / L;
+    const int j = (int)(bj % c), b = (int)(bj / c);
+    const long src = ((long)((start + j) % ctx) * B + b) * L + l;
+    long long p0 = ids[3 * r], p1 = ids[3 * r + 1], p2 = ids[3 * r + 2];
+    p0 = p0 < 0 ? 0 : (p0 >= max_x ? max_x - 1 : p0);
+    p1 = p1 < 0 ? 0 : (p1 >= max_y ? max_y - 1 : p1);
+    p2 = p2 < 0 ? 0 : (p2 >= max_t ? max_t - 1 : p2);
+    const size_t N = (size_t)n4 * 4;
+    const float4 a = __ldg(pre + src * n4 + q);
+    const float4 e0 = __ldg((const float4*)(x_emb + (size_t)p0 * N) + q), e1 = __ldg((const float4*)(y_emb + (size_t)p1 * N) + q),
+                 e2 = __ldg((const float4*)(t_emb + (size_t)p2 * N) + q);
+    fl_stg_stream4(out + g, make_float4(a.x + ((e0.x + e1.x) + e2.x), a.y + ((e0.y + e1.y) + e2.y), a.z + ((e0.z + e1.z) + e2.z),
+                                        a.w + ((e0.w + e1.w) + e2.w)));
+}
+
 }  // namespace
+
+extern "C" int fl_pos_add_ring(const float* d_pre, const float* d_x_emb, const float* d_y_emb, const float* d_t_emb,
+                               const long long* d_pos_ids, int max_x, int max_y, int max_t, float* d_out, int B, int c, int L, int ctx,
+                               int start, int out_dim, void* stream) {
+    FL_REQUIRE(d_pre && d_x_emb && d_y_emb && d_t_emb && d_pos_ids && d_out, FL_E_ARG, "fl_pos_add_ring: null pointer");
+    FL_REQUIRE(B > 0 && L > 0 && ctx > 0 && c > 0 && c <= ctx && start >= 0 && start < ctx && out_dim > 0 && out_dim % 4 == 0 &&
+                   max_x > 0 && max_y > 0 && max_t > 0,
+               FL_E_ARG, "fl_pos_add_ring: bad sizes");
+    FL_REQUIRE(((uintptr_t)d_pre | (uintptr_t)d_out | (uintptr_t)d_x_emb | (uintptr_t)d_y_emb | (uintptr_t)d_t_emb) % 16 == 0, FL_E_ALIGN,
+               "fl_pos_add_ring: buffers must be 16-byte aligned");
+    const long rows = (long)B * c * L, n = rows * (out_dim / 4);
+    k_pos_add_ring<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float4*)d_pre, d_x_emb, d_y_emb, d_t_emb, d_pos_ids,
+                                                                               max_x, max_y, max_t, (float4*)d_out, rows, out_dim / 4, B,
+                                                                               c, L, ctx, start);
+    FL_LAUNCH_CHECK();
+    return FL_OK;
+}
 
 extern "C" int fl_cast_bf16(const float* d_in, void* d_out_bf16, long n, void* stream) {
     FL_REQUIRE(d_in && d_out_bf16 && n > 0 && n % 4 == 0, FL_E_ARG, "fl_cast_bf16: need non-null buffers and n %% 4 == 0");
@@ -316,6 +361,8 @@ extern "C" int fl_patch_embed(const void* d_x_bf16, const void* d_w1_bf16, const
                "fl_patch_embed: dims (%d -> %d -> %d) must be multiples of 64 (K) and 256 (N)", in_dim, hid_dim, out_dim);
     FL_REQUIRE((d_pos_ids == nullptr) || (d_x_emb && d_y_emb && d_t_emb && max_x > 0 && max_y > 0 && max_t > 0), FL_E_ARG,
                "fl_patch_embed: position ids given without embedding tables");
+    FL_REQUIRE(d_pos_ids == nullptr || (max_x <= 32768 && max_y <= 32768 && max_t <= 32768), FL_E_ARG,
+               "fl_patch_embed: positional tables of more than 32768 rows are not supported (ids are staged as 16-bit)");
     FL_REQUIRE(((uintptr_t)d_x_bf16 | (uintptr_t)d_w1_bf16 | (uintptr_t)d_w2_bf16 | (uintptr_t)d_hidden_bf16 | (uintptr_t)d_out) % 16 == 0,
                FL_E_ALIGN, "fl_patch_embed: buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;

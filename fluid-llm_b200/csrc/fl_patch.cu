@@ -10,6 +10,7 @@
 // sides, so every thread copies one 128-bit piece of a row; the destination side is fully
 // coalesced and the source side is read in whole 32-byte sectors.
 #include "fl_common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -68,7 +69,7 @@ __global__ void k_permute_elem(const T* __restrict__ src, T* __restrict__ dst, l
 // patch-side unit of 4 floats: diffs = img gather, zero where mask, next = last + diffs
 __global__ void k_rollout_step(const float4* __restrict__ img, const uchar4* __restrict__ mask,
                                const float4* __restrict__ last, float4* __restrict__ diffs, float4* __restrict__ next,
-                               long total_units, int n_bx, int n_by, int C, int px, int upr) {
+                               uint2* __restrict__ next_bf16, long total_units, int n_bx, int n_by, int C, int px, int upr) {
     long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= total_units) return;
     int ju = (int)(u % upr);
@@ -87,7 +88,33 @@ __global__ void k_rollout_step(const float4* __restrict__ img, const uchar4* __r
     if (m.w) d.w = 0.f;
     float4 l = fl_ldg_stream4(last + u);
     fl_stg_stream4(diffs + u, d);
-    fl_stg_stream4(next + u, make_float4(l.x + d.x, l.y + d.y, l.z + d.z, l.w + d.w));
+    const float4 n = make_float4(l.x + d.x, l.y + d.y, l.z + d.z, l.w + d.w);
+    fl_stg_stream4(next + u, n);
+    if (next_bf16) {     // the same values as tokens for the patch embedding (what `.to(bfloat16)` under autocast would produce)
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(n.x, n.y), hi = __floats2bfloat162_rn(n.z, n.w);
+        next_bf16[u] = make_uint2(*(const unsigned*)&lo, *(const unsigned*)&hi);
+    }
+}
+
+// simple_dataloader.py:93,100: diffs = states[1:] - states[:-1]; masks = mask[1:] repeated over the 3 channels, as bool bytes.
+// One unit = 4 pixels of one (frame, patch): 3 x float4 of two frames in, 3 x float4 + 3 x uchar4 out.
+__global__ void k_sample_assemble(const float4* __restrict__ states, const uchar4* __restrict__ mask, float4* __restrict__ diffs,
+                                  uchar4* __restrict__ mask3, long units, long frame_units /* L * ppx / 4 */, int upp /* ppx / 4 */,
+                                  long frames_out_per_sample, long frames_in_per_sample) {
+    const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;       // over [B][T-1][L][ppx/4]
+    if (u >= units) return;
+    const long fo = u / frame_units, r = u - fo * frame_units;          // output frame (over all samples), unit inside the frame
+    const long b = fo / frames_out_per_sample, t = fo - b * frames_out_per_sample;
+    const long fi = b * frames_in_per_sample + t;                       // states[b, t]; the next frame is fi + 1
+    const long l = r / upp, k = r - l * upp;
+    const uchar4 m = mask[(fi + 1) * frame_units + r];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const long o = ((l * 3 + c) * upp + k);
+        const float4 a = __ldg(states + fi * 3 * frame_units + o), n = __ldg(states + (fi + 1) * 3 * frame_units + o);
+        diffs[fo * 3 * frame_units + o] = make_float4(n.x - a.x, n.y - a.y, n.z - a.z, n.w - a.w);
+        mask3[fo * 3 * frame_units + o] = m;
+    }
 }
 
 // NumPy's npy_floor_dividef (numpy/core/src/npymath/npy_math_internal.h.src), float32 throughout
@@ -174,8 +201,9 @@ extern "C" int fl_img_to_patch(const void* d_img, void* d_patches, int B, int n_
 }
 
 extern "C" int fl_rollout_step(const float* d_pred_img, const uint8_t* d_mask, const float* d_last, float* d_diffs,
-                               float* d_next, int B, int n_bx, int n_by, int C, int px, int py, void* stream) {
+                               float* d_next, void* d_next_bf16, int B, int n_bx, int n_by, int C, int px, int py, void* stream) {
     FL_REQUIRE(d_pred_img && d_mask && d_last && d_diffs && d_next, FL_E_ARG, "fl_rollout_step: null pointer");
+    FL_REQUIRE((uintptr_t)d_next_bf16 % 8 == 0, FL_E_ALIGN, "fl_rollout_step: the bf16 token buffer must be 8-byte aligned");
     FL_REQUIRE(B > 0 && n_bx > 0 && n_by > 0 && C > 0 && px > 0 && py > 0, FL_E_ARG, "fl_rollout_step: sizes must be positive");
     FL_REQUIRE(py % 4 == 0, FL_E_ARG, "fl_rollout_step: patch width %d must be a multiple of 4", py);
     FL_REQUIRE((((uintptr_t)d_pred_img | (uintptr_t)d_last | (uintptr_t)d_diffs | (uintptr_t)d_next) % 16 == 0) &&
@@ -183,8 +211,23 @@ extern "C" int fl_rollout_step(const float* d_pred_img, const uint8_t* d_mask, c
                FL_E_ALIGN, "fl_rollout_step: float buffers must be 16-byte aligned, mask 4-byte aligned");
     long units = (long)B * n_bx * n_by * C * px * py / 4;
     k_rollout_step<<<(unsigned)((units + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        (const float4*)d_pred_img, (const uchar4*)d_mask, (const float4*)d_last, (float4*)d_diffs, (float4*)d_next, units,
-        n_bx, n_by, C, px, py / 4);
+        (const float4*)d_pred_img, (const uchar4*)d_mask, (const float4*)d_last, (float4*)d_diffs, (float4*)d_next,
+        (uint2*)d_next_bf16, units, n_bx, n_by, C, px, py / 4);
+    FL_LAUNCH_CHECK();
+    return FL_OK;
+}
+
+extern "C" int fl_sample_assemble(const float* d_states, const uint8_t* d_mask, int B, int T, int L, int px, int py, float* d_diffs,
+                                  uint8_t* d_mask3, void* stream) {
+    FL_REQUIRE(d_states && d_mask && d_diffs && d_mask3, FL_E_ARG, "fl_sample_assemble: null pointer");
+    FL_REQUIRE(B > 0 && T > 1 && L > 0 && px > 0 && py > 0 && (px * py) % 4 == 0, FL_E_ARG,
+               "fl_sample_assemble: need B > 0, T > 1, L > 0 and px*py a multiple of 4");
+    FL_REQUIRE((((uintptr_t)d_states | (uintptr_t)d_diffs) % 16 == 0) && (((uintptr_t)d_mask | (uintptr_t)d_mask3) % 4 == 0), FL_E_ALIGN,
+               "fl_sample_assemble: float buffers must be 16-byte aligned, masks 4-byte aligned");
+    const int upp = px * py / 4;
+    const long frame_units = (long)L * upp, units = (long)B * (T - 1) * frame_units;
+    k_sample_assemble<<<(unsigned)((units + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)d_states, (const uchar4*)d_mask, (float4*)d_diffs, (uchar4*)d_mask3, units, frame_units, upp, T - 1, T);
     FL_LAUNCH_CHECK();
     return FL_OK;
 }

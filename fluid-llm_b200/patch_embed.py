@@ -46,8 +46,21 @@ class PatchEmbedder:
         return cls(layers[0].weight, layers[0].bias, layers[1].weight, layers[1].bias,
                    pe.x_embeddings.weight, pe.y_embeddings.weight, pe.time_embeddings.weight, device)
 
-    def __call__(self, x, position_ids=None):
-        """x (..., N_patch, 3, H, W) fp32 CUDA, position_ids (..., N_patch, 3) int64 -> (..., N_patch, llm_dim) fp32."""
+    def check_ids(self, position_ids):
+        """nn.Embedding raises IndexError for an id outside its table (input_embeddings.py:18-26 looks the three ids up in
+        nn.Embedding modules); the kernels clamp instead, so the eager call validates first (one device -> host read)."""
+        if self.pos is None:
+            raise ValueError("PatchEmbedder: position_ids given but no positional tables")
+        ids = position_ids.reshape(-1, 3)
+        lo, hi = ids.amin(dim=0).tolist(), ids.amax(dim=0).tolist()
+        for k, name in enumerate(("x", "y", "time")):
+            if lo[k] < 0 or hi[k] >= self.pos[k].shape[0]:
+                raise IndexError(f"PatchEmbedder: {name} position id out of range [0, {self.pos[k].shape[0]}) (found {lo[k]}..{hi[k]})")
+
+    def __call__(self, x, position_ids=None, validate_ids=True, out=None):
+        """x (..., N_patch, 3, H, W) fp32 CUDA, position_ids (..., N_patch, 3) int64 -> (..., N_patch, llm_dim) fp32.
+        validate_ids=False skips the range check of the ids (and its host synchronisation): out-of-range ids are then clamped.
+        `out`: a contiguous fp32 (n_tokens, llm_dim) CUDA tensor to write into instead of a fresh one."""
         if not x.is_cuda:
             raise _lib.FluidGridError("PatchEmbedder: x must be a CUDA tensor")
         lead = x.shape[:-1] if x.shape[-1] == self.in_dim else x.shape[:-3]     # already-flattened patches are accepted too
@@ -64,7 +77,10 @@ class PatchEmbedder:
                 xb = torch.empty((n, self.in_dim), dtype=torch.bfloat16, device=x.device)
                 check(lib.fl_cast_bf16(ptr(xf), ptr(xb), n * self.in_dim, stream_ptr()), "fl_cast_bf16")
             hidden = torch.empty((n, self.hid_dim), dtype=torch.bfloat16, device=x.device)
-            out = torch.empty((n, self.out_dim), dtype=torch.float32, device=x.device)
+            if out is None:
+                out = torch.empty((n, self.out_dim), dtype=torch.float32, device=x.device)
+            elif out.shape != (n, self.out_dim) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
+                raise ValueError("PatchEmbedder: out must be a contiguous float32 (n_tokens, llm_dim) tensor on x's device")
             ids = None
             if position_ids is not None:
                 if self.pos is None:
@@ -72,6 +88,8 @@ class PatchEmbedder:
                 ids = position_ids.reshape(-1, 3).to(torch.int64).contiguous()
                 if ids.shape[0] != n:
                     raise ValueError("PatchEmbedder: position_ids do not match the number of patches")
+                if validate_ids and not torch.cuda.is_current_stream_capturing():
+                    self.check_ids(ids)
             xe, ye, te = self.pos if self.pos is not None else (None, None, None)
             check(lib.fl_patch_embed(ptr(xb), ptr(self.w1), ptr(self.b1), ptr(self.w2), ptr(self.b2), ptr(xe), ptr(ye), ptr(te),
                                      ptr(ids), xe.shape[0] if xe is not None else 0, ye.shape[0] if ye is not None else 0,
@@ -102,20 +120,62 @@ class GraphedPatchEmbed:
             side = torch.cuda.Stream(dev)
             side.wait_stream(cur)
             with torch.cuda.stream(side):                 # warm-up outside the capture (function attributes, allocator)
-                emb(self.x, self.ids)
+                emb(self.x, self.ids, validate_ids=False)
             cur.wait_stream(side)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.out = emb(self.x, self.ids)
+                self.out = emb(self.x, self.ids, validate_ids=False)
 
     def replay(self):
         self.graph.replay()
         return self.out
 
-    def __call__(self, x, position_ids=None):
+    def __call__(self, x, position_ids=None, validate_ids=False):
         self.x.copy_(x.reshape(self.x.shape))
         if self.ids is not None:
             if position_ids is None:
                 raise ValueError("GraphedPatchEmbed: captured with position ids")
+            if validate_ids:
+                self.emb.check_ids(position_ids)
             self.ids.copy_(position_ids.reshape(-1, 3))
         return self.replay()
+
+
+class RolloutEmbedCache:
+    """The embedding side of the autoregressive rollout without re-embedding the whole context every step.
+
+    `src/models/model.py:187-204` feeds the last `max_ctx_len` states through `InputEmbeddings` at every predicted step, with
+    time ids re-based so that the oldest state of the context is t = 0 (`:196-199`).  Of those states only ONE is new; the
+    other rows of bf16(h W2^T + b2) are what they were a step ago and only the positional term moves.  The cache keeps the
+    pre-positional embedding of every state of the context in a ring [ctx, B, L, llm_dim]; a step embeds the new state alone
+    (bf16 tokens straight from `rollout_step(..., tokens_bf16=True)`: no cast kernel) and re-applies the positional add over
+    the ring (`fl_pos_add_ring`).  Results are bit-identical to embedding the concatenated context (tests/test_gpu_embed.py)."""
+
+    def __init__(self, emb: PatchEmbedder, batch: int, n_patch: int, ctx: int):
+        if emb.pos is None:
+            raise ValueError("RolloutEmbedCache needs the positional tables")
+        self.emb, self.B, self.L, self.ctx = emb, int(batch), int(n_patch), int(ctx)
+        dev = emb.device if emb.device.index is not None else torch.device("cuda", torch.cuda.current_device())
+        self.ring = torch.zeros((self.ctx, self.B, self.L, emb.out_dim), dtype=torch.float32, device=dev)
+        self.n = 0            # states in the ring
+        self.head = 0         # slot the next state goes to
+
+    def append(self, state):
+        """state (B, 1, L, 3, px, py) or (B, L, in_dim), fp32 or bf16: embed it (no positional term) into the ring."""
+        x = state.reshape(self.B * self.L, self.emb.in_dim)
+        self.emb(x, None, out=self.ring[self.head].view(self.B * self.L, self.emb.out_dim))
+        self.head = (self.head + 1) % self.ctx
+        self.n = min(self.n + 1, self.ctx)
+
+    def tokens(self, position_ids):
+        """position_ids (B, c, L, 3) int64 with c = states in the ring -> (B, c * L, llm_dim) fp32, oldest state first."""
+        c = self.n
+        ids = position_ids.reshape(self.B, c, self.L, 3).to(torch.int64).contiguous()
+        out = torch.empty((self.B, c, self.L, self.emb.out_dim), dtype=torch.float32, device=self.ring.device)
+        xe, ye, te = self.emb.pos
+        start = (self.head - c) % self.ctx
+        with torch.cuda.device(self.ring.device):
+            check(load().fl_pos_add_ring(ptr(self.ring), ptr(xe), ptr(ye), ptr(te), ptr(ids), xe.shape[0], ye.shape[0], te.shape[0],
+                                         ptr(out), self.B, c, self.L, self.ctx, start, self.emb.out_dim, stream_ptr()),
+                  "fl_pos_add_ring")
+        return out.view(self.B, c * self.L, self.emb.out_dim)

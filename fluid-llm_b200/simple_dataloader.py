@@ -18,6 +18,7 @@ import numpy as np
 import torch
 from torch.utils.data import Dataset
 
+from ._lib import check, load, ptr, stream_ptr
 from .field_path import TrajBatch, CYLINDER, DeviceTrajectory, Personality, interp_patchify
 from .mesh_utils import MeshPlan
 from .traj_store import PinnedStage, TrajectoryFile
@@ -38,6 +39,19 @@ def position_ids(seq_len, n_x_patch, n_y_patch):
     t_idx = arange // n_patch
     ids = np.stack([x_idx, y_idx, t_idx], axis=1).reshape(seq_len - 1, n_patch, 3)
     return torch.from_numpy(ids.astype(np.int64))
+
+
+def sample_assemble(states, mask):
+    """states (B, T, L, 3, px, py) f32, mask (B, T, L, px, py) u8 -> diffs = states[:, 1:] - states[:, :-1] and
+    masks = mask[:, 1:] repeated over the channels as torch.bool (simple_dataloader.py:93,100), one kernel launch."""
+    B, T, L, C, px, py = states.shape
+    diffs = torch.empty((B, T - 1, L, C, px, py), dtype=torch.float32, device=states.device)
+    mask3 = torch.empty((B, T - 1, L, C, px, py), dtype=torch.bool, device=states.device)
+    if T > 1:
+        with torch.cuda.device(states.device):
+            check(load().fl_sample_assemble(ptr(states), ptr(mask), B, T, L, px, py, ptr(diffs), ptr(mask3), stream_ptr()),
+                  "fl_sample_assemble")
+    return diffs, mask3
 
 
 class _GpuFieldDataset(Dataset):
@@ -245,9 +259,8 @@ class _GpuFieldDataset(Dataset):
         traj, local_step = self._load_window(save_file, step_num)
         states, mask, _ = interp_patchify(traj, local_step, self.seq_len, self.seq_interval, self.patch_size,
                                           self.personality, normalize=self.normalize)
-        diffs = states[1:] - states[:-1]                                  # :93
-        masks = mask[1:].unsqueeze(2).repeat(1, 1, 3, 1, 1).bool()         # :100
-        out = (states[:-1], states[1:], diffs, masks, self._get_pos_id().to(states.device))
+        diffs, masks = sample_assemble(states.unsqueeze(0), mask.unsqueeze(0))       # :93, :100 in one launch
+        out = (states[:-1], states[1:], diffs[0], masks[0], self._get_pos_id().to(states.device))
         if self.output_device is not None:
             out = tuple(t.to(self.output_device) for t in out)
         return out
@@ -269,8 +282,7 @@ class _GpuFieldDataset(Dataset):
         tabs = [t.plan.patch_table(self.patch_size, self.personality.crop_patches, self.personality.flip_y) for t in trajs]
         batch = TrajBatch(trajs, tabs, steps, self.seq_interval, self.seq_len)
         states, mask = batch.run(self.personality, self.normalize)     # (B, T, L, 3, px, py), (B, T, L, px, py)
-        diffs = states[:, 1:] - states[:, :-1]
-        masks = mask[:, 1:].unsqueeze(3).repeat(1, 1, 1, 3, 1, 1).bool()
+        diffs, masks = sample_assemble(states, mask)
         pos = self._get_pos_id().to(states.device)
         out = [(states[b, :-1], states[b, 1:], diffs[b], masks[b], pos) for b in range(len(trajs))]
         if self.output_device is not None:

@@ -32,7 +32,7 @@ extern "C" {
 #define FL_E_WORKSPACE (-3)/* workspace too small */
 #define FL_E_ALIGN (-4)    /* pointer not aligned as documented */
 
-#define FL_ABI_VERSION 7
+#define FL_ABI_VERSION 8
 
 /* personality flags of fl_plan_patch_table / fl_interp_patchify */
 #define FL_FLIP_Y 1u          /* airfoil_ds.py:80  -- y axis reversed after padding */
@@ -164,8 +164,16 @@ int fl_img_to_patch(const void* d_img, void* d_patches, int B, int n_bx, int n_b
  * next = last + diffs.  fp32.  d_pred_img [B, C, X, Y], d_mask u8 [B, L, C, px, py],
  * d_last [B, L, C, px, py] -> d_diffs, d_next same shape. */
 int fl_rollout_step(const float* d_pred_img, const uint8_t* d_mask, const float* d_last,
-                    float* d_diffs, float* d_next, int B, int n_bx, int n_by, int C, int px, int py,
+                    float* d_diffs, float* d_next, void* d_next_bf16, int B, int n_bx, int n_by, int C, int px, int py,
                     void* stream);
+/* d_next_bf16 (optional, NULL to skip): d_next rounded to bf16, same layout -- the patch tokens fl_patch_embed takes, so the
+ * rollout needs no separate cast of the new state (src/models/model.py:196-204 re-embeds it under bf16 autocast). */
+/* src/dataloader/simple_dataloader.py:93,100 (airfoil_ds.py:97-101): the sample's derived tensors in one launch.
+ * d_states f32[B, T, L, 3, px, py], d_mask u8[B, T, L, px, py] (the outputs of fl_interp_patchify for B samples of T frames) ->
+ * d_diffs f32[B, T-1, L, 3, px, py] = states[:, 1:] - states[:, :-1] and d_mask3 u8[B, T-1, L, 3, px, py] = mask[:, 1:]
+ * repeated over the three channels (0 / 1 bytes: a torch.bool tensor's storage). */
+int fl_sample_assemble(const float* d_states, const uint8_t* d_mask, int B, int T, int L, int px, int py,
+                       float* d_diffs, uint8_t* d_mask3, void* stream);
 /* eagle/Dataloader/IMG_Eagle.py:93-123 grid2mesh: nearest-cell grid -> node resample.
  * d_grid f32[T, H, W, C] (row 0 = Ymin, flipped inside as the reference does), d_mesh_pos f32[T, N, 2]
  * -> d_out f32[T, N, C].  Extents/steps are the reference's constants unless overridden;
@@ -216,6 +224,15 @@ int fl_stats_merge(const double* d_parts, int n_parts, double* d_out, void* stre
  * d_hidden_bf16 [n_tokens, hid_dim] workspace, d_out fp32 [n_tokens, out_dim].
  * in_dim, hid_dim multiples of 64; hid_dim, out_dim multiples of 256. */
 int fl_cast_bf16(const float* d_in, void* d_out_bf16, long n, void* stream);
+/* The positional add of fl_patch_embed on its own, over a ring of cached pre-positional embeddings (fl_patch_embed with
+ * d_pos_ids = NULL): src/models/model.py:196-199 re-bases the time ids of the whole context at every rollout step, but only ONE
+ * state of the context is new -- the others' bf16(h W2^T + b2) rows are unchanged and only their positional term moves.
+ * d_pre f32[ctx, B, L, out_dim] ring of per-state embeddings; the context is states start, start+1, ... (mod ctx), c of them;
+ * d_pos_ids int64[B, c, L, 3] -> d_out f32[B, c, L, out_dim] = pre + ((x_emb[p0] + y_emb[p1]) + t_emb[p2]), the same
+ * association as the fused epilogue (bit-identical results). */
+int fl_pos_add_ring(const float* d_pre, const float* d_x_emb, const float* d_y_emb, const float* d_t_emb,
+                    const long long* d_pos_ids, int max_x, int max_y, int max_t, float* d_out, int B, int c, int L, int ctx,
+                    int start, int out_dim, void* stream);
 int fl_patch_embed(const void* d_x_bf16, const void* d_w1_bf16, const float* d_b1, const void* d_w2_bf16, const float* d_b2,
                    const float* d_x_emb, const float* d_y_emb, const float* d_t_emb, const long long* d_pos_ids,
                    int max_x, int max_y, int max_t, void* d_hidden_bf16, float* d_out,

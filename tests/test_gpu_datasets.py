@@ -206,3 +206,15 @@ def test_ds_get_many_equals_per_sample_calls(tmp_path):
     for b in range(3):
         for x, y in zip(batch, ds.ds_get(b, 100)):
             assert torch.equal(x[b], y)
+
+
+def test_sample_assemble_equals_the_reference_tensor_ops():
+    """simple_dataloader.py:93,100 in one launch: diffs = states[1:] - states[:-1], masks = mask[1:] x 3 channels as bool."""
+    from fluid_llm_b200.simple_dataloader import sample_assemble
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for B, T, L, px, py in ((1, 10, 60, 16, 16), (3, 4, 7, 16, 8), (2, 2, 5, 16, 16), (2, 1, 5, 16, 16)):
+        states = torch.randn(B, T, L, 3, px, py, device="cuda", generator=g)
+        mask = (torch.rand(B, T, L, px, py, device="cuda", generator=g) < 0.3).to(torch.uint8)
+        diffs, m3 = sample_assemble(states, mask)
+        assert torch.equal(diffs, states[:, 1:] - states[:, :-1])
+        assert m3.dtype == torch.bool and torch.equal(m3, mask[:, 1:].unsqueeze(3).repeat(1, 1, 1, 3, 1, 1).bool())

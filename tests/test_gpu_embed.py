@@ -95,3 +95,41 @@ def test_patch_embed_writes_stay_inside_the_output_buffers(n_tokens):
     ref = torch.nn.functional.leaky_relu((x.float() @ w1.float().T).bfloat16().float(), 0.01).bfloat16()
     y = (ref.float() @ w2.float().T).bfloat16().float()
     torch.testing.assert_close(out[G:-G].view(n_tokens, 768), y, rtol=2e-2, atol=2e-2)
+
+
+def test_rollout_embed_cache_equals_reembedding_the_whole_context():
+    """model.py:187-204: every step re-embeds the last ctx states with time ids re-based to 0.  RolloutEmbedCache embeds only
+    the new state and re-applies the positional add over its ring: same bits as embedding the concatenated context."""
+    from fluid_llm_b200.patch_embed import PatchEmbedder, RolloutEmbedCache
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, L, ctx, d = 3, 60, 4, 768
+    w1, b1 = torch.randn(512, 768, device="cuda", generator=g) * 0.03, torch.randn(512, device="cuda", generator=g) * 0.1
+    w2, b2 = torch.randn(d, 512, device="cuda", generator=g) * 0.04, torch.randn(d, device="cuda", generator=g) * 0.1
+    tabs = [torch.randn(m, d, device="cuda", generator=g) * 0.03 for m in (15, 4, 12)]
+    emb = PatchEmbedder(w1, b1, w2, b2, *tabs)
+    cache = RolloutEmbedCache(emb, B, L, ctx)
+    xs = torch.arange(L, device="cuda") // 4
+    ys = torch.arange(L, device="cuda") % 4
+    states = []
+    for step in range(7):                      # the ring fills up, then wraps
+        s = torch.randn(B, 1, L, 3, 16, 16, device="cuda", generator=g)
+        states.append(s)
+        cache.append(s.bfloat16() if step % 2 else s)            # bf16 tokens and fp32 states give the same embedding
+        c = min(len(states), ctx)
+        ids = torch.stack([xs.expand(B, c, L), ys.expand(B, c, L), torch.arange(c, device="cuda").view(1, c, 1).expand(B, c, L)], dim=-1)
+        got = cache.tokens(ids)
+        want = emb(torch.cat(states[-c:], dim=1), ids).view(B, c * L, d)
+        assert torch.equal(got, want), step
+
+
+def test_position_ids_outside_the_tables_raise_like_nn_embedding():
+    from fluid_llm_b200.patch_embed import PatchEmbedder
+    tabs = [torch.zeros(m, 768) for m in (5, 4, 3)]
+    emb = PatchEmbedder(torch.randn(512, 768), torch.zeros(512), torch.randn(768, 512), torch.zeros(768), *tabs)
+    x = torch.randn(6, 3, 16, 16, device="cuda")
+    ids = torch.zeros(6, 3, dtype=torch.int64, device="cuda")
+    emb(x, ids)
+    ids[2, 1] = 4
+    with pytest.raises(IndexError):
+        emb(x, ids)
+    assert emb(x, ids, validate_ids=False).shape == (6, 768)      # clamped, as the kernels always did

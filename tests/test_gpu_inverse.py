@@ -77,6 +77,8 @@ def test_rollout_step_matches_reference_glue():
     assert torch.equal(diffs, d) and torch.equal(nxt, last + d)         # model.py:210
     want_next, want_d = P.rollout_step(last.cpu().numpy(), pred.cpu().numpy(), mask.cpu().numpy(), PATCH)
     assert np.array_equal(nxt.cpu().numpy(), want_next) and np.array_equal(diffs.cpu().numpy(), want_d)
+    n2, d2, tok = rollout_step(last, pred, mask, props, tokens_bf16=True)       # the same call also emits the embedding's tokens
+    assert torch.equal(n2, nxt) and torch.equal(d2, diffs) and tok.dtype == torch.bfloat16 and torch.equal(tok, nxt.bfloat16())
     with pytest.raises(ValueError):
         rollout_step(last, pred[..., :32], mask, props)
 

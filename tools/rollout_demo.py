@@ -16,7 +16,7 @@ from fluid_llm_b200 import synth
 from fluid_llm_b200.ds_props import DSProps
 from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
 from fluid_llm_b200.mesh_utils import MeshPlan
-from fluid_llm_b200.patch_embed import PatchEmbedder
+from fluid_llm_b200.patch_embed import PatchEmbedder, RolloutEmbedCache
 from fluid_llm_b200.simple_dataloader import position_ids
 from fluid_llm_b200.utils_model import patch_to_img, rollout_step
 
@@ -50,39 +50,47 @@ def main():
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     t_path = t_bb = 0.0
+    cached = "--reembed" not in sys.argv          # default: RolloutEmbedCache (one new state embedded per step)
     buf = [state0]
     g_embed = None
+    cache = RolloutEmbedCache(embed, bs, L, ctx)
+    tok = state0
     all_states = [state0]
     with torch.no_grad():
         for step in range(1, n_steps + 1):
             e0, e1, e2, e3 = ev(), ev(), ev(), ev()
-            seq = torch.cat(buf[-ctx:], dim=1)                                     # (bs, c, L, 3, 16, 16)
-            c = seq.shape[1]
+            c = min(len(buf), ctx)
             ids = pos_all[:c].unsqueeze(0).expand(bs, c, L, 3)                     # time ids re-based to 0 (model.py:196-199)
             e0.record()
-            if c == ctx:                                                           # steady state: fixed shape -> CUDA-graph form
+            if cached:
+                cache.append(tok)                                                  # only the newest state goes through the GEMMs
+                emb = cache.tokens(ids)
+            elif c == ctx:                                                         # steady state: fixed shape -> CUDA-graph form
+                seq = torch.cat(buf[-ctx:], dim=1)                                 # (bs, c, L, 3, 16, 16)
                 if g_embed is None:
                     g_embed = embed.graphed(bs * ctx * L, True, torch.float32)
                     e0.record()
                 emb = g_embed(seq, ids).view(bs, c * L, d)
             else:
-                emb = embed(seq, ids).view(bs, c * L, d)                           # tcgen05 patch embedding
+                emb = embed(torch.cat(buf[-ctx:], dim=1), ids, validate_ids=False).view(bs, c * L, d)      # tcgen05 patch embedding
             e1.record()
             x = torch.cat([bos.expand(bs, 1, d), emb.to(torch.bfloat16)], dim=1)
             h = backbone(inputs_embeds=x).last_hidden_state[:, -L:]                # stock PyTorch backbone
             pred = decoder(h).float().view(bs, 1, L, 3, 16, 16) * 0.05             # diff_scale_factor
             e2.record()
             pred_img = patch_to_img(pred, props)                                   # decoder output is image-shaped in the reference
-            nxt, _ = rollout_step(buf[-1], pred_img, bc, props)                    # model.py:164,206,210 fused
+            nxt, _, tok = rollout_step(buf[-1], pred_img, bc, props, tokens_bf16=True)   # model.py:164,206,210 fused (+ bf16 tokens)
             e3.record()
             torch.cuda.synchronize()
             t_path += e0.elapsed_time(e1) + e2.elapsed_time(e3)
             t_bb += e1.elapsed_time(e2)
             buf.append(nxt)
+            buf = buf[-ctx:]
             all_states.append(nxt)
         imgs = patch_to_img(torch.cat(all_states, dim=1), props)                   # model.py:231
     tokens = min(ctx, n_steps) * L + 1
     print(f"rollout: batch {bs}, {n_steps} steps, context {ctx} states x {L} patches + BOS = {tokens} tokens, output {tuple(imgs.shape)}")
+    print("embedding: " + ("RolloutEmbedCache (new state only + positional add over the ring)" if cached else "whole context re-embedded (graphed)"))
     print(f"per predicted step: data path {t_path / n_steps * 1e3:.1f} us (embed + unpatchify + fused step), "
           f"backbone+decoder (stock PyTorch bf16) {t_bb / n_steps * 1e3:.1f} us -> data path = "
           f"{100 * t_path / (t_path + t_bb):.1f} % of the step")
