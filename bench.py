@@ -414,6 +414,54 @@ def run_extra_workload(name, rank, world, dev, peak):
     return res
 
 
+def dataset_e2e(dev, n_files=8, n_samples=64, seq_len=10):
+    """Samples/s through the reference-facing data set API (`MGNDataset.ds_get` / `ds_get_many`, the calls a DataLoader makes)
+    on the reference's own pickle format: cold = every sample reads its 18 MB pickle (ingest pool unpickles ahead), warm =
+    trajectories resident in HBM.  A few seconds on rank 0."""
+    import pickle
+    import shutil
+    import tempfile
+    from fluid_llm_b200 import synth
+    from fluid_llm_b200.simple_dataloader import MGNDataset
+    tmp = tempfile.mkdtemp(prefix="fluidgrid_bench_ds_")
+    try:
+        for i in range(n_files):
+            with open(os.path.join(tmp, f"save_{i:03d}.pkl"), "wb") as f:
+                pickle.dump(synth.make_trajectory("cylinder", 600, mesh_seed=i, field_seed=100 + i), f)
+        rng = np.random.default_rng(0)
+        order = [(int(rng.integers(n_files)), int(rng.integers(0, 500))) for _ in range(n_samples)]
+        out = {"sample": f"{n_samples} samples of seq_len {seq_len} from {n_files} cylinder-shaped pickles (T=600, 17.9 MB each, page cache warm)",
+               "unit": "samples/s"}
+
+        def timed(fn):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize(dev)
+            return n_samples / (time.perf_counter() - t0)
+        ds = MGNDataset(tmp, RES, PATCH, PATCH, seq_len, mode="valid", device=dev)
+        ds.cache_size = 0                                   # cold: nothing stays resident
+
+        def cold():
+            for i, (fi, step) in enumerate(order):
+                ds.prefetch(order[i:i + 24])                 # what num_workers x prefetch_factor does (utils_model.LookaheadBatchSampler)
+                ds.ds_get(fi, step)
+        ds.ds_get(0, 0)
+        out["pickle_cold_ingest_pool"] = timed(cold)
+        out["ingest_workers"] = ds._ingest.workers if ds._ingest is not None else 0
+        ds._ingest.close()
+        ds = MGNDataset(tmp, RES, PATCH, PATCH, seq_len, mode="valid", device=dev)
+        for i in range(n_files):
+            ds.ds_get(i, 0)
+        out["resident_one_sample_per_call"] = timed(lambda: [ds.ds_get(fi, step) for fi, step in order])
+        out["resident_batches_of_8"] = timed(lambda: [ds.ds_get_many(order[i:i + 8]) for i in range(0, n_samples, 8)])
+        if ds._ingest is not None:
+            ds._ingest.close()
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
@@ -604,6 +652,13 @@ def run_ours(args, w):
                "trifinder_note": "the reference rebuilds triangulation + trapezoid map + find_many on every __getitem__ "
                                  "(simple_dataloader.py:181); for a 10-frame training sample that is this many ms on top of 10 frame-times"}
 
+    ds_e2e = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            ds_e2e = dataset_e2e(dev)
+        except Exception as e:      # never at the cost of the headline line
+            ds_e2e = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -626,6 +681,7 @@ def run_ours(args, w):
                 "locate_one_off": locate,
                 "stats": stats,
                 "workloads": extra,
+                "dataset_e2e": ds_e2e,
                 "clocks": sampler.result()}
         print(json.dumps(line), flush=True)
     if world > 1:

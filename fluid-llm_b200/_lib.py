@@ -40,8 +40,10 @@ SIGNATURES = {
     "fl_locate_workspace_bytes": (c_size_t, [c_int, c_int]),
     "fl_locate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                           c_void_p, c_void_p, c_size_t, c_void_p]),
+    "fl_locate_async": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "fl_plan_patch_table": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint, c_void_p, c_void_p,
-                                    POINTER(c_int), POINTER(c_int), c_void_p]),
+                                    POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p]),
     "fl_interp_patchify": (c_int, [POINTER(FlTraj), c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                    c_uint, c_void_p]),
     "fl_interp_patchify_dev": (c_int, [c_void_p, POINTER(FlTraj), c_int, c_int, c_int, c_int, POINTER(c_float),

@@ -113,14 +113,15 @@ __global__ void k_fill(const TriRange* __restrict__ tri_range_all, int n_cells, 
 
 __global__ void k_locate(const float* __restrict__ pos, const int* __restrict__ tri_v, const float* __restrict__ ax,
                          const float* __restrict__ ay, int nx, int ny, int nby, const int* __restrict__ bin_start,
-                         const int* __restrict__ items, int* __restrict__ tri_index, FlCellIdx* __restrict__ cell_idx,
+                         const int* __restrict__ items, int capacity, int* __restrict__ tri_index, FlCellIdx* __restrict__ cell_idx,
                          FlCellW* __restrict__ cell_w) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nx * ny) return;
     int ix = c / ny, iy = c - ix * ny;
     double qx = (double)ax[ix], qy = (double)ay[iy];
     int b = (ix / BIN) * nby + iy / BIN;
-    int tri = locate_in_bin(pos, tri_v, items, bin_start[b], bin_start[b + 1], qx, qy);
+    // (an item store that overflowed holds the first `capacity` entries only: the asynchronous entry point reports it)
+    int tri = locate_in_bin(pos, tri_v, items, min(bin_start[b], capacity), min(bin_start[b + 1], capacity), qx, qy);
     if (tri_index) tri_index[c] = tri;
     if (cell_idx) {
         FlCellIdx rec{0, 0, 0, -1};
@@ -137,7 +138,7 @@ __global__ void k_locate(const float* __restrict__ pos, const int* __restrict__ 
 __global__ void k_plan_patch_table(const FlCellIdx* __restrict__ cell_idx, const FlCellW* __restrict__ cell_w, int nx,
                                    int ny, int px, int py, int n_bx, int n_by, int crop, int pad_x0, int pad_y0,
                                    int padded_ny, int flip_y, FlCellIdx* __restrict__ out_idx,
-                                   FlCellW* __restrict__ out_w) {
+                                   FlCellW* __restrict__ out_w, const int* __restrict__ node_slot, FlCellIdx* __restrict__ out_idx_slot) {
     int o = blockIdx.x * blockDim.x + threadIdx.x;
     int total = n_bx * n_by * px * py;
     if (o >= total) return;
@@ -151,6 +152,15 @@ __global__ void k_plan_patch_table(const FlCellIdx* __restrict__ cell_idx, const
     if (ix >= 0 && ix < nx && iy >= 0 && iy < ny) { rec = cell_idx[ix * ny + iy]; w = cell_w[ix * ny + iy]; }
     out_idx[o] = rec;
     out_w[o] = w;
+    if (out_idx_slot) {          // the same record with node ids replaced by their shared-memory slots (cells inside the mesh only)
+        if (rec.tri >= 0) { rec.v0 = node_slot[rec.v0]; rec.v1 = node_slot[rec.v1]; rec.v2 = node_slot[rec.v2]; }
+        out_idx_slot[o] = rec;
+    }
+}
+
+__global__ void k_locate_status(const int* __restrict__ flags, int capacity, int* __restrict__ status) {
+    status[0] = flags[0];
+    status[1] = flags[1] > capacity ? flags[1] - capacity : 0;
 }
 
 }  // namespace
@@ -180,36 +190,55 @@ extern "C" size_t fl_locate_workspace_bytes(int n_nodes, int n_cells) {
     return bin_ws_fixed_bytes(1, n_cells, (int)nbins_max) + sizeof(int) * (16 * (size_t)n_cells + 4 * nbins_max) + 256;
 }
 
-extern "C" int fl_locate(const float* d_pos, const int32_t* d_cells, int n_nodes, int n_cells, const float* d_grid_ax,
-                         const float* d_grid_ay, int nx, int ny, int32_t* d_tri_index, FlCellIdx* d_cell_idx,
-                         FlCellW* d_cell_w, void* d_workspace, size_t workspace_bytes, void* stream) {
-    FL_REQUIRE(d_pos && d_cells && d_grid_ax && d_grid_ay && d_workspace, FL_E_ARG, "fl_locate: null pointer");
-    FL_REQUIRE(n_nodes > 0 && n_cells > 0 && nx > 0 && ny > 0, FL_E_ARG, "fl_locate: sizes must be positive");
-    FL_REQUIRE(nx <= 32767 * BIN && ny <= 32767 * BIN, FL_E_ARG, "fl_locate: grid too large");
-    FL_REQUIRE((d_cell_idx == nullptr) == (d_cell_w == nullptr), FL_E_ARG, "fl_locate: d_cell_idx and d_cell_w go together");
-    FL_REQUIRE(((uintptr_t)d_workspace & 255) == 0, FL_E_ALIGN, "fl_locate: workspace must be 256-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
+static int locate_impl(const float* d_pos, const int32_t* d_cells, int n_nodes, int n_cells, const float* d_grid_ax,
+                       const float* d_grid_ay, int nx, int ny, int32_t* d_tri_index, FlCellIdx* d_cell_idx, FlCellW* d_cell_w,
+                       void* d_workspace, size_t workspace_bytes, int32_t* d_status, const char* who, cudaStream_t st) {
+    FL_REQUIRE(d_pos && d_cells && d_grid_ax && d_grid_ay && d_workspace, FL_E_ARG, "%s: null pointer", who);
+    FL_REQUIRE(n_nodes > 0 && n_cells > 0 && nx > 0 && ny > 0, FL_E_ARG, "%s: sizes must be positive", who);
+    FL_REQUIRE(nx <= 32767 * BIN && ny <= 32767 * BIN, FL_E_ARG, "%s: grid too large", who);
+    FL_REQUIRE((d_cell_idx == nullptr) == (d_cell_w == nullptr), FL_E_ARG, "%s: d_cell_idx and d_cell_w go together", who);
+    FL_REQUIRE(((uintptr_t)d_workspace & 255) == 0, FL_E_ALIGN, "%s: workspace must be 256-byte aligned", who);
     BinWs w;
-    FL_REQUIRE(bin_ws_carve(d_workspace, workspace_bytes, 1, n_cells, nx, ny, &w), FL_E_WORKSPACE,
-               "fl_locate: workspace too small (%zu bytes)", workspace_bytes);
+    FL_REQUIRE(bin_ws_carve(d_workspace, workspace_bytes, 1, n_cells, nx, ny, &w), FL_E_WORKSPACE, "%s: workspace too small (%zu bytes)", who,
+               workspace_bytes);
     int rc = bin_frames(d_pos, 0, d_cells, n_nodes, d_grid_ax, d_grid_ay, nx, ny, w, false, st);
     if (rc) return rc;
-    int h_flags[2];
-    FL_CUDA(cudaMemcpyAsync(h_flags, w.flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
-    FL_CUDA(cudaStreamSynchronize(st));  // one-off per mesh: the item count decides whether the workspace fits
-    FL_REQUIRE(h_flags[0] == 0, FL_E_RANGE, "fl_locate: %d triangles index nodes outside 0 <= i < %d", h_flags[0], n_nodes);
-    FL_REQUIRE(h_flags[1] <= w.capacity, FL_E_WORKSPACE, "fl_locate: workspace too small, need %zu more bytes",
-               sizeof(int) * ((size_t)h_flags[1] - (size_t)w.capacity));
+    if (d_status) {
+        k_locate_status<<<1, 1, 0, st>>>(w.flags, w.capacity, d_status);      // no host synchronisation: the caller reads it later
+        FL_LAUNCH_CHECK();
+    } else {
+        int h_flags[2];
+        FL_CUDA(cudaMemcpyAsync(h_flags, w.flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+        FL_CUDA(cudaStreamSynchronize(st));  // one-off per mesh: the item count decides whether the workspace fits
+        FL_REQUIRE(h_flags[0] == 0, FL_E_RANGE, "%s: %d triangles index nodes outside 0 <= i < %d", who, h_flags[0], n_nodes);
+        FL_REQUIRE(h_flags[1] <= w.capacity, FL_E_WORKSPACE, "%s: workspace too small, need %zu more bytes", who,
+                   sizeof(int) * ((size_t)h_flags[1] - (size_t)w.capacity));
+    }
     int n = nx * ny;
-    k_locate<<<(n + 127) / 128, 128, 0, st>>>(d_pos, w.tri_v, d_grid_ax, d_grid_ay, nx, ny, w.nby, w.bin_start, w.items,
+    k_locate<<<(n + 127) / 128, 128, 0, st>>>(d_pos, w.tri_v, d_grid_ax, d_grid_ay, nx, ny, w.nby, w.bin_start, w.items, w.capacity,
                                               d_tri_index, d_cell_idx, d_cell_w);
     FL_LAUNCH_CHECK();
     return FL_OK;
 }
 
+extern "C" int fl_locate(const float* d_pos, const int32_t* d_cells, int n_nodes, int n_cells, const float* d_grid_ax,
+                         const float* d_grid_ay, int nx, int ny, int32_t* d_tri_index, FlCellIdx* d_cell_idx,
+                         FlCellW* d_cell_w, void* d_workspace, size_t workspace_bytes, void* stream) {
+    return locate_impl(d_pos, d_cells, n_nodes, n_cells, d_grid_ax, d_grid_ay, nx, ny, d_tri_index, d_cell_idx, d_cell_w, d_workspace,
+                       workspace_bytes, nullptr, "fl_locate", (cudaStream_t)stream);
+}
+
+extern "C" int fl_locate_async(const float* d_pos, const int32_t* d_cells, int n_nodes, int n_cells, const float* d_grid_ax,
+                               const float* d_grid_ay, int nx, int ny, int32_t* d_tri_index, FlCellIdx* d_cell_idx,
+                               FlCellW* d_cell_w, void* d_workspace, size_t workspace_bytes, int32_t* d_status, void* stream) {
+    FL_REQUIRE(d_status, FL_E_ARG, "fl_locate_async: null status pointer");
+    return locate_impl(d_pos, d_cells, n_nodes, n_cells, d_grid_ax, d_grid_ay, nx, ny, d_tri_index, d_cell_idx, d_cell_w, d_workspace,
+                       workspace_bytes, d_status, "fl_locate_async", (cudaStream_t)stream);
+}
+
 extern "C" int fl_plan_patch_table(const FlCellIdx* d_cell_idx, const FlCellW* d_cell_w, int nx, int ny, int px, int py,
                                    int crop_patches, unsigned flags, FlCellIdx* d_out_idx, FlCellW* d_out_w,
-                                   int* h_n_bx, int* h_n_by, void* stream) {
+                                   int* h_n_bx, int* h_n_by, const int32_t* d_node_slot, FlCellIdx* d_out_idx_slot, void* stream) {
     FL_REQUIRE(nx > 0 && ny > 0 && px > 0 && py > 0 && crop_patches >= 0, FL_E_ARG, "fl_plan_patch_table: bad sizes");
     int pad_x = ((-nx) % px + px) % px, pad_y = ((-ny) % py + py) % py;   // simple_dataloader.py:140-141
     int n_bx = (nx + pad_x) / px - 2 * crop_patches, n_by = (ny + pad_y) / py - 2 * crop_patches;
@@ -217,12 +246,13 @@ extern "C" int fl_plan_patch_table(const FlCellIdx* d_cell_idx, const FlCellW* d
     if (h_n_by) *h_n_by = n_by;
     if (!d_out_idx && !d_out_w) return FL_OK;   // size query
     FL_REQUIRE(d_cell_idx && d_cell_w && d_out_idx && d_out_w, FL_E_ARG, "fl_plan_patch_table: null pointer");
+    FL_REQUIRE((d_node_slot == nullptr) == (d_out_idx_slot == nullptr), FL_E_ARG, "fl_plan_patch_table: d_node_slot and d_out_idx_slot go together");
     FL_REQUIRE(n_bx > 0 && n_by > 0, FL_E_ARG, "fl_plan_patch_table: no patches left after cropping");
     long total = (long)n_bx * n_by * px * py;
     FL_REQUIRE(total < 0x7fffffffL, FL_E_ARG, "fl_plan_patch_table: too many pixels");
     k_plan_patch_table<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         d_cell_idx, d_cell_w, nx, ny, px, py, n_bx, n_by, crop_patches, pad_x / 2, pad_y / 2, ny + pad_y,
-        (flags & FL_FLIP_Y) ? 1 : 0, d_out_idx, d_out_w);
+        (flags & FL_FLIP_Y) ? 1 : 0, d_out_idx, d_out_w, d_node_slot, d_out_idx_slot);
     FL_LAUNCH_CHECK();
     return FL_OK;
 }

@@ -206,12 +206,15 @@ class MeshPlan:
     `x`, `y`, `triangles` are kept (host) because the reference's interpolator checks `z` against
     `triangulation.x.shape` (src/_triinterpolate.py:37-39)."""
 
-    def __init__(self, pos, faces, grid_res=238, numpy_semantics=None, device=None, allow_degenerate=False):
+    def __init__(self, pos, faces, grid_res=238, numpy_semantics=None, device=None, allow_degenerate=False, sync=True):
         """`allow_degenerate`: matplotlib's trapezoid-map trifinder is undefined on triangles of zero area (three colinear
         nodes: their edges overlap, its map builder raises or loops), and its plane fit takes a pseudo-inverse branch there
         (`calculate_plane_coefficients`); the data sets contain none.  By default such input raises ValueError like an
         invalid triangulation does upstream; with allow_degenerate=True the rule locator treats the triangle like any
-        other and a grid point located in it gets the value of the triangle's first vertex (weights 0, 0)."""
+        other and a grid point located in it gets the value of the triangle's first vertex (weights 0, 0).
+        `sync=False` (the data sets' ingest path): nothing in the constructor waits for the GPU -- one pinned upload, the
+        locate kernels with their status word left on the device; call `ready()` before trusting the tables (it re-locates
+        with a larger workspace if the bin store overflowed, and says so)."""
         _lib.require_cuda()
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if dev.index is None:
@@ -252,21 +255,76 @@ class MeshPlan:
         self.nx, self.ny = len(self.ax), len(self.ay)
         dev = self.device
         with torch.cuda.device(dev):
-            self.pos_d = torch.from_numpy(pos32).to(dev)
-            self.cells_d = torch.from_numpy(tri).to(dev)
-            self.ax_d = torch.from_numpy(self.ax).to(dev)
-            self.ay_d = torch.from_numpy(self.ay).to(dev)
             self.n_padded = (self.n_nodes + 3) // 4 * 4
-            self.node_slot_d = torch.from_numpy(morton_slots(pos32, self.n_padded)).to(dev)
+            slots = morton_slots(pos32, self.n_padded)
+            # one pinned pack, one upload: positions | triangles | grid axes | node slots (16-byte aligned pieces)
+            parts = [pos32.reshape(-1).view(np.uint8), tri.reshape(-1).view(np.uint8), np.ascontiguousarray(self.ax).view(np.uint8),
+                     np.ascontiguousarray(self.ay).view(np.uint8), slots.view(np.uint8)]
+            offs, total = [], 0
+            for a in parts:
+                offs.append(total)
+                total += (a.nbytes + 15) // 16 * 16
+            pin = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+            pin_np = pin.numpy()
+            for a, o in zip(parts, offs):
+                pin_np[o:o + a.nbytes] = a
+            pack = torch.empty(total, dtype=torch.uint8, device=dev)
+            pack.copy_(pin, non_blocking=True)
+            self._pin, self._pack = pin, pack           # the pinned source stays alive at least as long as the plan
+
+            def piece(k, dtype, shape):
+                return pack[offs[k]:offs[k] + parts[k].nbytes].view(dtype).view(shape)
+            self.pos_d = piece(0, torch.float32, (self.n_nodes, 2))
+            self.cells_d = piece(1, torch.int32, (self.n_cells, 3))
+            self.ax_d = piece(2, torch.float32, (self.nx,))
+            self.ay_d = piece(3, torch.float32, (self.ny,))
+            self.node_slot_d = piece(4, torch.int32, (self.n_padded,))
             n = self.nx * self.ny
             self.tri_index_d = torch.empty((self.nx, self.ny), dtype=torch.int32, device=dev)
             self.cell_idx_d = torch.empty((n, 4), dtype=torch.int32, device=dev)
             self.cell_w_d = torch.empty((n, 2), dtype=torch.float64, device=dev)
             self._ws_bytes = int(load().fl_locate_workspace_bytes(self.n_nodes, self.n_cells))
             self._tri_index_host = None
-            self.locate()
+            self._status = None
+            if sync:
+                self.locate()
+            else:
+                self._locate_async()
         self._tables = {}
         self._tri_index_host = None
+
+    def _locate_async(self):
+        """fl_locate_async on the current stream + the status word on its way to pinned memory; `ready()` reads it."""
+        lib = load()
+        with torch.cuda.device(self.device):
+            self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=self.device)
+            st_d = torch.empty(2, dtype=torch.int32, device=self.device)
+            check(lib.fl_locate_async(ptr(self.pos_d), ptr(self.cells_d), self.n_nodes, self.n_cells, ptr(self.ax_d), ptr(self.ay_d),
+                                      self.nx, self.ny, ptr(self.tri_index_d), ptr(self.cell_idx_d), ptr(self.cell_w_d), ptr(self._ws),
+                                      self._ws_bytes, ptr(st_d), stream_ptr()), "fl_locate_async")
+            st_h = torch.empty(2, dtype=torch.int32, pin_memory=True)
+            st_h.copy_(st_d, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._status = (st_h, ev, st_d)
+
+    def ready(self):
+        """True if the asynchronously built tables were fine (or the plan was built synchronously); False if the bin store had
+        overflowed: the tables have then been rebuilt synchronously with a larger workspace and whatever was computed from
+        the old ones must be redone."""
+        if self._status is None:
+            return True
+        st_h, ev, _ = self._status
+        ev.synchronize()
+        self._status = None
+        self._ws = None
+        bad, over = int(st_h[0]), int(st_h[1])
+        if bad == 0 and over == 0:
+            return True
+        self._ws_bytes += 4 * over + 256
+        self._tables = {}
+        self.locate()          # raises for bad node ids, as the synchronous constructor does
+        return False
 
     def locate(self):
         """(Re)run the point-location kernels (fl_locate) on the resident mesh: fills tri_index and the static table.
@@ -296,6 +354,7 @@ class MeshPlan:
     @property
     def tri_index(self):
         """int32 (nx, ny) on the host, what `triang.get_trifinder()(grid_x, grid_y)` returns."""
+        self.ready()
         if self._tri_index_host is None:
             self._tri_index_host = self.tri_index_d.cpu().numpy()
         return self._tri_index_host
@@ -309,20 +368,18 @@ class MeshPlan:
             nbx, nby = ctypes.c_int(0), ctypes.c_int(0)
             flags = FL_FLIP_Y if flip_y else 0
             check(lib.fl_plan_patch_table(None, None, self.nx, self.ny, px, py, key[2], flags, None, None,
-                                          ctypes.byref(nbx), ctypes.byref(nby), None), "fl_plan_patch_table")
+                                          ctypes.byref(nbx), ctypes.byref(nby), None, None, None), "fl_plan_patch_table")
             if nbx.value < 1 or nby.value < 1:
                 raise ValueError(f"no patches left: grid {self.nx}x{self.ny}, patch {px}x{py}, crop {key[2]}")
             total = nbx.value * nby.value * px * py
             with torch.cuda.device(self.device):
                 idx = torch.empty((total, 4), dtype=torch.int32, device=self.device)
+                idx_slot = torch.empty((total, 4), dtype=torch.int32, device=self.device)
                 w = torch.empty((total, 2), dtype=torch.float64, device=self.device)
+                # the table in output-pixel order, and the same with node ids as shared-memory slots, in one launch
                 check(lib.fl_plan_patch_table(ptr(self.cell_idx_d), ptr(self.cell_w_d), self.nx, self.ny, px, py, key[2],
                                               flags, ptr(idx), ptr(w), ctypes.byref(nbx), ctypes.byref(nby),
-                                              stream_ptr()), "fl_plan_patch_table")
-                # node ids -> shared-memory slots for the cells inside the mesh (no boolean indexing: that would synchronise)
-                inside = (idx[:, 3] >= 0).unsqueeze(1)
-                slots = self.node_slot_d[idx[:, :3].clamp(min=0, max=self.n_nodes - 1).long()]
-                idx_slot = torch.cat([torch.where(inside, slots, idx[:, :3]), idx[:, 3:4]], dim=1).contiguous()
+                                              ptr(self.node_slot_d), ptr(idx_slot), stream_ptr()), "fl_plan_patch_table")
             tab = PatchTable(idx, w, nbx.value, nby.value, px, py, idx_slot, self.n_nodes)
             self._tables[key] = tab
         return tab

@@ -151,7 +151,9 @@ class RolloutEmbedCache:
     (bf16 tokens straight from `rollout_step(..., tokens_bf16=True)`: no cast kernel) and re-applies the positional add over
     the ring (`fl_pos_add_ring`).  Results are bit-identical to embedding the concatenated context (tests/test_gpu_embed.py)."""
 
-    def __init__(self, emb: PatchEmbedder, batch: int, n_patch: int, ctx: int):
+    def __init__(self, emb: PatchEmbedder, batch: int, n_patch: int, ctx: int, graphs: bool = False):
+        """graphs=True: once the ring is full, `step(tokens, ids)` replays one CUDA graph per ring position (the two GEMMs of
+        the new state + the positional add: one submission instead of three launches and four tensor-map encodes)."""
         if emb.pos is None:
             raise ValueError("RolloutEmbedCache needs the positional tables")
         self.emb, self.B, self.L, self.ctx = emb, int(batch), int(n_patch), int(ctx)
@@ -159,6 +161,44 @@ class RolloutEmbedCache:
         self.ring = torch.zeros((self.ctx, self.B, self.L, emb.out_dim), dtype=torch.float32, device=dev)
         self.n = 0            # states in the ring
         self.head = 0         # slot the next state goes to
+        self.graphs = {} if graphs else None
+        if graphs:
+            self.g_tok = torch.zeros((self.B * self.L, emb.in_dim), dtype=torch.bfloat16, device=dev)
+            self.g_ids = torch.zeros((self.B, self.ctx, self.L, 3), dtype=torch.int64, device=dev)
+            self.g_out = None
+
+    def step(self, state, position_ids):
+        """append(state) + tokens(position_ids) in one call; with graphs=True and a full ring, one graph replay.
+        The returned tensor is reused by the next replay."""
+        if self.graphs is None or self.n < self.ctx - 1 or state.dtype != torch.bfloat16:
+            self.append(state)
+            return self.tokens(position_ids)
+        self.g_tok.copy_(state.reshape(self.g_tok.shape))
+        self.g_ids.copy_(position_ids.reshape(self.g_ids.shape))
+        g = self.graphs.get(self.head)
+        if g is None:
+            dev = self.ring.device
+            cur = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(cur)
+            n0, h0 = self.n, self.head
+            with torch.cuda.stream(side):                 # warm-up outside the capture
+                self.append(self.g_tok)
+                self.tokens(self.g_ids)
+            cur.wait_stream(side)
+            self.n, self.head = n0, h0
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.append(self.g_tok)
+                out = self.tokens(self.g_ids, out=self.g_out)
+            if self.g_out is None:
+                self.g_out = out
+            self.n, self.head = n0, h0
+            self.graphs[h0] = g
+        g.replay()
+        self.head = (self.head + 1) % self.ctx
+        self.n = min(self.n + 1, self.ctx)
+        return self.g_out.view(self.B, self.ctx * self.L, self.emb.out_dim)
 
     def append(self, state):
         """state (B, 1, L, 3, px, py) or (B, L, in_dim), fp32 or bf16: embed it (no positional term) into the ring."""
@@ -167,11 +207,12 @@ class RolloutEmbedCache:
         self.head = (self.head + 1) % self.ctx
         self.n = min(self.n + 1, self.ctx)
 
-    def tokens(self, position_ids):
+    def tokens(self, position_ids, out=None):
         """position_ids (B, c, L, 3) int64 with c = states in the ring -> (B, c * L, llm_dim) fp32, oldest state first."""
         c = self.n
         ids = position_ids.reshape(self.B, c, self.L, 3).to(torch.int64).contiguous()
-        out = torch.empty((self.B, c, self.L, self.emb.out_dim), dtype=torch.float32, device=self.ring.device)
+        if out is None:
+            out = torch.empty((self.B, c, self.L, self.emb.out_dim), dtype=torch.float32, device=self.ring.device)
         xe, ye, te = self.emb.pos
         start = (self.head - c) % self.ctx
         with torch.cuda.device(self.ring.device):

@@ -60,7 +60,7 @@ class _GpuFieldDataset(Dataset):
     personality: Personality = CYLINDER
     cache_size = 4096          # trajectories kept resident on the device (plan + node fields), at most ...
     cache_fraction = 0.25      # ... this fraction of the device's memory (a 1000-trajectory MGN data set is ~18 GB of 180)
-    ingest_workers = None      # processes that unpickle ahead of the GPU (None: min(8, cores - 1); 0: unpickle in-process)
+    ingest_workers = None      # processes that unpickle ahead of the GPU (None: min(12, cores - 2); 0: unpickle in-process)
     ingest_airfoil_crop = False
     plan_cache_size = 256   # mesh plans kept resident (static tables, ~1 MB each) for window loads from .fgt files
     window_loads = True     # .fgt file not resident: read and upload only the time steps the sample needs
@@ -90,6 +90,8 @@ class _GpuFieldDataset(Dataset):
         self.numpy_semantics = numpy_semantics
         self._cache = OrderedDict()
         self._cache_bytes = 0
+        self._unverified = []
+        self.ingest_times = {"wait": 0.0, "plan": 0.0, "upload": 0.0, "n": 0}
         self._ingest = None
         self._uploads = []         # (event, release) of ingest slots whose host -> device copies are still in flight
         self._plans = OrderedDict()
@@ -143,16 +145,23 @@ class _GpuFieldDataset(Dataset):
                        "velocity": np.asarray(tf.array("velocity"))[:, :2 * n].reshape(tf.n_steps, n, 2),
                        "pressure": np.asarray(tf.array("pressure"))[:, :n, None]}
                 pos, faces, vel, prs = self._prepare_mesh(raw)
-                plan = MeshPlan(pos, faces, self.resolution, self.numpy_semantics, self.device)
+                plan = self._new_plan(pos, faces)
                 traj = DeviceTrajectory(vel, prs, plan)
             else:
-                plan = MeshPlan(tf.mesh_pos, tf.cells, self.resolution, self.numpy_semantics, self.device)
+                plan = self._new_plan(tf.mesh_pos, tf.cells)
                 traj = tf.to_device(plan, pinned=self._pinned)
         elif self._ingest_pool() is not None:
             # a worker process unpickled (and cropped) it into a page-locked slot: only the copies are issued here
+            import time as _time
+            t0 = _time.perf_counter()
             pos, faces, vel, prs, release = self._ingest.take(path)
-            plan = MeshPlan(pos, faces, self.resolution, self.numpy_semantics, self.device)
+            t1 = _time.perf_counter()
+            plan = self._new_plan(pos, faces)
+            t2 = _time.perf_counter()
             traj = DeviceTrajectory.from_padded(vel, prs, plan)
+            t3 = _time.perf_counter()
+            tt = self.ingest_times                 # seconds spent waiting for the pool / building the mesh plan / issuing the upload
+            tt["wait"] += t1 - t0; tt["plan"] += t2 - t1; tt["upload"] += t3 - t2; tt["n"] += 1
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(plan.device))
             self._uploads.append((ev, release))
@@ -161,7 +170,7 @@ class _GpuFieldDataset(Dataset):
             with open(path, 'rb') as f:
                 save_data = pickle.load(f)
             pos, faces, vel, prs = self._prepare_mesh(save_data)
-            plan = MeshPlan(pos, faces, self.resolution, self.numpy_semantics, self.device)
+            plan = self._new_plan(pos, faces)
             traj = DeviceTrajectory(vel, prs, plan)
         self._cache[key] = traj
         self._cache_bytes += self._traj_bytes(traj)
@@ -172,6 +181,22 @@ class _GpuFieldDataset(Dataset):
             _, old = self._cache.popitem(last=False)
             self._cache_bytes -= self._traj_bytes(old)
         return traj
+
+    def _new_plan(self, pos, faces):
+        """A mesh plan built without waiting for the GPU (MeshPlan(sync=False)); `_verify_plans` checks it before the sample
+        that used it is handed out."""
+        plan = MeshPlan(pos, faces, self.resolution, self.numpy_semantics, self.device, sync=False)
+        self._unverified.append(plan)
+        return plan
+
+    def _verify_plans(self):
+        """-> True if every plan built since the last call was fine; False if one had to be rebuilt (bin store overflow on a
+        very uneven mesh): the caller recomputes its sample from the rebuilt tables."""
+        ok = True
+        for plan in self._unverified:
+            ok = plan.ready() and ok
+        self._unverified = []
+        return ok
 
     @staticmethod
     def _traj_bytes(traj):
@@ -203,7 +228,7 @@ class _GpuFieldDataset(Dataset):
     def prefetch(self, requests):
         """Start loading the pickles of upcoming samples -- [(save_file or index, step_num), ...] or file names / indices --
         in the ingest pool; resident trajectories and .fgt files need nothing.  Returns at once."""
-        if self._ingest_pool() is None:
+        if self.ingest_workers == 0:
             return
         paths = []
         for r in requests:
@@ -213,7 +238,7 @@ class _GpuFieldDataset(Dataset):
             path = f"{self.load_dir}/{f}"
             if path.endswith('.pkl') and (path, os.path.getmtime(path)) not in self._cache and path not in paths:
                 paths.append(path)
-        if paths:
+        if paths and self._ingest_pool() is not None:          # (the pool is only started once a pickle has to be read)
             self._ingest.submit(paths)
 
     def _load_window(self, save_file, step_num):
@@ -230,7 +255,7 @@ class _GpuFieldDataset(Dataset):
             return self._load_step(save_file), step_num            # needs the node crop: whole-trajectory route
         plan = self._plans.get(key)
         if plan is None:
-            plan = MeshPlan(tf.mesh_pos, tf.cells, self.resolution, self.numpy_semantics, self.device)
+            plan = self._new_plan(tf.mesh_pos, tf.cells)
             self._plans[key] = plan
             while len(self._plans) > self.plan_cache_size:
                 self._plans.popitem(last=False)
@@ -260,6 +285,8 @@ class _GpuFieldDataset(Dataset):
         states, mask, _ = interp_patchify(traj, local_step, self.seq_len, self.seq_interval, self.patch_size,
                                           self.personality, normalize=self.normalize)
         diffs, masks = sample_assemble(states.unsqueeze(0), mask.unsqueeze(0))       # :93, :100 in one launch
+        if not self._verify_plans():            # (everything above is enqueued by now: this wait overlaps the GPU work)
+            return self.ds_get(save_file, step_num)
         out = (states[:-1], states[1:], diffs[0], masks[0], self._get_pos_id().to(states.device))
         if self.output_device is not None:
             out = tuple(t.to(self.output_device) for t in out)
@@ -283,6 +310,8 @@ class _GpuFieldDataset(Dataset):
         batch = TrajBatch(trajs, tabs, steps, self.seq_interval, self.seq_len)
         states, mask = batch.run(self.personality, self.normalize)     # (B, T, L, 3, px, py), (B, T, L, px, py)
         diffs, masks = sample_assemble(states, mask)
+        if not self._verify_plans():
+            return self.ds_get_many(requests)
         pos = self._get_pos_id().to(states.device)
         out = [(states[b, :-1], states[b, 1:], diffs[b], masks[b], pos) for b in range(len(trajs))]
         if self.output_device is not None:

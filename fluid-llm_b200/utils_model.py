@@ -117,6 +117,32 @@ def rollout_step(last_state, pred_diff_img, mask, ds_props: DSProps, tokens_bf16
     return (nxt, diffs, tok) if tokens_bf16 else (nxt, diffs)
 
 
+class LookaheadBatchSampler(torch.utils.data.Sampler):
+    """A batch sampler that tells the data set which files the NEXT batches will need, so that its ingest pool
+    (`ingest.PickleIngest`) unpickles them while the current batch is on the GPU -- what the reference gets from
+    `num_workers` processes with `prefetch_factor` batches each (src/utils_model.py:35-36), without moving the CUDA work out of
+    the calling process.  Same index order as `BatchSampler(sampler, batch_size, drop_last)`."""
+
+    def __init__(self, sampler, batch_size, drop_last, dataset, lookahead=2):
+        self.sampler, self.batch_size, self.drop_last = sampler, int(batch_size), bool(drop_last)
+        self.dataset, self.lookahead = dataset, int(lookahead)
+
+    def __len__(self):
+        n = len(self.sampler)
+        return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
+
+    def __iter__(self):
+        idx = list(self.sampler)
+        batches = [idx[i:i + self.batch_size] for i in range(0, len(idx), self.batch_size)]
+        if batches and self.drop_last and len(batches[-1]) < self.batch_size:
+            batches.pop()
+        for i, b in enumerate(batches):
+            ahead = [j for nb in batches[i:i + 1 + self.lookahead] for j in nb]
+            if hasattr(self.dataset, "prefetch"):
+                self.dataset.prefetch(ahead)
+            yield b
+
+
 def get_data_loader(config, mode="train", device=None, numpy_semantics=None):
     """utils_model.py:9-45: config -> (DataLoader, DSProps), same dataset selection, same DSProps.
 
@@ -136,6 +162,9 @@ def get_data_loader(config, mode="train", device=None, numpy_semantics=None):
         ds = AirfoilDataset(**kw)
     else:
         raise ValueError(f"Invalid dataset {ds_name}")
-    dl = DataLoader(ds, batch_size=config['batch_size'], num_workers=0, shuffle=(mode == 'train'))
+    from torch.utils.data import RandomSampler, SequentialSampler
+    sampler = RandomSampler(ds) if mode == 'train' else SequentialSampler(ds)          # shuffle=(mode == 'train'), :36
+    dl = DataLoader(ds, num_workers=0,
+                    batch_sampler=LookaheadBatchSampler(sampler, config['batch_size'], False, ds, config.get('prefetch_batches', 2)))
     ds_props = DSProps(Nx_patch=ds.N_x_patch, Ny_patch=ds.N_y_patch, patch_size=ds.patch_size, seq_len=ds.seq_len - 1)
     return dl, ds_props

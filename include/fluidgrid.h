@@ -77,15 +77,26 @@ int fl_locate(const float* d_pos, const int32_t* d_cells, int n_nodes, int n_cel
               int32_t* d_tri_index, FlCellIdx* d_cell_idx, FlCellW* d_cell_w,
               void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* The same without host synchronisation: d_status i32[2] is written on the stream -- [0] = triangles with a node id outside
+ * 0 <= i < n_nodes (they are left out), [1] = bin entries that did not fit the workspace (0 = it fitted).  The results are valid
+ * iff both are 0; otherwise call again with fl_locate (bad ids raise there) or a workspace larger by 4 * status[1] bytes. */
+int fl_locate_async(const float* d_pos, const int32_t* d_cells, int n_nodes, int n_cells,
+                    const float* d_grid_ax, const float* d_grid_ay, int nx, int ny,
+                    int32_t* d_tri_index, FlCellIdx* d_cell_idx, FlCellW* d_cell_w,
+                    void* d_workspace, size_t workspace_bytes, int32_t* d_status, void* stream);
+
 /* Re-order the static table into output-pixel order for one dataset personality:
  * pad to multiples of the patch (simple_dataloader.py:137-152), optional y flip
  * (airfoil_ds.py:80), optional removal of `crop` outer rings of patches (airfoil_ds.py:132-133).
  * Output index = (l*px + i)*py + j with l = bx*n_by + by (F.unfold order,
  * simple_dataloader.py:131).  Padded pixels get tri = -1.
- * d_out_idx/d_out_w: [n_bx*n_by*px*py].  n_bx/n_by are returned through out pointers (host). */
+ * d_out_idx/d_out_w: [n_bx*n_by*px*py].  n_bx/n_by are returned through out pointers (host).
+ * d_node_slot i32[n_nodes] + d_out_idx_slot (optional, both or neither): also emit the table with node ids replaced by
+ * d_node_slot[id] (FlTraj::d_idx_slot). */
 int fl_plan_patch_table(const FlCellIdx* d_cell_idx, const FlCellW* d_cell_w, int nx, int ny,
                         int px, int py, int crop_patches, unsigned flags,
-                        FlCellIdx* d_out_idx, FlCellW* d_out_w, int* h_n_bx, int* h_n_by, void* stream);
+                        FlCellIdx* d_out_idx, FlCellW* d_out_w, int* h_n_bx, int* h_n_by,
+                        const int32_t* d_node_slot, FlCellIdx* d_out_idx_slot, void* stream);
 
 /* ---- per step: gather -> fp64 FMA -> fp32 -> mask -> normalise -> patchify --------------------
  * Replaces the body of  simple_dataloader.py:72-121,166-216 / airfoil_ds.py:71-122,189-244

@@ -120,6 +120,18 @@ def test_rollout_embed_cache_equals_reembedding_the_whole_context():
         got = cache.tokens(ids)
         want = emb(torch.cat(states[-c:], dim=1), ids).view(B, c * L, d)
         assert torch.equal(got, want), step
+    # the graphed form: one replay per step once the ring is full, a graph per ring position
+    gc = RolloutEmbedCache(emb, B, L, ctx, graphs=True)
+    hist = []
+    for step in range(11):
+        s = torch.randn(B, 1, L, 3, 16, 16, device="cuda", generator=g).bfloat16()
+        hist.append(s)
+        c = min(len(hist), ctx)
+        ids = torch.stack([xs.expand(B, c, L), ys.expand(B, c, L), torch.arange(c, device="cuda").view(1, c, 1).expand(B, c, L)], dim=-1)
+        got = gc.step(s, ids)
+        want = emb(torch.cat(hist[-c:], dim=1), ids).view(B, c * L, d)
+        assert torch.equal(got, want), step
+    assert len(gc.graphs) == ctx
 
 
 def test_position_ids_outside_the_tables_raise_like_nn_embedding():

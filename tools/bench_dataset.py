@@ -20,7 +20,7 @@ import torch
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--files", type=int, default=12)
-    ap.add_argument("--samples", type=int, default=48)
+    ap.add_argument("--samples", type=int, default=96)
     ap.add_argument("--seq-len", type=int, default=10)
     args = ap.parse_args()
     from fluid_llm_b200 import synth
@@ -72,7 +72,7 @@ def main():
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 for i in range(0, len(order), batch):
-                    dsp.prefetch(order[i:i + 4 * batch])              # what a DataLoader's prefetch_factor does
+                    dsp.prefetch(order[i:i + max(3 * batch, 2 * dsp._ingest.workers)])      # what num_workers x prefetch_factor does (utils_model.LookaheadBatchSampler)
                     if batch == 1:
                         dsp.ds_get(*order[i])
                     else:
@@ -81,6 +81,11 @@ def main():
                 dt = time.perf_counter() - t0
                 lab = f"{name} cold, ingest pool ({dsp._ingest.workers} processes), " + ("one sample per call" if batch == 1 else f"batches of {batch}")
                 print(f"{lab:58s} {args.samples / dt:9.1f} samples/s  {args.samples * args.seq_len / dt:10.1f} frames/s  {dt / args.samples * 1e3:8.2f} ms/sample")
+                tt = dsp.ingest_times
+                print(f"    parent, per sample: waiting for the pool {tt['wait'] / tt['n'] * 1e3:.2f} ms, mesh plan {tt['plan'] / tt['n'] * 1e3:.2f} ms, "
+                      f"upload calls {tt['upload'] / tt['n'] * 1e3:.2f} ms (of {dt / args.samples * 1e3:.2f} ms)")
+                for k in tt:
+                    tt[k] = 0
             cold_pool(1)
             cold_pool(8)
             dsp._ingest.close()

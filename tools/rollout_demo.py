@@ -53,7 +53,7 @@ def main():
     cached = "--reembed" not in sys.argv          # default: RolloutEmbedCache (one new state embedded per step)
     buf = [state0]
     g_embed = None
-    cache = RolloutEmbedCache(embed, bs, L, ctx)
+    cache = RolloutEmbedCache(embed, bs, L, ctx, graphs=True)
     tok = state0
     all_states = [state0]
     with torch.no_grad():
@@ -63,8 +63,7 @@ def main():
             ids = pos_all[:c].unsqueeze(0).expand(bs, c, L, 3)                     # time ids re-based to 0 (model.py:196-199)
             e0.record()
             if cached:
-                cache.append(tok)                                                  # only the newest state goes through the GEMMs
-                emb = cache.tokens(ids)
+                emb = cache.step(tok, ids)                                         # only the newest state goes through the GEMMs
             elif c == ctx:                                                         # steady state: fixed shape -> CUDA-graph form
                 seq = torch.cat(buf[-ctx:], dim=1)                                 # (bs, c, L, 3, 16, 16)
                 if g_embed is None:
