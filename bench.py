@@ -421,6 +421,7 @@ def dataset_e2e(dev, n_files=8, n_samples=64, seq_len=10):
     import pickle
     import shutil
     import tempfile
+    import torch
     from fluid_llm_b200 import synth
     from fluid_llm_b200.simple_dataloader import MGNDataset
     tmp = tempfile.mkdtemp(prefix="fluidgrid_bench_ds_")

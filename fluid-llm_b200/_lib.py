@@ -59,6 +59,7 @@ SIGNATURES = {
     "fl_sample_assemble": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "fl_pos_add_ring": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_void_p]),
+    "fl_affine_channels": (c_int, [c_void_p, c_void_p, ctypes.c_long, c_int, POINTER(c_float), POINTER(c_float), c_int, c_void_p]),
     "fl_grid2mesh": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                              c_double, c_double, c_void_p]),
     "fl_dyn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -176,6 +176,31 @@ int permute(const void* src, void* dst, int B, int n_bx, int n_by, int C, int px
     return FL_OK;
 }
 
+// channel-last affine map of the pre-gridded EAGLE states (eagle/Dataloader/IMG_Eagle.py:72-90): mode 0 = (x - mean) / std,
+// mode 1 = x * std + mean, each as two separately rounded fp32 operations like the reference's torch expressions
+struct AffineC { float mean[8], stdv[8]; };
+__global__ void k_affine_channels(const float* __restrict__ in, float* __restrict__ out, long n, int C, AffineC k, int mode) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % C);
+    const float x = __ldg(in + i);
+    out[i] = mode == 0 ? __fdiv_rn(__fsub_rn(x, k.mean[c]), k.stdv[c]) : __fadd_rn(__fmul_rn(x, k.stdv[c]), k.mean[c]);
+}
+__global__ void k_affine_channels4(const float4* __restrict__ in, float4* __restrict__ out, long n4, AffineC k, int mode) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 x = fl_ldg_stream4(in + i);
+    float4 y;
+    if (mode == 0) {
+        y = make_float4(__fdiv_rn(__fsub_rn(x.x, k.mean[0]), k.stdv[0]), __fdiv_rn(__fsub_rn(x.y, k.mean[1]), k.stdv[1]),
+                        __fdiv_rn(__fsub_rn(x.z, k.mean[2]), k.stdv[2]), __fdiv_rn(__fsub_rn(x.w, k.mean[3]), k.stdv[3]));
+    } else {
+        y = make_float4(__fadd_rn(__fmul_rn(x.x, k.stdv[0]), k.mean[0]), __fadd_rn(__fmul_rn(x.y, k.stdv[1]), k.mean[1]),
+                        __fadd_rn(__fmul_rn(x.z, k.stdv[2]), k.mean[2]), __fadd_rn(__fmul_rn(x.w, k.stdv[3]), k.mean[3]));
+    }
+    fl_stg_stream4(out + i, y);
+}
+
 int check_perm_args(const char* who, const void* a, const void* b, int B, int n_bx, int n_by, int C, int px, int py, int es) {
     FL_REQUIRE(a && b, FL_E_ARG, "%s: null pointer", who);
     FL_REQUIRE(B > 0 && n_bx > 0 && n_by > 0 && C > 0 && px > 0 && py > 0, FL_E_ARG, "%s: sizes must be positive", who);
@@ -228,6 +253,23 @@ extern "C" int fl_sample_assemble(const float* d_states, const uint8_t* d_mask, 
     const long frame_units = (long)L * upp, units = (long)B * (T - 1) * frame_units;
     k_sample_assemble<<<(unsigned)((units + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const float4*)d_states, (const uchar4*)d_mask, (float4*)d_diffs, (uchar4*)d_mask3, units, frame_units, upp, T - 1, T);
+    FL_LAUNCH_CHECK();
+    return FL_OK;
+}
+
+extern "C" int fl_affine_channels(const float* d_in, float* d_out, long n_values, int C, const float* h_mean, const float* h_std,
+                                  int denormalize, void* stream) {
+    FL_REQUIRE(d_in && d_out && h_mean && h_std, FL_E_ARG, "fl_affine_channels: null pointer");
+    FL_REQUIRE(n_values > 0 && C >= 1 && C <= 8 && n_values % C == 0, FL_E_ARG, "fl_affine_channels: need 1 <= C <= 8 and n_values a multiple of C");
+    AffineC k;
+    for (int c = 0; c < 8; ++c) { k.mean[c] = c < C ? h_mean[c] : 0.f; k.stdv[c] = c < C ? h_std[c] : 1.f; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 4 && ((uintptr_t)d_in | (uintptr_t)d_out) % 16 == 0) {
+        const long n4 = n_values / 4;
+        k_affine_channels4<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const float4*)d_in, (float4*)d_out, n4, k, denormalize ? 1 : 0);
+    } else {
+        k_affine_channels<<<(unsigned)((n_values + 255) / 256), 256, 0, st>>>(d_in, d_out, n_values, C, k, denormalize ? 1 : 0);
+    }
     FL_LAUNCH_CHECK();
     return FL_OK;
 }

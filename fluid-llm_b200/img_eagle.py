@@ -1,18 +1,113 @@
-"""`grid2mesh`: grid -> node nearest-cell resample on the GPU.
+"""The pre-gridded EAGLE consumer on the GPU: `EagleDataset` over `states.npy` and `grid2mesh`.
 
-Mirror of `/root/reference/eagle/Dataloader/IMG_Eagle.py:93-123` (same constants, same float32
-index arithmetic as NumPy 1.26 evaluates it, same row flip and negative-index wrap).  Returns CPU
-tensors like the reference when given NumPy/CPU inputs, device tensors for device inputs.
+Mirror of `/root/reference/eagle/Dataloader/IMG_Eagle.py`: the data set class (`:8-90`: window of the pre-gridded 4-channel
+states, normalised with the fixed mean / std of `:76-77`, pixel-type mask, optional irregular mesh) and `grid2mesh` (`:93-123`:
+same constants, same float32 index arithmetic as NumPy 1.26 evaluates it, same row flip and negative-index wrap).  `grid2mesh`
+returns CPU tensors like the reference when given NumPy/CPU inputs, device tensors for device inputs.
 """
 from __future__ import annotations
 
+import ctypes
+import os
+import random
+
 import numpy as np
 import torch
+from torch.utils.data import Dataset
 
 from . import _lib
 from ._lib import check, load, ptr, stream_ptr
 
 XMIN, XMAX, YMIN, YMAX, LENGTH, HEIGHT = -2.5, 2.5, -1.7, 1.5, 256, 128   # IMG_Eagle.py:95-99
+STATE_MEAN = (-0.0147, 0.2125, -0.5327, 3.7694)                          # IMG_Eagle.py:76,86
+STATE_STD = (1.5943, 1.8824, 6.3553, 9.0565)                             # IMG_Eagle.py:77,87
+
+
+def _affine(state, denormalize):
+    """(state - mean) / std or state * std + mean over the last (4-channel) axis; CUDA tensors go through
+    fl_affine_channels, CPU tensors through the same two fp32 torch operations the reference uses."""
+    if state.shape[-1] != 4:
+        raise RuntimeError(f"shape '[-1, 4]' is invalid for input of size {state.numel()}")      # the reference's reshape(-1, 4)
+    if not state.is_cuda:
+        mean, std = torch.tensor(STATE_MEAN).to(state.device), torch.tensor(STATE_STD).to(state.device)
+        flat = state.reshape(-1, 4)
+        return ((flat * std + mean) if denormalize else ((flat - mean) / std)).reshape(state.shape)
+    x = state.float().contiguous()
+    out = torch.empty_like(x)
+    m, s = (ctypes.c_float * 4)(*STATE_MEAN), (ctypes.c_float * 4)(*STATE_STD)
+    with torch.cuda.device(x.device):
+        check(load().fl_affine_channels(ptr(x), ptr(out), x.numel(), 4, m, s, 1 if denormalize else 0, stream_ptr()),
+              "fl_affine_channels")
+    return out
+
+
+class EagleDataset(Dataset):
+    """IMG_Eagle.py:8-90 with the window's float conversion and normalisation on the GPU: the window of `states.npy` goes from
+    the memory map through pinned memory to the device, one kernel normalises it.  `output_device=None` (default) leaves
+    `'states'` on the GPU for a GPU consumer; `"cpu"` returns the reference's host tensor.  `splits_dir` is where
+    `{mode}.txt` lives (the reference reads `Splits/{mode}.txt` relative to the working directory)."""
+
+    def __init__(self, data_path, mode="test", window_length=990, with_mesh=False, device=None, output_device=None,
+                 splits_dir="Splits"):
+        super().__init__()
+        assert mode in ["train", "test", "valid"]
+        self.window_length = window_length
+        assert window_length <= 990, "window length must be smaller than 990"
+        self.fn = data_path
+        assert os.path.exists(self.fn), f"Path {self.fn} does not exist"
+        self.dataloc = []
+        with open(os.path.join(splits_dir, f"{mode}.txt"), "r") as f:
+            for line in f.readlines():
+                self.dataloc.append(os.path.join(self.fn, line.strip()))
+        self.mode = mode
+        self.length = 990
+        self.with_mesh = with_mesh
+        _lib.require_cuda()
+        self.device = torch.device(device or "cuda")
+        self.output_device = output_device
+        self._pin = None
+
+    def __len__(self):
+        return len(self.dataloc)
+
+    def __getitem__(self, item):
+        # IMG_Eagle.py:39-41: random window in training, fixed start otherwise
+        t = random.randint(1, 990 - self.window_length) if self.window_length != 990 else 1
+        t = 550 if self.mode in ["test", "valid"] and self.window_length != 990 else t
+        states = np.load(os.path.join(self.dataloc[item], "states.npy"), mmap_mode='r')
+        mask = np.load(os.path.join(self.dataloc[item], "pixel_type.npy"), mmap_mode='r')
+        win = states[t:t + self.window_length]
+        if win.dtype == np.float32:
+            if self._pin is None or self._pin.shape != win.shape:
+                self._pin = torch.empty(win.shape, dtype=torch.float32, pin_memory=True)
+            else:
+                torch.cuda.current_stream(self.device).synchronize()      # the previous window's upload has left the buffer
+            self._pin.numpy()[...] = win                                   # page cache -> pinned memory
+            dev_states = self._pin.to(self.device, non_blocking=True)
+        else:
+            dev_states = torch.from_numpy(win.copy()).to(self.device).float()      # `.float()` of the reference, on the device
+        states_n = self.normalize(dev_states)
+        if self.output_device is not None:
+            states_n = states_n.to(self.output_device)
+        output = {'states': states_n,
+                  'mask': mask.copy(),
+                  'example': torch.tensor((int(self.dataloc[item].split("/")[-2]),)), }
+        if self.with_mesh:
+            path = self.dataloc[item].replace("_img", "")
+            assert os.path.exists(path), f"Can not find mesh files in {path}, please check the path in the dataloader"
+            data = np.load(os.path.join(path, 'sim.npz'), mmap_mode='r')
+            sl = slice(t, t + self.window_length)
+            output['mesh_pos'] = data["pointcloud"][sl].copy()
+            output['mesh_velocity'] = np.stack([data['VX'][sl].copy(), data['VY'][sl].copy()], axis=-1)
+            output['mesh_pressure'] = np.stack([data['PS'][sl].copy(), data['PG'][sl].copy()], axis=-1)
+            output['mesh_node_type'] = data['mask'][sl].copy()
+        return output
+
+    def normalize(self, state):
+        return _affine(state, False)
+
+    def denormalize(self, state):
+        return _affine(state, True)
 
 
 def _resample(grid, pos, step_x, step_y, x_min, y_min):

@@ -192,6 +192,12 @@ int fl_sample_assemble(const float* d_states, const uint8_t* d_mask, int B, int 
 int fl_grid2mesh(const float* d_grid, const float* d_mesh_pos, float* d_out, int T, int N, int H, int W, int C,
                  float x_min, float y_min, double step_x, double step_y, void* stream);
 
+/* eagle/Dataloader/IMG_Eagle.py:72-90 (EagleDataset.normalize / denormalize over the pre-gridded states.npy, 4 channels):
+ * channel-last values [..., C], C <= 8; denormalize = 0: (x - mean[c]) / std[c], 1: x * std[c] + mean[c]; every operation
+ * rounded separately in fp32 like the reference's torch expressions.  In place (d_out == d_in) is allowed. */
+int fl_affine_channels(const float* d_in, float* d_out, long n_values, int C, const float* h_mean, const float* h_std,
+                       int denormalize, void* stream);
+
 /* ---- per-frame dynamic meshes --------------------------------------------------------------------
  * True EAGLE trajectories (max/ds_download/eagle.py:123-144: pointcloud[T,N,2], triangles[T,F,3], VX/VY/PS per frame)
  * have a different mesh in every frame, so the chain get_mesh_interpolation -> 3 x to_grid -> _pad -> _patch ->

@@ -324,6 +324,30 @@ def rollout_step(last_state, diff_img, mask, patch_size):
     return (last_state + diffs).astype(last_state.dtype), diffs
 
 
+IMG_EAGLE_MEAN = np.array([-0.0147, 0.2125, -0.5327, 3.7694], dtype=np.float32)      # eagle/Dataloader/IMG_Eagle.py:76,86
+IMG_EAGLE_STD = np.array([1.5943, 1.8824, 6.3553, 9.0565], dtype=np.float32)         # :77,87
+
+
+def img_eagle_normalize(state):
+    """eagle/Dataloader/IMG_Eagle.py:72-80: (state - mean) / std over the 4 channels, float32 throughout."""
+    s = np.asarray(state, dtype=np.float32)
+    return ((s.reshape(-1, 4) - IMG_EAGLE_MEAN) / IMG_EAGLE_STD).astype(np.float32).reshape(s.shape)
+
+
+def img_eagle_denormalize(state):
+    """eagle/Dataloader/IMG_Eagle.py:82-90: state * std + mean (a rounded product, then a rounded sum)."""
+    s = np.asarray(state, dtype=np.float32)
+    return ((s.reshape(-1, 4) * IMG_EAGLE_STD).astype(np.float32) + IMG_EAGLE_MEAN).astype(np.float32).reshape(s.shape)
+
+
+def img_eagle_item(states, pixel_type, window_length, mode):
+    """eagle/Dataloader/IMG_Eagle.py:37-49 for the deterministic modes: window start 550 (or 1 for the full 990), the
+    normalised window, the pixel-type mask."""
+    t = 1 if window_length == 990 else 550
+    assert mode in ("test", "valid")
+    return img_eagle_normalize(states[t:t + window_length]), np.array(pixel_type)
+
+
 def _floor_divide_f(a, b, dtype):
     """numpy's npy_floor_divide for floats, evaluated in `dtype` (NumPy C source semantics)."""
     a = np.asarray(a, dtype=dtype)

@@ -167,3 +167,30 @@ def test_get_nrmse_matches_oracle():
     want = P.get_nrmse(true, pred, pos, faces)
     assert got.shape == (1, T)
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5)
+
+
+def test_img_eagle_dataset_reproduces_frozen_reference(tmp_path):
+    """img_eagle.EagleDataset (window of states.npy -> pinned -> device -> fl_affine_channels) == the reference's EagleDataset
+    on the same files, bit for bit; normalize / denormalize on CUDA and on CPU tensors."""
+    import os
+    from oracle.make_golden_img_eagle import WINDOW, img_eagle_inputs, write_tree
+    from fluid_llm_b200.img_eagle import EagleDataset
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_img_eagle.npz"))
+    data_path = write_tree(str(tmp_path))
+    ds = EagleDataset(data_path, mode="test", window_length=WINDOW, splits_dir=str(tmp_path / "Splits"))
+    assert len(ds) == int(g["n"][0])
+    for _ in range(2):                                  # the second call reuses the pinned staging buffer
+        out = ds[0]
+        assert out["states"].is_cuda and out["states"].dtype == torch.float32
+        assert np.array_equal(out["states"].cpu().numpy().view(np.int32), g["states"].view(np.int32))
+        assert np.array_equal(out["mask"], g["mask"]) and np.array_equal(out["example"].numpy(), g["example"])
+    den = ds.denormalize(out["states"])
+    assert np.array_equal(den.cpu().numpy().view(np.int32), g["denormalized"].view(np.int32))
+    assert np.array_equal(ds.denormalize(out["states"].cpu()).numpy().view(np.int32), g["denormalized"].view(np.int32))
+    host = EagleDataset(data_path, mode="test", window_length=WINDOW, splits_dir=str(tmp_path / "Splits"), output_device="cpu")[0]
+    assert not host["states"].is_cuda and np.array_equal(host["states"].numpy().view(np.int32), g["states"].view(np.int32))
+    states, pixel_type = img_eagle_inputs()
+    want, _ = P.img_eagle_item(states, pixel_type, WINDOW, "test")
+    assert np.array_equal(out["states"].cpu().numpy(), want)
+    with pytest.raises(RuntimeError):
+        ds.normalize(torch.zeros(3, 5, device="cuda"))

@@ -297,3 +297,14 @@ def test_reference_callers_reproduce_the_frozen_fixture_live():
     assert np.array_equal(all_states.numpy(), g["ro_all_states"]) and np.array_equal(all_diffs.numpy(), g["ro_all_diffs"])
     sha = [hashlib.sha256(np.ascontiguousarray(t.numpy()).tobytes()).hexdigest() for t in (img_s, img_d)]
     assert sha == list(g["ro_img_sha256"])
+
+
+def test_img_eagle_oracle_reproduces_frozen_reference():
+    """oracle.pipeline.img_eagle_* == the reference's EagleDataset over pre-gridded states (fixture made by
+    oracle/make_golden_img_eagle.py from the unmodified eagle/Dataloader/IMG_Eagle.py)."""
+    from oracle.make_golden_img_eagle import WINDOW, img_eagle_inputs
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_img_eagle.npz"))
+    states, pixel_type = img_eagle_inputs()
+    got, mask = P.img_eagle_item(states, pixel_type, WINDOW, "test")
+    assert np.array_equal(got.view(np.int32), g["states"].view(np.int32)) and np.array_equal(mask, g["mask"])
+    assert np.array_equal(P.img_eagle_denormalize(got).view(np.int32), g["denormalized"].view(np.int32))
