@@ -9,6 +9,7 @@ parent has page-locked once (`cudaHostRegister`): the parent only issues the asy
 
 Every worker owns its own two slots and keeps them mapped for its lifetime: a process that maps a 20 MB slot for the first
 time pays ~20 ms of page faults, four times the unpickling itself, so slots are never handed from one worker to another.
+The workers are separate interpreters (`_ingest_worker.py`, started with fork+exec), not forks of the calling process.
 
     pool = PickleIngest(workers=8)
     pool.submit(paths)                       # runs ahead; order of consumption is free
@@ -23,69 +24,18 @@ import atexit
 import os
 import pickle
 from collections import OrderedDict
-from multiprocessing import get_context, shared_memory
+import subprocess
+import sys
+from multiprocessing import Pipe, shared_memory
+from multiprocessing.connection import wait as conn_wait
 
 import numpy as np
 import torch
 
+from ._ingest_worker import fill_slot as _fill_slot, load_trajectory, strides as _strides
+
 SLOTS_PER_WORKER = 2
-
-
-def _strides(n_nodes):
-    ps = (n_nodes + 3) // 4 * 4
-    return 2 * ps, ps
-
-
-def load_trajectory(path, airfoil_crop):
-    """Unpickle `path` and crop if asked -> (mesh_pos f32 [N,2], cells i32 [F,3], velocity [T,N,2], pressure [T,N,1])."""
-    with open(path, "rb") as f:
-        d = pickle.load(f)
-    pos, cells = np.asarray(d["mesh_pos"]), np.asarray(d["cells"])
-    vel, prs = np.asarray(d["velocity"]), np.asarray(d["pressure"])
-    if airfoil_crop:
-        mask = (pos[:, 0] > -.5) & (pos[:, 0] < 2) & (pos[:, 1] > -.75) & (pos[:, 1] < 0.75)      # airfoil_ds.py:166-168
-        wanted = np.nonzero(mask)[0]
-        renum = np.zeros(len(mask), dtype=np.int64)
-        renum[mask] = np.arange(len(wanted), dtype=np.int64)
-        cells = renum[cells[np.isin(cells, wanted).all(axis=1)]]
-        pos, vel, prs = pos[mask], vel[:, mask], prs[:, mask]
-    return np.ascontiguousarray(pos, dtype=np.float32), np.ascontiguousarray(cells, dtype=np.int32), vel, prs
-
-
-def _fill_slot(buf, nbytes, vel, prs):
-    """Write the node fields in the device pitch (frames padded to 4 nodes, pad = 0) into `buf`; -> None, or the bytes needed."""
-    T, N = vel.shape[0], vel.shape[1]
-    vs, ps = _strides(N)
-    need = 4 * T * (vs + ps)
-    if need > nbytes:
-        return need
-    v = np.ndarray((T, vs), dtype=np.float32, buffer=buf, offset=0)
-    p = np.ndarray((T, ps), dtype=np.float32, buffer=buf, offset=4 * T * vs)
-    v[:, :2 * N] = vel.reshape(T, 2 * N)
-    v[:, 2 * N:] = 0
-    p[:, :N] = prs.reshape(T, N)
-    p[:, N:] = 0
-    return None
-
-
-def _worker_main(in_q, out_q, slot_names, slot_bytes, airfoil_crop):
-    shms = [shared_memory.SharedMemory(name=n) for n in slot_names]       # mapped once, for the life of the worker
-    try:
-        while True:
-            job = in_q.get()
-            if job is None:
-                break
-            ticket, path, si = job
-            try:
-                pos, cells, vel, prs = load_trajectory(path, airfoil_crop)
-                need = _fill_slot(shms[si].buf, slot_bytes, vel, prs)
-                r = {"too_small": need} if need else {"mesh_pos": pos, "cells": cells, "T": vel.shape[0], "N": pos.shape[0]}
-            except Exception as e:      # noqa: BLE001 -- reported to the parent, which re-raises
-                r = {"error": f"{type(e).__name__}: {e}"}
-            out_q.put((ticket, r))
-    finally:
-        for s in shms:
-            s.close()
+WORKER_SCRIPT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ingest_worker.py")
 
 
 class _Slot:
@@ -111,17 +61,18 @@ class PickleIngest:
         self.workers = workers or max(2, min(12, (os.cpu_count() or 4) - 2))
         self.slot_bytes = slot_bytes
         self.airfoil_crop = airfoil_crop
-        # fork, like torch's DataLoader workers: the children only unpickle and copy with NumPy, they never touch CUDA
-        ctx = get_context("fork")
-        self._out_q = ctx.Queue()
         self._slots = [[_Slot(slot_bytes) for _ in range(SLOTS_PER_WORKER)] for _ in range(self.workers)]
-        self._in_qs, self._procs = [], []
+        # workers are separate interpreters started with fork+exec (see _ingest_worker.py for why they are not forks of this
+        # process); each talks to the parent over its own duplex pipe
+        self._conns, self._procs = [], []
         for w in range(self.workers):
-            q = ctx.Queue()
-            p = ctx.Process(target=_worker_main, daemon=True,
-                            args=(q, self._out_q, [s.shm.name for s in self._slots[w]], slot_bytes, airfoil_crop))
-            p.start()
-            self._in_qs.append(q)
+            parent_c, child_c = Pipe(duplex=True)
+            fd = child_c.fileno()
+            os.set_inheritable(fd, True)
+            p = subprocess.Popen([sys.executable, WORKER_SCRIPT, str(fd), str(slot_bytes), "1" if airfoil_crop else "0",
+                                  *[s.shm.name for s in self._slots[w]]], pass_fds=(fd,), close_fds=True)
+            child_c.close()
+            self._conns.append(parent_c)
             self._procs.append(p)
         self._free = [(w, si) for si in range(SLOTS_PER_WORKER) for w in range(self.workers)]     # round-robin over the workers
         self._pending = OrderedDict()          # path -> ticket
@@ -138,7 +89,7 @@ class PickleIngest:
             self._ticket += 1
             self._pending[path] = self._ticket
             self._where[self._ticket] = (w, si)
-            self._in_qs[w].put((self._ticket, path, si))
+            self._conns[w].send((self._ticket, path, si))
 
     # -- API -----------------------------------------------------------------------------------
     def submit(self, paths):
@@ -161,8 +112,12 @@ class PickleIngest:
                 return self._load_here(path)
         ticket = self._pending.pop(path)
         while ticket not in self._done:
-            t, r = self._out_q.get()
-            self._done[t] = r
+            for c in conn_wait(self._conns):
+                try:
+                    t, r = c.recv()
+                except EOFError:
+                    raise RuntimeError("an ingest worker process died") from None
+                self._done[t] = r
         r = self._done.pop(ticket)
         w, si = self._where.pop(ticket)
         slot = self._slots[w][si]
@@ -196,15 +151,18 @@ class PickleIngest:
         procs, self._procs = getattr(self, "_procs", None), None
         if not procs:
             return
-        for q in self._in_qs:
+        for c in self._conns:
             try:
-                q.put(None)
+                c.send(None)
             except Exception:
                 pass
         for p in procs:
-            p.join(timeout=2)
-            if p.is_alive():
-                p.terminate()
+            try:
+                p.wait(timeout=2)
+            except Exception:
+                p.kill()
+        for c in self._conns:
+            c.close()
         for ws in self._slots:
             for s in ws:
                 try:
