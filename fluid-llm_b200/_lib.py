@@ -61,7 +61,7 @@ SIGNATURES = {
                                 c_int, c_int, c_int, c_void_p]),
     "fl_affine_channels": (c_int, [c_void_p, c_void_p, ctypes.c_long, c_int, POINTER(c_float), POINTER(c_float), c_int, c_void_p]),
     "fl_grid2mesh": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
-                             c_double, c_double, c_void_p]),
+                             c_double, c_double, c_void_p, c_void_p]),
     "fl_dyn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "fl_dyn_capacity": (c_int, [c_int, c_int, c_int, c_int, c_size_t]),
     "fl_dyn_interp_patchify": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,

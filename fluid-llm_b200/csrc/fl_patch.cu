@@ -133,7 +133,7 @@ __device__ __forceinline__ float np_floor_divide_f(float a, float b) {
 
 __global__ void k_grid2mesh(const float* __restrict__ grid, const float* __restrict__ mesh_pos, float* __restrict__ out,
                             int T, int N, int H, int W, int C, float x_min, float y_min, float half_sx, float half_sy,
-                            float sx, float neg_sy) {
+                            float sx, float neg_sy, int* __restrict__ oob) {
     long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long)T * N) return;
     long t = g / N;
@@ -144,7 +144,8 @@ __global__ void k_grid2mesh(const float* __restrict__ grid, const float* __restr
     long ix = (long)fx, iy = (long)fy;
     if (ix < 0) ix += W;                       // NumPy negative indices wrap once
     if (iy < 0) iy += H;
-    ix = ix < 0 ? 0 : (ix >= W ? W - 1 : ix);  // the reference raises IndexError beyond that; clamp
+    if (oob && (ix < 0 || ix >= W || iy < 0 || iy >= H)) atomicAdd(oob, 1);   // the reference raises IndexError here: counted for the host
+    ix = ix < 0 ? 0 : (ix >= W ? W - 1 : ix);  // (and clamped, so that the kernel itself stays inside the grid)
     iy = iy < 0 ? 0 : (iy >= H ? H - 1 : iy);
     long row = H - 1 - iy;                     // np.flip(grid, axis=1), IMG_Eagle.py:105-106
     const float* s = grid + ((t * H + row) * W + ix) * C;
@@ -275,7 +276,7 @@ extern "C" int fl_affine_channels(const float* d_in, float* d_out, long n_values
 }
 
 extern "C" int fl_grid2mesh(const float* d_grid, const float* d_mesh_pos, float* d_out, int T, int N, int H, int W, int C,
-                            float x_min, float y_min, double step_x, double step_y, void* stream) {
+                            float x_min, float y_min, double step_x, double step_y, int32_t* d_out_of_range, void* stream) {
     FL_REQUIRE(d_grid && d_mesh_pos && d_out, FL_E_ARG, "fl_grid2mesh: null pointer");
     FL_REQUIRE(T > 0 && N > 0 && H > 0 && W > 0 && C > 0, FL_E_ARG, "fl_grid2mesh: sizes must be positive");
     FL_REQUIRE(step_x != 0.0 && step_y != 0.0, FL_E_ARG, "fl_grid2mesh: zero grid step");
@@ -283,7 +284,7 @@ extern "C" int fl_grid2mesh(const float* d_grid, const float* d_mesh_pos, float*
     long n = (long)T * N;
     k_grid2mesh<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         d_grid, d_mesh_pos, d_out, T, N, H, W, C, x_min, y_min, (float)(step_x / 2), (float)(step_y / 2), (float)step_x,
-        (float)(-step_y));
+        (float)(-step_y), d_out_of_range);
     FL_LAUNCH_CHECK();
     return FL_OK;
 }

@@ -110,20 +110,21 @@ class EagleDataset(Dataset):
         return _affine(state, True)
 
 
-def _resample(grid, pos, step_x, step_y, x_min, y_min):
+def _resample(grid, pos, step_x, step_y, x_min, y_min, oob=None):
     T, H, W, C = grid.shape
     out = torch.empty((T, pos.shape[1], C), dtype=torch.float32, device=grid.device)
     with torch.cuda.device(grid.device):
         check(load().fl_grid2mesh(ptr(grid), ptr(pos), ptr(out), T, pos.shape[1], H, W, C, float(x_min), float(y_min),
-                                  float(step_x), float(step_y), stream_ptr()), "fl_grid2mesh")
+                                  float(step_x), float(step_y), ptr(oob), stream_ptr()), "fl_grid2mesh")
     return out
 
 
-def grid2mesh(velocity_grid, pressure_grid, mesh_pos, device=None):
+def grid2mesh(velocity_grid, pressure_grid, mesh_pos, device=None, check_bounds=True):
     """Project the grid back onto the mesh nodes (IMG_Eagle.py:93-123).
 
     velocity_grid (T, H, W, Cv), pressure_grid (T, H, W, Cp), mesh_pos (T, N, 2)
-    -> velocity_mesh (T, N, Cv), pressure_mesh (T, N, Cp)."""
+    -> velocity_mesh (T, N, Cv), pressure_mesh (T, N, Cp).  A node outside the grid raises IndexError as the reference's
+    fancy indexing does (`check_bounds=False` skips the check and its device -> host read: such nodes are then clamped)."""
     _lib.require_cuda()
     on_device = torch.is_tensor(velocity_grid) and velocity_grid.is_cuda
     dev = velocity_grid.device if on_device else torch.device(device or "cuda")
@@ -140,8 +141,11 @@ def grid2mesh(velocity_grid, pressure_grid, mesh_pos, device=None):
     x = np.linspace(XMIN, XMAX, LENGTH)              # IMG_Eagle.py:101-102
     y = np.linspace(YMAX, YMIN, HEIGHT)
     step_x, step_y = x[1] - x[0], y[1] - y[0]
-    vm = _resample(vg, mp, step_x, step_y, XMIN, YMIN)
-    pm = _resample(pg, mp, step_x, step_y, XMIN, YMIN)
+    oob = torch.zeros(1, dtype=torch.int32, device=dev) if check_bounds else None
+    vm = _resample(vg, mp, step_x, step_y, XMIN, YMIN, oob)
+    pm = _resample(pg, mp, step_x, step_y, XMIN, YMIN, None)
+    if check_bounds and int(oob.item()):
+        raise IndexError(f"grid2mesh: {int(oob.item())} node position(s) index outside the {vg.shape[1]} x {vg.shape[2]} grid")
     if on_device:
         return vm, pm
     return vm.cpu(), pm.cpu()

@@ -188,9 +188,11 @@ int fl_sample_assemble(const float* d_states, const uint8_t* d_mask, int B, int 
 /* eagle/Dataloader/IMG_Eagle.py:93-123 grid2mesh: nearest-cell grid -> node resample.
  * d_grid f32[T, H, W, C] (row 0 = Ymin, flipped inside as the reference does), d_mesh_pos f32[T, N, 2]
  * -> d_out f32[T, N, C].  Extents/steps are the reference's constants unless overridden;
- * index arithmetic in float32 exactly as NumPy 1.26 evaluates it.  Negative row indices wrap. */
+ * index arithmetic in float32 exactly as NumPy 1.26 evaluates it.  Negative indices wrap once, as NumPy's do.
+ * d_out_of_range (optional i32[1], ADDED to, zero it first): nodes whose cell index lies outside the grid after that wrap --
+ * the reference's fancy indexing raises IndexError for them; the kernel clamps them and counts. */
 int fl_grid2mesh(const float* d_grid, const float* d_mesh_pos, float* d_out, int T, int N, int H, int W, int C,
-                 float x_min, float y_min, double step_x, double step_y, void* stream);
+                 float x_min, float y_min, double step_x, double step_y, int32_t* d_out_of_range, void* stream);
 
 /* eagle/Dataloader/IMG_Eagle.py:72-90 (EagleDataset.normalize / denormalize over the pre-gridded states.npy, 4 channels):
  * channel-last values [..., C], C <= 8; denormalize = 0: (x - mean[c]) / std[c], 1: x * std[c] + mean[c]; every operation

@@ -38,7 +38,7 @@ def test_argument_errors_without_a_device(lib):
     assert b"null" in lib.fl_last_error()
     assert lib.fl_patch_to_img(None, None, 1, 1, 1, 1, 1, 1, 4, None) == -1
     assert lib.fl_ds_stats(None, None, 2, 1, 1, 1, None, None, 0, None) == -1
-    assert lib.fl_grid2mesh(None, None, None, 1, 1, 1, 1, 1, 0.0, 0.0, 1.0, 1.0, None) == -1
+    assert lib.fl_grid2mesh(None, None, None, 1, 1, 1, 1, 1, 0.0, 0.0, 1.0, 1.0, None, None) == -1
     assert lib.fl_interp_patchify(None, 1, 1, 16, 16, None, None, 0, None) == -1
     nbx, nby = ctypes.c_int(), ctypes.c_int()
     assert lib.fl_plan_patch_table(None, None, 238, 60, 16, 16, 0, 0, None, None, ctypes.byref(nbx), ctypes.byref(nby), None, None, None) == 0

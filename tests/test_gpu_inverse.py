@@ -121,6 +121,14 @@ def test_grid2mesh_matches_oracle_and_frozen_reference():
     v_low, _ = grid2mesh(vg[:1], pg[:1], low)
     w_low, _ = P.grid2mesh(vg[:1], pg[:1], low, "1.26")
     assert np.array_equal(v_low.numpy(), w_low)
+    # a node beyond the grid: the reference's fancy indexing raises IndexError, and so does the mirror (the oracle too)
+    far = np.array([[[9.0, 0.0], [1.0, 0.0]]], dtype=np.float32)
+    with pytest.raises(IndexError):
+        P.grid2mesh(vg[:1], pg[:1], far, "1.26")
+    with pytest.raises(IndexError):
+        grid2mesh(vg[:1], pg[:1], far)
+    v_far, _ = grid2mesh(vg[:1], pg[:1], far, check_bounds=False)           # unchecked: clamped to the last column
+    assert torch.isfinite(v_far).all()
 
 
 @pytest.mark.parametrize("kind", ["cylinder", "airfoil"])
