@@ -167,14 +167,27 @@ class RolloutEmbedCache:
             self.g_ids = torch.zeros((self.B, self.ctx, self.L, 3), dtype=torch.int64, device=dev)
             self.g_out = None
 
+    @property
+    def token_buffer(self):
+        """graphs=True: the static (B * L, in_dim) bf16 input of the graphs -- let `rollout_step(..., tokens_out=...)` write
+        the new state's tokens straight into it and call `step(None, ...)`."""
+        return self.g_tok
+
     def step(self, state, position_ids):
         """append(state) + tokens(position_ids) in one call; with graphs=True and a full ring, one graph replay.
-        The returned tensor is reused by the next replay."""
+        `state=None`: the tokens are already in `token_buffer`; `position_ids=None`: the ids of the previous call (in steady
+        state they are the same every step: time ids re-based to 0 .. ctx-1).  The returned tensor is reused by the next replay."""
+        if state is None:
+            state = self.g_tok
         if self.graphs is None or self.n < self.ctx - 1 or state.dtype != torch.bfloat16:
+            if position_ids is None:
+                raise ValueError("RolloutEmbedCache.step: position_ids=None needs the graphed steady state")
             self.append(state)
             return self.tokens(position_ids)
-        self.g_tok.copy_(state.reshape(self.g_tok.shape))
-        self.g_ids.copy_(position_ids.reshape(self.g_ids.shape))
+        if state is not self.g_tok:
+            self.g_tok.copy_(state.reshape(self.g_tok.shape))
+        if position_ids is not None:
+            self.g_ids.copy_(position_ids.reshape(self.g_ids.shape))
         g = self.graphs.get(self.head)
         if g is None:
             dev = self.ring.device

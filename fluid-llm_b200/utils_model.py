@@ -91,14 +91,15 @@ def img_to_patch(img, ds_props: DSProps):
     return out.view(bs, seq_len, ds_props.N_patch, channel, px_patch, py_patch)
 
 
-def rollout_step(last_state, pred_diff_img, mask, ds_props: DSProps, tokens_bf16=False):
+def rollout_step(last_state, pred_diff_img, mask, ds_props: DSProps, tokens_bf16=False, tokens_out=None):
     """model.py:164,206,210 fused into one kernel (fp32, inference only):
 
         diffs = img_to_patch(pred_diff_img);  diffs[mask] = 0.;  next_state = last_state + diffs
 
     last_state (bs, 1, N_patch, C, px, py), pred_diff_img (bs, 1, C, tot_px, tot_py),
     mask bool (bs, 1, N_patch, C, px, py) -> (next_state, diffs), or (next_state, diffs, next_state as bf16) with
-    tokens_bf16=True: the tokens the patch embedding takes, written by the same kernel."""
+    tokens_bf16=True: the tokens the patch embedding takes, written by the same kernel (into `tokens_out`, a contiguous
+    bf16 tensor of last_state's element count, if given -- e.g. `RolloutEmbedCache.token_buffer`)."""
     for t, n in ((last_state, "last_state"), (pred_diff_img, "pred_diff_img"), (mask, "mask")):
         if not t.is_cuda:
             raise _lib.FluidGridError(f"rollout_step: {n} must be a CUDA tensor")
@@ -110,7 +111,14 @@ def rollout_step(last_state, pred_diff_img, mask, ds_props: DSProps, tokens_bf16
     last_c, img_c = last_state.contiguous(), pred_diff_img.contiguous()
     m = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous()
     diffs, nxt = torch.empty_like(last_c), torch.empty_like(last_c)
-    tok = torch.empty(last_c.shape, dtype=torch.bfloat16, device=last_c.device) if tokens_bf16 else None
+    tok = None
+    if tokens_out is not None:
+        if tokens_out.dtype != torch.bfloat16 or tokens_out.numel() != last_c.numel() or not tokens_out.is_contiguous() \
+                or tokens_out.device != last_c.device:
+            raise ValueError("rollout_step: tokens_out must be a contiguous bf16 CUDA tensor with last_state's element count")
+        tok, tokens_bf16 = tokens_out, True
+    elif tokens_bf16:
+        tok = torch.empty(last_c.shape, dtype=torch.bfloat16, device=last_c.device)
     with torch.cuda.device(last_c.device):
         check(load().fl_rollout_step(ptr(img_c), ptr(m), ptr(last_c), ptr(diffs), ptr(nxt), ptr(tok), bs * T, ds_props.Nx_patch,
                                      ds_props.Ny_patch, C, px, py, stream_ptr()), "fl_rollout_step")

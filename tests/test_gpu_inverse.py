@@ -79,6 +79,9 @@ def test_rollout_step_matches_reference_glue():
     assert np.array_equal(nxt.cpu().numpy(), want_next) and np.array_equal(diffs.cpu().numpy(), want_d)
     n2, d2, tok = rollout_step(last, pred, mask, props, tokens_bf16=True)       # the same call also emits the embedding's tokens
     assert torch.equal(n2, nxt) and torch.equal(d2, diffs) and tok.dtype == torch.bfloat16 and torch.equal(tok, nxt.bfloat16())
+    buf = torch.zeros(60, 768, dtype=torch.bfloat16, device="cuda")              # a caller-owned token buffer (RolloutEmbedCache.token_buffer)
+    _, _, tok2 = rollout_step(last, pred, mask, props, tokens_out=buf)
+    assert tok2 is buf and torch.equal(buf.view(-1), tok.view(-1))
     with pytest.raises(ValueError):
         rollout_step(last, pred[..., :32], mask, props)
 
