@@ -50,19 +50,17 @@ class EagleDataset(Dataset):
     def __init__(self, data_path, mode="test", window_length=990, with_mesh=False, device=None, output_device=None,
                  splits_dir="Splits"):
         super().__init__()
-        assert mode in ["train", "test", "valid"]
-        self.window_length = window_length
-        assert window_length <= 990, "window length must be smaller than 990"
-        self.fn = data_path
-        assert os.path.exists(self.fn), f"Path {self.fn} does not exist"
-        self.dataloc = []
-        with open(os.path.join(splits_dir, f"{mode}.txt"), "r") as f:
-            for line in f.readlines():
-                self.dataloc.append(os.path.join(self.fn, line.strip()))
-        self.mode = mode
-        self.length = 990
-        self.with_mesh = with_mesh
+        if mode not in ("train", "test", "valid"):
+            raise AssertionError(f"unknown mode {mode!r}")
+        if window_length > 990:
+            raise AssertionError("window length must be smaller than 990")
+        if not os.path.exists(data_path):
+            raise AssertionError(f"Path {data_path} does not exist")
         _lib.require_cuda()
+        self.fn, self.mode, self.window_length, self.with_mesh = data_path, mode, window_length, with_mesh
+        self.length = 990
+        with open(os.path.join(splits_dir, f"{mode}.txt")) as f:
+            self.dataloc = [os.path.join(data_path, ln.strip()) for ln in f]
         self.device = torch.device(device or "cuda")
         self.output_device = output_device
         self._pin = None
@@ -70,37 +68,44 @@ class EagleDataset(Dataset):
     def __len__(self):
         return len(self.dataloc)
 
-    def __getitem__(self, item):
-        # IMG_Eagle.py:39-41: random window in training, fixed start otherwise
-        t = random.randint(1, 990 - self.window_length) if self.window_length != 990 else 1
-        t = 550 if self.mode in ["test", "valid"] and self.window_length != 990 else t
-        states = np.load(os.path.join(self.dataloc[item], "states.npy"), mmap_mode='r')
-        mask = np.load(os.path.join(self.dataloc[item], "pixel_type.npy"), mmap_mode='r')
-        win = states[t:t + self.window_length]
-        if win.dtype == np.float32:
-            if self._pin is None or self._pin.shape != win.shape:
-                self._pin = torch.empty(win.shape, dtype=torch.float32, pin_memory=True)
-            else:
-                torch.cuda.current_stream(self.device).synchronize()      # the previous window's upload has left the buffer
-            self._pin.numpy()[...] = win                                   # page cache -> pinned memory
-            dev_states = self._pin.to(self.device, non_blocking=True)
+    def _window_start(self):
+        """IMG_Eagle.py:39-41: the full trajectory starts at 1; shorter windows start at 550 in test / valid, at random in training."""
+        if self.window_length == 990:
+            return 1
+        if self.mode != "train":
+            return 550
+        return random.randint(1, 990 - self.window_length)
+
+    def _upload(self, win):
+        """A window of the memory-mapped states -> device float32: through a reused pinned buffer when it is float32 already."""
+        if win.dtype != np.float32:
+            return torch.from_numpy(win.copy()).to(self.device).float()           # the reference's `.float()`, on the device
+        if self._pin is not None and self._pin.shape == win.shape:
+            torch.cuda.current_stream(self.device).synchronize()                  # the previous window's upload has left the buffer
         else:
-            dev_states = torch.from_numpy(win.copy()).to(self.device).float()      # `.float()` of the reference, on the device
-        states_n = self.normalize(dev_states)
+            self._pin = torch.empty(win.shape, dtype=torch.float32, pin_memory=True)
+        self._pin.numpy()[...] = win                                              # page cache -> pinned memory
+        return self._pin.to(self.device, non_blocking=True)
+
+    def __getitem__(self, item):
+        t = self._window_start()
+        sim_dir = self.dataloc[item]
+        frames = slice(t, t + self.window_length)
+        states = np.load(os.path.join(sim_dir, "states.npy"), mmap_mode='r')
+        pixel_type = np.load(os.path.join(sim_dir, "pixel_type.npy"), mmap_mode='r')
+        normalised = self.normalize(self._upload(states[frames]))
         if self.output_device is not None:
-            states_n = states_n.to(self.output_device)
-        output = {'states': states_n,
-                  'mask': mask.copy(),
-                  'example': torch.tensor((int(self.dataloc[item].split("/")[-2]),)), }
-        if self.with_mesh:
-            path = self.dataloc[item].replace("_img", "")
-            assert os.path.exists(path), f"Can not find mesh files in {path}, please check the path in the dataloader"
-            data = np.load(os.path.join(path, 'sim.npz'), mmap_mode='r')
-            sl = slice(t, t + self.window_length)
-            output['mesh_pos'] = data["pointcloud"][sl].copy()
-            output['mesh_velocity'] = np.stack([data['VX'][sl].copy(), data['VY'][sl].copy()], axis=-1)
-            output['mesh_pressure'] = np.stack([data['PS'][sl].copy(), data['PG'][sl].copy()], axis=-1)
-            output['mesh_node_type'] = data['mask'][sl].copy()
+            normalised = normalised.to(self.output_device)
+        output = {'states': normalised, 'mask': pixel_type.copy(),
+                  'example': torch.tensor((int(sim_dir.split("/")[-2]),))}
+        if self.with_mesh:                                                        # IMG_Eagle.py:51-68: the irregular mesh of the same window
+            mesh_dir = sim_dir.replace("_img", "")
+            if not os.path.exists(mesh_dir):
+                raise AssertionError(f"Can not find mesh files in {mesh_dir}, please check the path in the dataloader")
+            sim = np.load(os.path.join(mesh_dir, 'sim.npz'), mmap_mode='r')
+            take = lambda key: sim[key][frames].copy()
+            output.update(mesh_pos=take("pointcloud"), mesh_velocity=np.stack([take("VX"), take("VY")], axis=-1),
+                          mesh_pressure=np.stack([take("PS"), take("PG")], axis=-1), mesh_node_type=take("mask"))
         return output
 
     def normalize(self, state):

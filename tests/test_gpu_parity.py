@@ -523,3 +523,36 @@ def test_to_grid_refuses_a_foreign_tri_index():
     other[10, 10] = (other[10, 10] + 1) % triang.n_cells
     with pytest.raises(ValueError, match="tri_index differs"):
         to_grid(val, gx, gy, triang, other)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_ragged_batch_through_the_c_abi(kernel):
+    """One call over trajectories with DIFFERENT frame counts, start frames and intervals (FlTraj::n_frames / t0 / interval are
+    per trajectory): every kernel writes exactly the frames each trajectory asks for -- bit-identical to that trajectory
+    computed alone -- and nothing behind them."""
+    from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, TrajBatch
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    spec = [(7, 0, 1), (3, 2, 3), (1, 5, 1), (5, 1, 2)]          # (n_frames, t0, interval)
+    trajs, tabs = [], []
+    for seed in range(len(spec)):
+        tr = trajectory("cylinder", 12, seed, 20 + seed)
+        plan = MeshPlan(tr["mesh_pos"], tr["cells"], 238)
+        trajs.append(DeviceTrajectory(tr["velocity"], tr["pressure"], plan))
+        tabs.append(plan.patch_table(PATCH))
+    ka = _kernel_args(kernel)
+    run_kw = dict(force_gather=ka.get("force_gather", False), force_ring=ka.get("force_ring", False))
+    n_max = max(s[0] for s in spec)
+    batch = TrajBatch(trajs, tabs, [0] * len(spec), 1, n_max, tile_patches=ka["tile_patches"])
+    for i, (nf, t0, iv) in enumerate(spec):
+        batch.host_desc[i].n_frames, batch.host_desc[i].t0, batch.host_desc[i].interval = nf, t0, iv
+    batch.desc = torch.from_numpy(np.frombuffer(bytes(batch.host_desc), dtype=np.uint8).copy()).cuda()
+    batch.states.fill_(777.0)
+    batch.mask.fill_(77)
+    states, mask = batch.run(CYLINDER, **run_kw)
+    torch.cuda.synchronize()
+    for i, (nf, t0, iv) in enumerate(spec):
+        alone = TrajBatch([trajs[i]], [tabs[i]], [t0], iv, nf, tile_patches=0)
+        s1, m1 = alone.run(CYLINDER)
+        assert torch.equal(states[i, :nf].view(torch.int32), s1[0].view(torch.int32)), (kernel, i)
+        assert torch.equal(mask[i, :nf], m1[0]), (kernel, i)
+        assert bool((states[i, nf:] == 777.0).all()) and bool((mask[i, nf:] == 77).all()), (kernel, i)
