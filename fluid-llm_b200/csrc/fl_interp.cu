@@ -95,8 +95,10 @@ __global__ void k_to_grid(const FlCellIdx* __restrict__ idx, const FlCellW* __re
 // Staged kernel (the fast path).  One persistent 512-thread CTA per SM; a work item is TF
 // consecutive selected frames of one trajectory.
 //   staging   coalesced 128-bit streaming loads of 4 nodes' (u,v) pairs and pressures are written to
-//             shared memory as four 16-byte node records {u f32, v f32, p f64}: pressure is converted
-//             once per NODE instead of three times per PIXEL, and one 128-bit gather fetches a vertex.
+//             shared memory as four 16-byte node records with all three values ALREADY widened to fp64 (their
+//             high words + one word holding the top byte of each low word: a widened float has no other low
+//             bits): conversions happen once per NODE instead of nine times per PIXEL, one 128-bit gather
+//             fetches a vertex and three PRMTs rebuild its doubles.
 //             Records sit at Morton-ordered slots (d_node_slot); the same pass scans for non-finite /
 //             huge values.  (A TMA bulk-copy staging of the frames in their global layout was measured
 //             slower: twice the gather instructions and three more conversions per pixel.)
@@ -107,7 +109,7 @@ __global__ void k_to_grid(const FlCellIdx* __restrict__ idx, const FlCellW* __re
 //   output    128 B per warp store (streaming, no L1 allocate); each (frame, patch, channel) block of
 //             1 KB is written whole by two warps.
 // HBM traffic: 12 N + 12 P bytes per frame (compulsory); L2 -> SM adds 32 P / TF (table).
-// Arithmetic per pixel-frame: 6 f32->f64 (u, v), 3 DMUL + 6 DFMA, 3 f64->f32, then (v - mean) / std as
+// Arithmetic per pixel-frame: 9 PRMT, 3 DMUL + 6 DFMA, 3 f64->f32, then (v - mean) / std as
 // a reciprocal multiply with one Markstein correction step on the packed fp32 pipe (bit-identical to
 // IEEE division for the ranges checked on the host and in the staging scan; anything else takes the
 // checked path).  What bounds it today (profiles/README.md): the L1/shared LSU data pipe at ~80 %.
@@ -115,7 +117,24 @@ __global__ void k_to_grid(const FlCellIdx* __restrict__ idx, const FlCellW* __re
 constexpr int ST_THREADS = 512;
 constexpr int NP = 4;        // pixels per thread
 
-template <bool CHECKED>
+// wide node record {bits, hi(u), hi(p), hi(v)}: the three values widened to fp64 at staging; byte k of `bits` = the top byte of the
+// k-th value's low word (u, v, p), whose other 24 bits are zero for a widened float (normal, denormal, inf or NaN alike)
+__device__ __forceinline__ float4 make_wide(float u, float v, float p) {
+    const double du = (double)u, dv = (double)v, dp = (double)p;
+    const uint32_t bits = ((uint32_t)__double2loint(du) >> 24) | (((uint32_t)__double2loint(dv) >> 24) << 8) |
+                          (((uint32_t)__double2loint(dp) >> 24) << 16);
+    return make_float4(__uint_as_float(bits), __int_as_float(__double2hiint(du)), __int_as_float(__double2hiint(dp)),
+                       __int_as_float(__double2hiint(dv)));
+}
+__device__ __forceinline__ void load_wide(const unsigned char* addr, double& u, double& v, double& p) {
+    const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(addr);      // x = {bits, hi(u)}, y = {hi(p), hi(v)}
+    const uint32_t bits = (uint32_t)r.x;
+    p = __hiloint2double((int)(uint32_t)r.y, (int)__byte_perm(bits, 0u, 0x2444));
+    v = __longlong_as_double((long long)((r.y & 0xffffffff00000000ull) | __byte_perm(bits, 0u, 0x1444)));
+    u = __longlong_as_double((long long)((r.x & 0xffffffff00000000ull) | __byte_perm(bits, 0u, 0x0444)));
+}
+
+template <bool CHECKED, bool WIDE>
 __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned char* __restrict__ s_nodes, int slot_b,
                                             int fbeg, int nf, int n_patches, int ppx, int ppx_shift, const StagedConst& sc,
                                             unsigned flags) {
@@ -173,14 +192,22 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
             unsigned fm = mbits;
 #pragma unroll
             for (int r = 0; r < NP; ++r) {
-                const float4 a0 = *reinterpret_cast<const float4*>(nb + ov[r][0]);   // one 128-bit gather per vertex
-                const float4 a1 = *reinterpret_cast<const float4*>(nb + ov[r][1]);
-                const float4 a2 = *reinterpret_cast<const float4*>(nb + ov[r][2]);
-                const double p0 = __hiloint2double(__float_as_int(a0.w), __float_as_int(a0.z));
-                const double p1 = __hiloint2double(__float_as_int(a1.w), __float_as_int(a1.z));
-                const double p2 = __hiloint2double(__float_as_int(a2.w), __float_as_int(a2.z));
-                res[0][r] = (float)fma(w2[r], (double)a2.x, fma(w1[r], (double)a1.x, w0[r] * (double)a0.x));
-                res[1][r] = (float)fma(w2[r], (double)a2.y, fma(w1[r], (double)a1.y, w0[r] * (double)a0.y));
+                double u0, v0, p0, u1, v1, p1, u2, v2, p2;
+                if (WIDE) {          // records {bits, hi(u), hi(p), hi(v)}: the doubles are rebuilt with PRMTs, no conversion
+                    load_wide(nb + ov[r][0], u0, v0, p0);
+                    load_wide(nb + ov[r][1], u1, v1, p1);
+                    load_wide(nb + ov[r][2], u2, v2, p2);
+                } else {             // records {u f32, v f32, p f64}
+                    const float4 a0 = *reinterpret_cast<const float4*>(nb + ov[r][0]);   // one 128-bit gather per vertex
+                    const float4 a1 = *reinterpret_cast<const float4*>(nb + ov[r][1]);
+                    const float4 a2 = *reinterpret_cast<const float4*>(nb + ov[r][2]);
+                    p0 = __hiloint2double(__float_as_int(a0.w), __float_as_int(a0.z));
+                    p1 = __hiloint2double(__float_as_int(a1.w), __float_as_int(a1.z));
+                    p2 = __hiloint2double(__float_as_int(a2.w), __float_as_int(a2.z));
+                    u0 = (double)a0.x; v0 = (double)a0.y; u1 = (double)a1.x; v1 = (double)a1.y; u2 = (double)a2.x; v2 = (double)a2.y;
+                }
+                res[0][r] = (float)fma(w2[r], u2, fma(w1[r], u1, w0[r] * u0));
+                res[1][r] = (float)fma(w2[r], v2, fma(w1[r], v1, w0[r] * v0));
                 res[2][r] = (float)fma(w2[r], p2, fma(w1[r], p1, w0[r] * p0));
                 if (CHECKED) {
                     if (!finite_f(res[2][r])) fm |= 1u << (8 * r);           // pressure mask only
@@ -237,7 +264,7 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
 
 __global__ void __launch_bounds__(ST_THREADS, 1)
 k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int groups_per_traj, int TF, int n_patches,
-                         int ppx, int ppx_shift, int slot_nodes, StagedConst sc, unsigned flags) {
+                         int ppx, int ppx_shift, int slot_nodes, StagedConst sc, unsigned flags, int wide) {
     extern __shared__ __align__(128) unsigned char fl_smem[];
     float4* s_nodes = (float4*)fl_smem;          // [TF][slot_nodes] records {u, v, p as fp64}
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -264,16 +291,28 @@ k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int grou
             float4* d = s_nodes + (size_t)f * slot_nodes;
             int4 sl = make_int4(4 * k4, 4 * k4 + 1, 4 * k4 + 2, 4 * k4 + 3);
             if (tr.d_node_slot) sl = __ldg((const int4*)tr.d_node_slot + k4);      // spatially sorted slots
-            const double p0 = (double)pp.x, p1 = (double)pp.y, p2 = (double)pp.z, p3 = (double)pp.w;
-            d[sl.x] = make_float4(va.x, va.y, __int_as_float(__double2loint(p0)), __int_as_float(__double2hiint(p0)));
-            d[sl.y] = make_float4(va.z, va.w, __int_as_float(__double2loint(p1)), __int_as_float(__double2hiint(p1)));
-            d[sl.z] = make_float4(vb.x, vb.y, __int_as_float(__double2loint(p2)), __int_as_float(__double2hiint(p2)));
-            d[sl.w] = make_float4(vb.z, vb.w, __int_as_float(__double2loint(p3)), __int_as_float(__double2hiint(p3)));
+            if (wide) {
+                d[sl.x] = make_wide(va.x, va.y, pp.x);
+                d[sl.y] = make_wide(va.z, va.w, pp.y);
+                d[sl.z] = make_wide(vb.x, vb.y, pp.z);
+                d[sl.w] = make_wide(vb.z, vb.w, pp.w);
+            } else {
+                const double p0 = (double)pp.x, p1 = (double)pp.y, p2 = (double)pp.z, p3 = (double)pp.w;
+                d[sl.x] = make_float4(va.x, va.y, __int_as_float(__double2loint(p0)), __int_as_float(__double2hiint(p0)));
+                d[sl.y] = make_float4(va.z, va.w, __int_as_float(__double2loint(p1)), __int_as_float(__double2hiint(p1)));
+                d[sl.z] = make_float4(vb.x, vb.y, __int_as_float(__double2loint(p2)), __int_as_float(__double2hiint(p2)));
+                d[sl.w] = make_float4(vb.z, vb.w, __int_as_float(__double2loint(p3)), __int_as_float(__double2hiint(p3)));
+            }
         }
         const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || !sc.fast_div);
         const unsigned char* snb = (const unsigned char*)s_nodes;
-        if (bad) staged_item<true>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
-        else staged_item<false>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+        if (wide) {
+            if (bad) staged_item<true, true>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+            else staged_item<false, true>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+        } else {
+            if (bad) staged_item<true, false>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+            else staged_item<false, false>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+        }
         __syncthreads();   // every gather of this item is done before the next item's staging lands
     }
 }
@@ -331,8 +370,10 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             int ppx_shift = -1;
             for (int b = 0; b < 16; ++b) if ((1 << b) == ppx) ppx_shift = b;
             const int grid = n_items < FL_SM_COUNT ? (int)n_items : FL_SM_COUNT;      // one persistent CTA per SM
+            int wide = 1;        // fully pre-widened records (round 2: +4 % on all three workloads); FLUIDGRID_WIDE=0 keeps {u, v f32, p f64}
+            if (const char* e = getenv("FLUIDGRID_WIDE")) wide = atoi(e) != 0;
             k_interp_patchify_staged<<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift, slot_prs,
-                                                                     sc, flags);
+                                                                     sc, flags, wide);
             FL_LAUNCH_CHECK();
             g_last_kernel = "k_interp_patchify_staged";
             return FL_OK;
