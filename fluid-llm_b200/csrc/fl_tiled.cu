@@ -10,10 +10,9 @@
 //              tile's node list holds exactly the mesh nodes its pixels touch (FlTraj::d_tile_*), and the table carries
 //              tile-local slots.  A work item = one tile x TF consecutive selected frames of one trajectory, so shared
 //              memory holds TF x (nodes of ONE tile) records whatever the size of the mesh.
-//   records    16 bytes per node and frame with u and v ALREADY in fp64 form: their high words plus one word with the
-//              three non-zero bits of each low word (a float widened to double has 29 zero bits at the bottom), and p
-//              as fp32.  A vertex costs one LDS.128 + two PRMT (written in place next to the high words) + one
-//              F2F.F64.F32 instead of one LDS.128 + two F2F: half the load on the conversion unit per vertex.
+//   records    16 bytes per node and frame with u, v and p ALREADY in fp64 form: their high words plus one word with the
+//              top byte of each low word (a float widened to double has 29 zero bits at the bottom).  A vertex costs
+//              one LDS.128 + three PRMT and no conversion.
 //   producers  the last warps of the CTA only stage: they walk the CTA's items, load the tile's nodes frame by frame
 //              (several frames in flight per thread), convert, write the records of item k into buffer k & 1 and arrive
 //              on its `full` mbarrier; they wait on `empty` before overwriting a buffer.
@@ -80,20 +79,21 @@ __device__ __forceinline__ float ldg_stream1(const float* p) {
     return r;
 }
 
-// node record {bits, hi(u), p, hi(v)}: u and v already widened to fp64 (high words; byte 0 / 1 of `bits` = the top byte of
-// their low words, whose other 29 bits are zero for a widened float), p still fp32
+// node record {bits, hi(u), hi(p), hi(v)}: the three values widened to fp64; byte k of `bits` = the top byte of the k-th value's
+// low word (u, v, p), whose other 24 bits are zero for a widened float (normal, denormal, inf or NaN alike)
 __device__ __forceinline__ uint4 make_record(float u, float v, float p) {
-    const double du = (double)u, dv = (double)v;
-    const uint32_t bits = ((uint32_t)__double2loint(du) >> 24) | (((uint32_t)__double2loint(dv) >> 24) << 8);
-    return make_uint4(bits, (uint32_t)__double2hiint(du), __float_as_uint(p), (uint32_t)__double2hiint(dv));
+    const double du = (double)u, dv = (double)v, dp = (double)p;
+    const uint32_t bits = ((uint32_t)__double2loint(du) >> 24) | (((uint32_t)__double2loint(dv) >> 24) << 8) |
+                          (((uint32_t)__double2loint(dp) >> 24) << 16);
+    return make_uint4(bits, (uint32_t)__double2hiint(du), (uint32_t)__double2hiint(dp), (uint32_t)__double2hiint(dv));
 }
-// one 128-bit gather -> the three doubles.  Written on the 64-bit halves so that u and v are completed IN PLACE (one PRMT
-// each writes the low word next to the high word that is already there); p takes the one F2F.F64.F32.
+// one 128-bit gather -> the three doubles, no conversion: u and v are completed IN PLACE (a PRMT writes the low word next to
+// the high word the load put there), p takes a PRMT and a move
 __device__ __forceinline__ void load_record(uint32_t addr, double& u, double& v, double& p) {
-    unsigned long long A, B;        // A = {bits, hi(u)}, B = {p as float, hi(v)}
+    unsigned long long A, B;        // A = {bits, hi(u)}, B = {hi(p), hi(v)}
     asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(A), "=l"(B) : "r"(addr));
     const uint32_t bits = (uint32_t)A;
-    p = (double)__uint_as_float((uint32_t)B);
+    p = __hiloint2double((int)(uint32_t)B, (int)__byte_perm(bits, 0u, 0x2444));
     v = __longlong_as_double((long long)((B & 0xffffffff00000000ull) | __byte_perm(bits, 0u, 0x1444)));
     u = __longlong_as_double((long long)((A & 0xffffffff00000000ull) | __byte_perm(bits, 0u, 0x0444)));
 }
