@@ -134,7 +134,7 @@ __device__ __forceinline__ void load_wide(const unsigned char* addr, double& u, 
     u = __longlong_as_double((long long)((r.x & 0xffffffff00000000ull) | __byte_perm(bits, 0u, 0x0444)));
 }
 
-template <bool CHECKED, bool WIDE>
+template <bool CHECKED, int WIDE>
 __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned char* __restrict__ s_nodes, int slot_b,
                                             int fbeg, int nf, int n_patches, int ppx, int ppx_shift, const StagedConst& sc,
                                             unsigned flags) {
@@ -193,7 +193,7 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
 #pragma unroll
             for (int r = 0; r < NP; ++r) {
                 double u0, v0, p0, u1, v1, p1, u2, v2, p2;
-                if (WIDE) {          // records {bits, hi(u), hi(p), hi(v)}: the doubles are rebuilt with PRMTs, no conversion
+                if (WIDE == 1) {     // records {bits, hi(u), hi(p), hi(v)}: the doubles are rebuilt with PRMTs, no conversion
                     load_wide(nb + ov[r][0], u0, v0, p0);
                     load_wide(nb + ov[r][1], u1, v1, p1);
                     load_wide(nb + ov[r][2], u2, v2, p2);
@@ -307,11 +307,11 @@ k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int grou
         const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || !sc.fast_div);
         const unsigned char* snb = (const unsigned char*)s_nodes;
         if (wide) {
-            if (bad) staged_item<true, true>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
-            else staged_item<false, true>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+            if (bad) staged_item<true, 1>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+            else staged_item<false, 1>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
         } else {
-            if (bad) staged_item<true, false>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
-            else staged_item<false, false>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+            if (bad) staged_item<true, 0>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+            else staged_item<false, 0>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
         }
         __syncthreads();   // every gather of this item is done before the next item's staging lands
     }
@@ -371,7 +371,7 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             for (int b = 0; b < 16; ++b) if ((1 << b) == ppx) ppx_shift = b;
             const int grid = n_items < FL_SM_COUNT ? (int)n_items : FL_SM_COUNT;      // one persistent CTA per SM
             int wide = 1;        // fully pre-widened records (round 2: +4 % on all three workloads); FLUIDGRID_WIDE=0 keeps {u, v f32, p f64}
-            if (const char* e = getenv("FLUIDGRID_WIDE")) wide = atoi(e) != 0;
+            if (const char* e = getenv("FLUIDGRID_WIDE")) wide = atoi(e);
             k_interp_patchify_staged<<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift, slot_prs,
                                                                      sc, flags, wide);
             FL_LAUNCH_CHECK();
