@@ -126,16 +126,18 @@ __device__ __forceinline__ float4 make_wide(float u, float v, float p) {
     return make_float4(__uint_as_float(bits), __int_as_float(__double2hiint(du)), __int_as_float(__double2hiint(dp)),
                        __int_as_float(__double2hiint(dv)));
 }
-__device__ __forceinline__ void load_wide(const unsigned char* addr, double& u, double& v, double& p) {
-    const ulonglong2 r = *reinterpret_cast<const ulonglong2*>(addr);      // x = {bits, hi(u)}, y = {hi(p), hi(v)}
-    const uint32_t bits = (uint32_t)r.x;
-    p = __hiloint2double((int)(uint32_t)r.y, (int)__byte_perm(bits, 0u, 0x2444));
-    v = __longlong_as_double((long long)((r.y & 0xffffffff00000000ull) | __byte_perm(bits, 0u, 0x1444)));
-    u = __longlong_as_double((long long)((r.x & 0xffffffff00000000ull) | __byte_perm(bits, 0u, 0x0444)));
+// (32-bit shared address: with a warp-uniform base the add folds into LDS.128 [R + UR])
+__device__ __forceinline__ void load_wide(uint32_t addr, double& u, double& v, double& p) {
+    unsigned long long A, B;        // A = {bits, hi(u)}, B = {hi(p), hi(v)}
+    asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(A), "=l"(B) : "r"(addr));
+    const uint32_t bits = (uint32_t)A;
+    p = __hiloint2double((int)(uint32_t)B, (int)__byte_perm(bits, 0u, 0x2444));
+    v = __longlong_as_double((long long)((B & 0xffffffff00000000ull) | __byte_perm(bits, 0u, 0x1444)));
+    u = __longlong_as_double((long long)((A & 0xffffffff00000000ull) | __byte_perm(bits, 0u, 0x0444)));
 }
 
 template <bool CHECKED, int WIDE>
-__device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned char* __restrict__ s_nodes, int slot_b,
+__device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned char* __restrict__ s_nodes, uint32_t s_base, int slot_b,
                                             int fbeg, int nf, int n_patches, int ppx, int ppx_shift, const StagedConst& sc,
                                             unsigned flags) {
     const bool mask_aware = flags & FL_MASK_AWARE_NORM, no_norm = flags & FL_NO_NORM;
@@ -188,15 +190,16 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
         const unsigned char* nb = s_nodes;    // loop-carried uniform base: folds into LDS.128 [R + UR]
 #pragma unroll 1
         for (int f = 0; f < nf; ++f, nb += slot_b) {
+            const uint32_t nb32 = s_base + (uint32_t)f * (uint32_t)slot_b;      // warp-uniform: stays in a uniform register
             float res[3][NP];
             unsigned fm = mbits;
 #pragma unroll
             for (int r = 0; r < NP; ++r) {
                 double u0, v0, p0, u1, v1, p1, u2, v2, p2;
                 if (WIDE == 1) {     // records {bits, hi(u), hi(p), hi(v)}: the doubles are rebuilt with PRMTs, no conversion
-                    load_wide(nb + ov[r][0], u0, v0, p0);
-                    load_wide(nb + ov[r][1], u1, v1, p1);
-                    load_wide(nb + ov[r][2], u2, v2, p2);
+                    load_wide(nb32 + ov[r][0], u0, v0, p0);
+                    load_wide(nb32 + ov[r][1], u1, v1, p1);
+                    load_wide(nb32 + ov[r][2], u2, v2, p2);
                 } else {             // records {u f32, v f32, p f64}
                     const float4 a0 = *reinterpret_cast<const float4*>(nb + ov[r][0]);   // one 128-bit gather per vertex
                     const float4 a1 = *reinterpret_cast<const float4*>(nb + ov[r][1]);
@@ -306,12 +309,13 @@ k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int grou
         }
         const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || !sc.fast_div);
         const unsigned char* snb = (const unsigned char*)s_nodes;
+        const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(fl_smem);
         if (wide) {
-            if (bad) staged_item<true, 1>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
-            else staged_item<false, 1>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+            if (bad) staged_item<true, 1>(tr, snb, s_base, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+            else staged_item<false, 1>(tr, snb, s_base, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
         } else {
-            if (bad) staged_item<true, 0>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
-            else staged_item<false, 0>(tr, snb, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+            if (bad) staged_item<true, 0>(tr, snb, s_base, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+            else staged_item<false, 0>(tr, snb, s_base, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
         }
         __syncthreads();   // every gather of this item is done before the next item's staging lands
     }
