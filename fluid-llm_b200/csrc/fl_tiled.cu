@@ -535,9 +535,17 @@ int fli::launch_tiled(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, 
     const int cons_warps = TL_WARPS - prod_warps;
     const size_t ring = fl_align_up((size_t)(cons_warps / wpp) * 2 * ppx * 13, 128);
     const size_t fixed = HEAD_BYTES + ring;
-    long TF = ((long)SMEM_TOTAL - (long)fixed) / 2 / (16L * slot_rec);
+    // Frames per item: the two record buffers take what is left of a shared-memory budget that deliberately stops short of
+    // the 227 KB an SM has -- the rest stays L1 for the producers' list / node loads and the consumers' table reads
+    // (measured on the 1 M-triangle mesh, 4 x 64 frames: 11 frames per item with 225 KB of shared memory 2.99 ms, 8 frames
+    // with 171 KB 2.47 ms) -- and the frames of a trajectory are cut into groups of equal length (no short last item).
+    long budget = 176 * 1024;
+    if (const char* e = getenv("FLUIDGRID_TILED_SMEM_KB")) { long v = atol(e) * 1024; if (v >= 64 * 1024 && v <= SMEM_TOTAL) budget = v; }
+    long TF = (budget - (long)fixed) / 2 / (16L * slot_rec);
+    if (TF < 1) TF = ((long)SMEM_TOTAL - (long)fixed) / 2 / (16L * slot_rec);      // big tiles: whatever fits at all
     if (TF > 16) TF = 16;
     if (TF > max_frames) TF = max_frames;
+    if (TF >= 1) { const long groups = (max_frames + TF - 1) / TF; TF = (max_frames + groups - 1) / groups; }
     if (const char* e = getenv("FLUIDGRID_TF")) { long v = atol(e); if (v >= 1 && v < TF) TF = v; }
     if (TF < 1) return 1;        // a tile's nodes do not fit: the caller falls back (plan smaller tiles)
     TiledArgs a;
