@@ -106,9 +106,10 @@ class PatchTable:
     """The static table re-ordered into output-pixel order for one dataset personality.
     `idx_slot` is the same table with node ids replaced by the plan's shared-memory slots."""
 
-    def __init__(self, idx, w, n_bx, n_by, px, py, idx_slot=None, n_nodes=0):
+    def __init__(self, idx, w, n_bx, n_by, px, py, idx_slot=None, n_nodes=0, node_rank=None):
         self.idx, self.w, self.n_bx, self.n_by, self.px, self.py = idx, w, n_bx, n_by, px, py
         self.idx_slot = idx_slot
+        self.node_rank = node_rank          # rank of every node in a spatial (Morton) sort: orders the slots inside a tile
         self.n_patches = n_bx * n_by
         self.n_nodes = n_nodes
         self._tile_plans = {}
@@ -144,12 +145,21 @@ class PatchTable:
             uniq, inv = torch.unique(key.reshape(-1), return_inverse=True)                    # sorted: tile-major, node ids ascending
             n_valid = int((uniq < sentinel).sum().item())
             u_tile = uniq[:n_valid] // N
+            node_u = uniq[:n_valid] % N
             counts = torch.bincount(u_tile, minlength=n_tiles)
             node_off = torch.cumsum(counts, 0) - counts
+            # slots inside a tile follow a spatial (Morton) order of the nodes, not their ids: on a mesh numbered row by row the
+            # nodes of neighbouring columns would sit a whole column apart, i.e. in the same bank group again and again
+            if self.node_rank is not None and n_valid:
+                sorder = torch.argsort(u_tile * N + self.node_rank[node_u].long(), stable=True)
+                pos_of = torch.empty_like(sorder)
+                pos_of[sorder] = torch.arange(n_valid, device=dev)
+                pos_of = torch.cat([pos_of, torch.full((uniq.numel() - n_valid,), n_valid, dtype=pos_of.dtype, device=dev)])
+                inv = pos_of[inv]
+                u_tile, node_u = u_tile[sorder], node_u[sorder]
             local = (inv.reshape(-1, 3) - node_off[tile_px].unsqueeze(1)) * 16                  # byte offset of the node's record
             idx_tile = torch.cat([torch.where(inside.unsqueeze(1), local, torch.zeros_like(local)).to(torch.int32),
                                   self.idx[:, 3:4]], dim=1).contiguous()
-            node_u = uniq[:n_valid] % N
             tile_nodes = node_u.to(torch.int32).contiguous()
             # per tile the quads (4 consecutive node ids) that hold its nodes, and per quad the slots of its nodes
             NQ = (N + 3) // 4 + 1
@@ -380,7 +390,7 @@ class MeshPlan:
                 check(lib.fl_plan_patch_table(ptr(self.cell_idx_d), ptr(self.cell_w_d), self.nx, self.ny, px, py, key[2],
                                               flags, ptr(idx), ptr(w), ctypes.byref(nbx), ctypes.byref(nby),
                                               ptr(self.node_slot_d), ptr(idx_slot), stream_ptr()), "fl_plan_patch_table")
-            tab = PatchTable(idx, w, nbx.value, nby.value, px, py, idx_slot, self.n_nodes)
+            tab = PatchTable(idx, w, nbx.value, nby.value, px, py, idx_slot, self.n_nodes, self.node_slot_d[:self.n_nodes])
             self._tables[key] = tab
         return tab
 
