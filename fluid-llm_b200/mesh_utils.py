@@ -93,6 +93,55 @@ def choose_tile_patches(n_patches, n_nodes, ppx):
     return max(1, min((12 if dense else 14) // wpp, n_patches))
 
 
+def colour_entries(ent, n_entries, tile_of, n_tiles, n_colours=8, rounds=24, seed=0):
+    """Bank-group colouring of the tiles' node entries.  ent: int64 [P, 3] = entry (tile-local node) of every output pixel's
+    three vertices, n_entries for pixels outside the mesh; pixels in output order, P a multiple of 32, patch rows of 16.
+    A gather instruction's quarter-warp serves a 2 x 4 block of pixels (csrc/fl_tiled.cu: lane permutation) and reads the
+    k-th vertex of each: entries read by the same quarter-warp instruction should get different colours (= slot mod 8 = bank
+    group).  Jones-Plassmann style: in every round the uncoloured entries whose random priority beats all their uncoloured
+    neighbours take, among the colours no neighbour holds, the one their TILE has used least (tile_of: tile of every entry), so
+    that a tile's colours stay balanced and its slot list short.  -> int64 [n_entries] colours (entries that found no free
+    colour keep the one their fewest neighbours hold)."""
+    dev = ent.device
+    P = ent.shape[0]
+    blocks = ent.view(P // 32, 2, 4, 4, 3).permute(0, 2, 4, 1, 3).reshape(-1, 8)          # [block x k, 8 lanes]
+    ii, jj = torch.triu_indices(8, 8, offset=1, device=dev)
+    a, b = blocks[:, ii].reshape(-1), blocks[:, jj].reshape(-1)
+    ok = (a != b) & (a < n_entries) & (b < n_entries)
+    a, b = a[ok], b[ok]
+    if a.numel():
+        e = torch.unique(torch.minimum(a, b) * n_entries + torch.maximum(a, b))
+        a, b = e // n_entries, e % n_entries
+    src, dst = torch.cat([a, b]), torch.cat([b, a])                                           # both directions
+    g = torch.Generator(device=dev).manual_seed(seed)
+    prio = torch.rand(n_entries, generator=g, device=dev, dtype=torch.float64)
+    colour = torch.full((n_entries,), -1, dtype=torch.int64, device=dev)
+    used = torch.zeros((n_entries, n_colours), dtype=torch.int32, device=dev)               # neighbours holding each colour
+    load = torch.zeros((n_tiles, n_colours), dtype=torch.int64, device=dev)
+    for _ in range(rounds):
+        un = colour < 0
+        if not bool(un.any()):
+            break
+        # highest priority among uncoloured neighbours
+        nb = torch.where(un[src], prio[src], torch.full((1,), -1.0, dtype=torch.float64, device=dev))
+        best = torch.full((n_entries,), -1.0, dtype=torch.float64, device=dev).scatter_reduce(0, dst, nb, "amax", include_self=True)
+        pick = un & (prio > best)
+        idx = torch.nonzero(pick).squeeze(1)
+        if idx.numel() == 0:
+            break
+        # free colours first (fewest neighbours holding it), ties to the least-loaded colour
+        score = used[idx].long() * (1 << 40) + load[tile_of[idx]]
+        c = torch.argmin(score, dim=1)
+        colour[idx] = c
+        load.index_put_((tile_of[idx], c), torch.ones(idx.numel(), dtype=torch.int64, device=dev), accumulate=True)
+        m = pick[src]
+        used.index_put_((dst[m], colour[src[m]]), torch.ones(int(m.sum().item()), dtype=torch.int32, device=dev), accumulate=True)
+    rest = torch.nonzero(colour < 0).squeeze(1)
+    if rest.numel():
+        colour[rest] = torch.argmin(used[rest].long() * (1 << 40) + load[tile_of[rest]], dim=1)
+    return colour
+
+
 class TilePlan:
     """The patch table split into tiles for csrc/fl_tiled.cu (FlTraj::d_idx_tile, d_tile_*)."""
 
@@ -127,6 +176,8 @@ class PatchTable:
             return plan
         dev = self.idx.device
         L, ppx, N = self.n_patches, self.px * self.py, max(int(self.n_nodes), 1)
+        P_total = L * ppx
+        colour_slots = os.environ.get("FLUIDGRID_COLOUR_SLOTS", "1") != "0"
         order = serpentine_patches(self.n_bx, self.n_by)
         sizes = tile_sizes(L, tp)
         n_tiles = len(sizes)
@@ -148,8 +199,9 @@ class PatchTable:
             node_u = uniq[:n_valid] % N
             counts = torch.bincount(u_tile, minlength=n_tiles)
             node_off = torch.cumsum(counts, 0) - counts
-            # slots inside a tile follow a spatial (Morton) order of the nodes, not their ids: on a mesh numbered row by row the
-            # nodes of neighbouring columns would sit a whole column apart, i.e. in the same bank group again and again
+            # Slots inside a tile.  (1) A spatial (Morton) order of the nodes, not their ids: on a mesh numbered row by row the
+            # nodes of neighbouring columns would sit a whole column apart, i.e. in the same bank group again and again.
+            real = None
             if self.node_rank is not None and n_valid:
                 sorder = torch.argsort(u_tile * N + self.node_rank[node_u].long(), stable=True)
                 pos_of = torch.empty_like(sorder)
@@ -157,13 +209,65 @@ class PatchTable:
                 pos_of = torch.cat([pos_of, torch.full((uniq.numel() - n_valid,), n_valid, dtype=pos_of.dtype, device=dev)])
                 inv = pos_of[inv]
                 u_tile, node_u = u_tile[sorder], node_u[sorder]
+            # (2) On top of that, bank groups by colouring: entries that one quarter-warp gather reads together get different
+            # slot mod 8; the r-th entry of a (tile, colour) in Morton order sits at slot 8 r + colour.  A tile's list is as long
+            # as its fullest colour needs; unused slots repeat the tile's first node (staged, never gathered).
+            if colour_slots and n_valid and P_total % 32 == 0 and self.py == 16:
+                col = colour_entries(inv.reshape(-1, 3), n_valid, u_tile, n_tiles)
+
+                def rank_in(key):            # position of every entry inside its run of equal keys, Morton order kept
+                    o = torch.argsort(key, stable=True)
+                    _, cnt = torch.unique_consecutive(key[o], return_counts=True)
+                    start = torch.cumsum(cnt, 0) - cnt
+                    r = torch.empty(n_valid, dtype=torch.int64, device=dev)
+                    r[o] = torch.arange(n_valid, device=dev) - torch.repeat_interleave(start, cnt)
+                    return r
+                # every colour of a tile holds at most cap = ceil(n / 8) entries, so that the list is no longer than n + 7: the
+                # entries beyond cap move, in order, into the free places of the tile's other colours (a few conflicts come back)
+                cap = (counts + 7) // 8
+                r_in = rank_in(u_tile * 8 + col)
+                excess = r_in >= cap[u_tile]
+                if bool(excess.any()):
+                    per = torch.zeros((n_tiles, 8), dtype=torch.int64, device=dev)
+                    per.index_put_((u_tile, col), torch.ones(n_valid, dtype=torch.int64, device=dev), accumulate=True)
+                    free = (cap.unsqueeze(1) - per).clamp(min=0)                          # [tile, colour] places left
+                    # the j-th excess entry of a tile takes the j-th free place of the tile (colours in order)
+                    ex_idx = torch.nonzero(excess).squeeze(1)
+                    j = rank_in(torch.where(excess, u_tile, torch.full_like(u_tile, n_tiles)))[ex_idx]
+                    cum = torch.cumsum(free, dim=1)                                       # [tile, 8]
+                    tgt = torch.searchsorted(cum[u_tile[ex_idx]].contiguous(), j.unsqueeze(1), right=True).squeeze(1).clamp(max=7)
+                    col = col.clone()
+                    col[ex_idx] = tgt
+                    r_in = rank_in(u_tile * 8 + col)
+                slot = 8 * r_in + col
+                need = torch.zeros(n_tiles, dtype=torch.int64, device=dev).scatter_reduce(0, u_tile, slot + 1, "amax", include_self=True)
+                if int(need.max().item()) <= int(1.25 * counts.max().item()) + 8:      # (badly unbalanced colours: keep plain Morton)
+                    new_off = torch.cumsum(need, 0) - need
+                    total = int(need.sum().item())
+                    first_node = torch.zeros(n_tiles, dtype=torch.int64, device=dev)
+                    first_node[u_tile.flip(0)] = node_u.flip(0)
+                    nodes_full = torch.repeat_interleave(first_node, need)
+                    gpos = new_off[u_tile] + slot
+                    nodes_full[gpos] = node_u
+                    place = torch.cat([gpos, torch.full((uniq.numel() - n_valid,), total, dtype=torch.int64, device=dev)])
+                    inv = place[inv]
+                    real = torch.zeros(total, dtype=torch.bool, device=dev)
+                    real[gpos] = True
+                    u_tile = torch.repeat_interleave(torch.arange(n_tiles, device=dev), need)
+                    node_u = nodes_full
+                    counts, node_off, n_valid = need, new_off, total
             local = (inv.reshape(-1, 3) - node_off[tile_px].unsqueeze(1)) * 16                  # byte offset of the node's record
             idx_tile = torch.cat([torch.where(inside.unsqueeze(1), local, torch.zeros_like(local)).to(torch.int32),
                                   self.idx[:, 3:4]], dim=1).contiguous()
             tile_nodes = node_u.to(torch.int32).contiguous()
             # per tile the quads (4 consecutive node ids) that hold its nodes, and per quad the slots of its nodes
             NQ = (N + 3) // 4 + 1
-            qkey = u_tile * NQ + node_u // 4
+            if real is not None:                     # the quad lists describe the real nodes only (holes are never staged by quads)
+                keep = torch.nonzero(real).squeeze(1)
+                q_ut, q_nu, q_local = u_tile[keep], node_u[keep], (keep - node_off[u_tile[keep]])
+            else:
+                q_ut, q_nu, q_local = u_tile, node_u, torch.arange(n_valid, device=dev) - node_off[u_tile]
+            qkey = q_ut * NQ + q_nu // 4
             uq, qinv = torch.unique(qkey, return_inverse=True)
             q_tile = uq // NQ
             tile_quads = (uq % NQ).to(torch.int32).contiguous()
@@ -172,8 +276,7 @@ class PatchTable:
             q_max = torch.zeros(n_tiles, dtype=torch.int64, device=dev).scatter_reduce(0, q_tile, uq % NQ + 1, "amax", include_self=True)
             qslots = torch.full((max(int(uq.numel()), 1) * 4,), -1, dtype=torch.int32, device=dev)
             if n_valid:
-                local_u = torch.arange(n_valid, device=dev) - node_off[u_tile]
-                qslots[qinv * 4 + node_u % 4] = local_u.to(torch.int32)
+                qslots[qinv * 4 + q_nu % 4] = q_local.to(torch.int32)
             if tile_quads.numel() == 0:
                 tile_quads = torch.zeros(4, dtype=torch.int32, device=dev)
             if tile_nodes.numel() == 0:
