@@ -154,11 +154,15 @@ class TrajBatch:
             tp = int(tile_patches) if tile_patches else biggest.default_tile_patches()
             self.tile_plans = [tab.tile_plan(tp) for tab in tables]
         arr = (FlTraj * self.n_traj)()
+        colour = os.environ.get("FLUIDGRID_COLOUR_STAGED", "0") == "1" and ppx % 32 == 0 and py == 16
         for i, (tr, tab, t0) in enumerate(zip(trajs, tables, t0s)):
             tpl = self.tile_plans[i] if self.tile_plans else None
+            idx_slot, node_slot = tab.idx_slot, tr.plan.node_slot_d
+            if colour and use_slots and idx_slot is not None and tpl is None:
+                node_slot, idx_slot = tab.coloured_slots(tr.prs_stride)
             arr[i] = FlTraj(tr.vel_buf.data_ptr(), tr.prs_buf.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(),
-                            tab.idx_slot.data_ptr() if use_slots and tab.idx_slot is not None else 0,
-                            tr.plan.node_slot_d.data_ptr() if use_slots and tab.idx_slot is not None else 0,
+                            idx_slot.data_ptr() if use_slots and idx_slot is not None else 0,
+                            node_slot.data_ptr() if use_slots and idx_slot is not None else 0,
                             self.states[i].data_ptr(), self.mask[i].data_ptr() if want_mask else 0,
                             tr.plan.n_nodes, int(t0), int(interval), self.n_frames, tr.vel_stride, tr.prs_stride,
                             tpl.idx_tile.data_ptr() if tpl else 0, tpl.tile_nodes.data_ptr() if tpl else 0,

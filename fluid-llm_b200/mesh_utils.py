@@ -163,6 +163,52 @@ class PatchTable:
         self.n_nodes = n_nodes
         self._tile_plans = {}
 
+    def coloured_slots(self, n_slots):
+        """Shared-memory slots of the whole mesh's nodes for the staged kernel, by bank-group colouring instead of the plan's
+        Morton order: -> (node_slot int32 [n_slots], idx_slot int32 [P, 4]).  Nodes that one quarter-warp gather reads together
+        get different slot mod 8 where eight colours allow it; colour c owns the slots c, c + 8, ... below n_slots, so the
+        records still fit the frame pitch.  n_slots = the padded node count (FlTraj::prs_stride)."""
+        key = ("coloured", int(n_slots))
+        got = self._tile_plans.get(key)
+        if got is not None:
+            return got
+        dev = self.idx.device
+        P = self.idx.shape[0]
+        if P % 32 or self.py != 16 or n_slots < self.n_nodes:
+            raise ValueError("coloured_slots: needs 16-pixel patch rows and n_slots >= n_nodes")
+        inside = self.idx[:, 3] >= 0
+        ent = torch.where(inside.unsqueeze(1), self.idx[:, :3].long(), torch.full((1, 1), n_slots, dtype=torch.int64, device=dev))
+        zero = torch.zeros(n_slots, dtype=torch.int64, device=dev)
+        col = colour_entries(ent.contiguous(), n_slots, zero, 1)
+        rank = self.node_rank.long() if self.node_rank is not None else torch.arange(self.n_nodes, device=dev)
+        order_key = torch.cat([rank, torch.arange(self.n_nodes, n_slots, device=dev)])         # Morton order inside a colour, pads last
+        cap = (n_slots - torch.arange(8, device=dev) + 7) // 8                                     # slots congruent to c below n_slots
+
+        def rank_in(c):
+            o = torch.argsort(order_key, stable=True)
+            o = o[torch.argsort(c[o], stable=True)]
+            _, cnt = torch.unique_consecutive(c[o], return_counts=True)
+            start = torch.cumsum(cnt, 0) - cnt
+            r = torch.empty(n_slots, dtype=torch.int64, device=dev)
+            r[o] = torch.arange(n_slots, device=dev) - torch.repeat_interleave(start, cnt)
+            return r
+        r_in = rank_in(col)
+        excess = r_in >= cap[col]
+        if bool(excess.any()):
+            per = torch.bincount(col, minlength=8)
+            free = (cap - per).clamp(min=0)
+            ex_idx = torch.nonzero(excess).squeeze(1)
+            j = torch.arange(ex_idx.numel(), device=dev)
+            tgt = torch.searchsorted(torch.cumsum(free, 0), j, right=True).clamp(max=7)
+            col = col.clone()
+            col[ex_idx] = tgt
+            r_in = rank_in(col)
+        node_slot = (8 * r_in + col).to(torch.int32)
+        idx_slot = torch.cat([torch.where(inside.unsqueeze(1), node_slot[self.idx[:, :3].clamp(min=0, max=n_slots - 1).long()], self.idx[:, :3]),
+                              self.idx[:, 3:4]], dim=1).contiguous()
+        self._tile_plans[key] = (node_slot.contiguous(), idx_slot)
+        return self._tile_plans[key]
+
     def default_tile_patches(self):
         return choose_tile_patches(self.n_patches, self.n_nodes, self.px * self.py)
 
