@@ -454,8 +454,17 @@ def dataset_e2e(dev, n_files=8, n_samples=64, seq_len=10):
         ds = MGNDataset(tmp, RES, PATCH, PATCH, seq_len, mode="valid", device=dev)
         for i in range(n_files):
             ds.ds_get(i, 0)
-        out["resident_one_sample_per_call"] = timed(lambda: [ds.ds_get(fi, step) for fi, step in order])
-        out["resident_batches_of_8"] = timed(lambda: [ds.ds_get_many(order[i:i + 8]) for i in range(0, n_samples, 8)])
+        def one_by_one():                   # (samples are dropped as a consumer would: keeping all of them alive times cudaMalloc)
+            for fi, step in order:
+                ds.ds_get(fi, step)
+
+        def in_batches():
+            for i in range(0, n_samples, 8):
+                ds.ds_get_many(order[i:i + 8])
+        one_by_one()
+        out["resident_one_sample_per_call"] = timed(one_by_one)
+        in_batches()
+        out["resident_batches_of_8"] = timed(in_batches)
         if ds._ingest is not None:
             ds._ingest.close()
         return out
