@@ -16,6 +16,7 @@ FL_FORCE_GATHER = 8
 FL_FORCE_STAGED = 16
 FL_FORCE_TILED = 32
 FL_FORCE_RING = 64
+FL_NO_PAD = 128
 
 
 class FlTraj(ctypes.Structure):
@@ -42,7 +43,7 @@ SIGNATURES = {
                           c_void_p, c_void_p, c_size_t, c_void_p]),
     "fl_locate_async": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
-    "fl_plan_patch_table": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_uint, c_void_p, c_void_p,
+    "fl_plan_patch_table": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_uint, c_void_p, c_void_p,
                                     POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p]),
     "fl_interp_patchify": (c_int, [POINTER(FlTraj), c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                    c_uint, c_void_p]),

@@ -136,7 +136,7 @@ __global__ void k_locate(const float* __restrict__ pos, const int* __restrict__ 
 }
 
 __global__ void k_plan_patch_table(const FlCellIdx* __restrict__ cell_idx, const FlCellW* __restrict__ cell_w, int nx,
-                                   int ny, int px, int py, int n_bx, int n_by, int crop, int pad_x0, int pad_y0,
+                                   int ny, int px, int py, int sx, int sy, int n_bx, int n_by, int crop, int pad_x0, int pad_y0,
                                    int padded_ny, int flip_y, FlCellIdx* __restrict__ out_idx,
                                    FlCellW* __restrict__ out_w, const int* __restrict__ node_slot, FlCellIdx* __restrict__ out_idx_slot) {
     int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,7 +144,7 @@ __global__ void k_plan_patch_table(const FlCellIdx* __restrict__ cell_idx, const
     if (o >= total) return;
     int j = o % py, i = (o / py) % px, l = o / (px * py);
     int bx = l / n_by, by = l - bx * n_by;
-    int X = (bx + crop) * px + i, Y = (by + crop) * py + j;       // padded image coordinates
+    int X = crop * px + bx * sx + i, Y = crop * py + by * sy + j; // padded image coordinates: `crop` patch sizes of pixels cut, then unfold
     if (flip_y) Y = padded_ny - 1 - Y;                             // airfoil_ds.py:80
     int ix = X - pad_x0, iy = Y - pad_y0;
     FlCellIdx rec{0, 0, 0, -1};
@@ -237,11 +237,17 @@ extern "C" int fl_locate_async(const float* d_pos, const int32_t* d_cells, int n
 }
 
 extern "C" int fl_plan_patch_table(const FlCellIdx* d_cell_idx, const FlCellW* d_cell_w, int nx, int ny, int px, int py,
-                                   int crop_patches, unsigned flags, FlCellIdx* d_out_idx, FlCellW* d_out_w,
+                                   int sx, int sy, int crop_patches, unsigned flags, FlCellIdx* d_out_idx, FlCellW* d_out_w,
                                    int* h_n_bx, int* h_n_by, const int32_t* d_node_slot, FlCellIdx* d_out_idx_slot, void* stream) {
-    FL_REQUIRE(nx > 0 && ny > 0 && px > 0 && py > 0 && crop_patches >= 0, FL_E_ARG, "fl_plan_patch_table: bad sizes");
-    int pad_x = ((-nx) % px + px) % px, pad_y = ((-ny) % py + py) % py;   // simple_dataloader.py:140-141
-    int n_bx = (nx + pad_x) / px - 2 * crop_patches, n_by = (ny + pad_y) / py - 2 * crop_patches;
+    FL_REQUIRE(nx > 0 && ny > 0 && px > 0 && py > 0 && sx >= 0 && sy >= 0 && crop_patches >= 0, FL_E_ARG, "fl_plan_patch_table: bad sizes");
+    if (sx == 0) sx = px;
+    if (sy == 0) sy = py;
+    int pad_x = 0, pad_y = 0;
+    if (!(flags & FL_NO_PAD)) { pad_x = ((-nx) % px + px) % px; pad_y = ((-ny) % py + py) % py; }   // simple_dataloader.py:140-141
+    // F.unfold over what is left after `crop_patches` patch sizes of pixels are cut from every side (airfoil_ds.py:132-135):
+    // floor((extent - patch) / stride) + 1 windows, none when the extent is shorter than a patch
+    int ext_x = nx + pad_x - 2 * crop_patches * px, ext_y = ny + pad_y - 2 * crop_patches * py;
+    int n_bx = ext_x >= px ? (ext_x - px) / sx + 1 : 0, n_by = ext_y >= py ? (ext_y - py) / sy + 1 : 0;
     if (h_n_bx) *h_n_bx = n_bx;
     if (h_n_by) *h_n_by = n_by;
     if (!d_out_idx && !d_out_w) return FL_OK;   // size query
@@ -251,7 +257,7 @@ extern "C" int fl_plan_patch_table(const FlCellIdx* d_cell_idx, const FlCellW* d
     long total = (long)n_bx * n_by * px * py;
     FL_REQUIRE(total < 0x7fffffffL, FL_E_ARG, "fl_plan_patch_table: too many pixels");
     k_plan_patch_table<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        d_cell_idx, d_cell_w, nx, ny, px, py, n_bx, n_by, crop_patches, pad_x / 2, pad_y / 2, ny + pad_y,
+        d_cell_idx, d_cell_w, nx, ny, px, py, sx, sy, n_bx, n_by, crop_patches, pad_x / 2, pad_y / 2, ny + pad_y,
         (flags & FL_FLIP_Y) ? 1 : 0, d_out_idx, d_out_w, d_node_slot, d_out_idx_slot);
     FL_LAUNCH_CHECK();
     return FL_OK;

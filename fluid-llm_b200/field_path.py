@@ -193,11 +193,11 @@ class TrajBatch:
 
 def interp_patchify(traj: DeviceTrajectory, step_num: int, seq_len: int, seq_interval: int, patch_size,
                     personality: Personality, normalize=True, means=None, stds=None, force_gather=False, force_staged=False,
-                    tile_patches=None, force_ring=False):
+                    tile_patches=None, force_ring=False, stride=None, pad=True):
     """One trajectory, frames step_num, step_num+interval, ... -> (states (T,L,3,px,py) f32,
-    mask (T,L,px,py) u8, table)."""
+    mask (T,L,px,py) u8, table).  `stride` / `pad`: the data sets' unfold stride (default: the patch size) and padding switch."""
     _lib.require_cuda()
-    tab = traj.plan.patch_table(patch_size, personality.crop_patches, personality.flip_y)
+    tab = traj.plan.patch_table(patch_size, personality.crop_patches, personality.flip_y, stride, pad)
     batch = TrajBatch([traj], [tab], [step_num], seq_interval, seq_len, tile_patches=tile_patches)
     states, mask = batch.run(personality, normalize, means, stds, force_gather, force_staged, force_ring)
     return states[0], mask[0], tab

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import FL_FLIP_Y, check, load, ptr, stream_ptr
+from ._lib import FL_FLIP_Y, FL_NO_PAD, check, load, ptr, stream_ptr
 
 F32, F64 = np.float32, np.float64
 
@@ -518,25 +518,30 @@ class MeshPlan:
             self._tri_index_host = self.tri_index_d.cpu().numpy()
         return self._tri_index_host
 
-    def patch_table(self, patch_size, crop_patches=0, flip_y=False) -> PatchTable:
-        key = (int(patch_size[0]), int(patch_size[1]), int(crop_patches), bool(flip_y))
+    def patch_table(self, patch_size, crop_patches=0, flip_y=False, stride=None, pad=True) -> PatchTable:
+        """The static table in output-pixel order.  `stride` (default: the patch size) and `pad` are the data sets' arguments of
+        the same names (simple_dataloader.py:26-27,118-119,131): they only change which grid pixel an output pixel reads."""
+        stride = patch_size if stride is None else stride
+        key = (int(patch_size[0]), int(patch_size[1]), int(crop_patches), bool(flip_y), int(stride[0]), int(stride[1]), bool(pad))
+        if key[4] < 1 or key[5] < 1:
+            raise ValueError(f"stride must be positive, got {tuple(stride)}")
         tab = self._tables.get(key)
         if tab is None:
-            px, py = key[0], key[1]
+            px, py, sx, sy = key[0], key[1], key[4], key[5]
             lib = load()
             nbx, nby = ctypes.c_int(0), ctypes.c_int(0)
-            flags = FL_FLIP_Y if flip_y else 0
-            check(lib.fl_plan_patch_table(None, None, self.nx, self.ny, px, py, key[2], flags, None, None,
+            flags = (FL_FLIP_Y if flip_y else 0) | (0 if pad else FL_NO_PAD)
+            check(lib.fl_plan_patch_table(None, None, self.nx, self.ny, px, py, sx, sy, key[2], flags, None, None,
                                           ctypes.byref(nbx), ctypes.byref(nby), None, None, None), "fl_plan_patch_table")
             if nbx.value < 1 or nby.value < 1:
-                raise ValueError(f"no patches left: grid {self.nx}x{self.ny}, patch {px}x{py}, crop {key[2]}")
+                raise ValueError(f"no patches left: grid {self.nx}x{self.ny}, patch {px}x{py}, stride {sx}x{sy}, crop {key[2]}, pad {pad}")
             total = nbx.value * nby.value * px * py
             with torch.cuda.device(self.device):
                 idx = torch.empty((total, 4), dtype=torch.int32, device=self.device)
                 idx_slot = torch.empty((total, 4), dtype=torch.int32, device=self.device)
                 w = torch.empty((total, 2), dtype=torch.float64, device=self.device)
                 # the table in output-pixel order, and the same with node ids as shared-memory slots, in one launch
-                check(lib.fl_plan_patch_table(ptr(self.cell_idx_d), ptr(self.cell_w_d), self.nx, self.ny, px, py, key[2],
+                check(lib.fl_plan_patch_table(ptr(self.cell_idx_d), ptr(self.cell_w_d), self.nx, self.ny, px, py, sx, sy, key[2],
                                               flags, ptr(idx), ptr(w), ctypes.byref(nbx), ctypes.byref(nby),
                                               ptr(self.node_slot_d), ptr(idx_slot), stream_ptr()), "fl_plan_patch_table")
             tab = PatchTable(idx, w, nbx.value, nby.value, px, py, idx_slot, self.n_nodes, self.node_slot_d[:self.n_nodes])

@@ -20,7 +20,7 @@ from torch.utils.data import Dataset
 
 from ._lib import check, load, ptr, stream_ptr
 from .field_path import TrajBatch, CYLINDER, DeviceTrajectory, Personality, interp_patchify
-from .mesh_utils import MeshPlan
+from .mesh_utils import MeshPlan, to_grid
 from .traj_store import PinnedStage, TrajectoryFile
 
 
@@ -70,10 +70,8 @@ class _GpuFieldDataset(Dataset):
                  numpy_semantics=None):
         super().__init__()
         assert mode in ["train", "valid", "test"]
-        if tuple(patch_size) != tuple(stride):
-            raise ValueError("the GPU data path patchifies with stride == patch_size (as the reference's configs do)")
-        if not pad:
-            raise ValueError("pad=False is not supported: the reference's unfold would silently drop the remainder")
+        if len(patch_size) != 2 or len(stride) != 2 or min(*patch_size, *stride) < 1:
+            raise ValueError(f"patch_size and stride must be pairs of positive ints, got {patch_size}, {stride}")
         self.mode = mode
         self.load_dir = load_dir
         self.resolution = resolution
@@ -104,12 +102,28 @@ class _GpuFieldDataset(Dataset):
         # ... min / max over the whole padded frame, BEFORE the airfoil's ring crop (airfoil_ds.py:46-50): no crop here
         full = Personality(self.personality.name, self.personality.flip_y, 0, self.personality.mask_aware_norm,
                            self.personality.means, self.personality.stds)
-        states, _, _ = interp_patchify(traj, 20, 1, 1, self.patch_size, full, normalize=False)
+        # (the frame tiled without overlap or gaps -- stride = patch -- so that every pixel of it is seen exactly once)
+        states, _, _ = interp_patchify(traj, 20, 1, 1, self.patch_size, full, normalize=False, pad=self.pad)
         lo, hi = states[0].amin(dim=(0, 2, 3)).cpu().numpy(), states[0].amax(dim=(0, 2, 3)).cpu().numpy()
+        if not self.pad:                        # unfold dropped the remainder columns / rows: the plain gridded frame instead
+            plan = traj.plan
+            fields = torch.stack([traj.velocity[20, :, 0], traj.velocity[20, :, 1], traj.pressure[20, :, 0]])
+            grid, _ = to_grid(fields, plan.grid_x, plan.grid_y, plan, plan.tri_index)
+            lo, hi = grid.amin(dim=(1, 2)).cpu().numpy(), grid.amax(dim=(1, 2)).cpu().numpy()
         self.ds_min_max = [(lo[0], hi[0]), (lo[1], hi[1]), (lo[2], hi[2])]
-        tab = traj.plan.patch_table(self.patch_size, self.personality.crop_patches, self.personality.flip_y)
-        self.N_x_patch, self.N_y_patch = tab.n_bx, tab.n_by
+        self._table_of(traj.plan)               # refuses a patch / stride / pad combination that leaves no patches
+        # simple_dataloader.py:52-56 / airfoil_ds.py:52-55: patches per axis of the frame BEFORE the airfoil's ring crop, minus
+        # two for the airfoil -- which is the number of patches unfold produces only when stride == patch_size; the reference's
+        # attributes (and the position ids made from them) are reproduced as they are
+        nx_full = traj.plan.nx + ((-traj.plan.nx) % self.patch_size[0] if self.pad else 0)
+        ny_full = traj.plan.ny + ((-traj.plan.ny) % self.patch_size[1] if self.pad else 0)
+        ring = 2 * self.personality.crop_patches
+        self.N_x_patch = num_patches(nx_full, self.patch_size[0], self.stride[0]) - ring
+        self.N_y_patch = num_patches(ny_full, self.patch_size[1], self.stride[1]) - ring
         self.N_patch = self.N_x_patch * self.N_y_patch
+
+    def _table_of(self, plan):
+        return plan.patch_table(self.patch_size, self.personality.crop_patches, self.personality.flip_y, self.stride, self.pad)
 
     # -- file handling ----------------------------------------------------------------------
     def _list_files(self):
@@ -283,7 +297,7 @@ class _GpuFieldDataset(Dataset):
             step_num = self.max_step_num
         traj, local_step = self._load_window(save_file, step_num)
         states, mask, _ = interp_patchify(traj, local_step, self.seq_len, self.seq_interval, self.patch_size,
-                                          self.personality, normalize=self.normalize)
+                                          self.personality, normalize=self.normalize, stride=self.stride, pad=self.pad)
         diffs, masks = sample_assemble(states.unsqueeze(0), mask.unsqueeze(0))       # :93, :100 in one launch
         if not self._verify_plans():            # (everything above is enqueued by now: this wait overlaps the GPU work)
             return self.ds_get(save_file, step_num)
@@ -306,7 +320,7 @@ class _GpuFieldDataset(Dataset):
             traj, local_step = self._load_window(save_file, step_num)
             trajs.append(traj)
             steps.append(local_step)
-        tabs = [t.plan.patch_table(self.patch_size, self.personality.crop_patches, self.personality.flip_y) for t in trajs]
+        tabs = [self._table_of(t.plan) for t in trajs]
         batch = TrajBatch(trajs, tabs, steps, self.seq_interval, self.seq_len)
         states, mask = batch.run(self.personality, self.normalize)     # (B, T, L, 3, px, py), (B, T, L, px, py)
         diffs, masks = sample_assemble(states, mask)

@@ -32,7 +32,7 @@ extern "C" {
 #define FL_E_WORKSPACE (-3)/* workspace too small */
 #define FL_E_ALIGN (-4)    /* pointer not aligned as documented */
 
-#define FL_ABI_VERSION 8
+#define FL_ABI_VERSION 9
 
 /* personality flags of fl_plan_patch_table / fl_interp_patchify */
 #define FL_FLIP_Y 1u          /* airfoil_ds.py:80  -- y axis reversed after padding */
@@ -41,6 +41,7 @@ extern "C" {
 #define FL_FORCE_GATHER 8u    /* testing: always the gather-from-global kernel */
 #define FL_FORCE_STAGED 16u   /* testing: ignore the tile plan (whole-mesh staged kernel, or the gather kernel) */
 #define FL_FORCE_TILED 32u    /* testing: with a tile plan, always the node-list kernel (fl_tiled.cu) */
+#define FL_NO_PAD 128u        /* fl_plan_patch_table: pad=False (simple_dataloader.py:118-119) */
 #define FL_FORCE_RING 64u     /* testing: with a tile plan of <= 6 patches (px*py = 256) per tile and frames that fit shared memory a few
                                  times over, the experimental frame-ring kernel (fl_ring.cu); otherwise ignored */
 
@@ -90,11 +91,14 @@ int fl_locate_async(const float* d_pos, const int32_t* d_cells, int n_nodes, int
  * (airfoil_ds.py:80), optional removal of `crop` outer rings of patches (airfoil_ds.py:132-133).
  * Output index = (l*px + i)*py + j with l = bx*n_by + by (F.unfold order,
  * simple_dataloader.py:131).  Padded pixels get tri = -1.
+ * sx, sy: the unfold stride (simple_dataloader.py:131 `stride=self.stride`; 0 = the patch size): patch (bx, by) starts at
+ * pixel (bx*sx, by*sy) of the padded (and cropped) frame, n_bx = floor((extent - px) / sx) + 1.  FL_NO_PAD (pad=False,
+ * simple_dataloader.py:118): no padding; unfold then drops the remainder columns / rows.
  * d_out_idx/d_out_w: [n_bx*n_by*px*py].  n_bx/n_by are returned through out pointers (host).
  * d_node_slot i32[n_nodes] + d_out_idx_slot (optional, both or neither): also emit the table with node ids replaced by
  * d_node_slot[id] (FlTraj::d_idx_slot). */
 int fl_plan_patch_table(const FlCellIdx* d_cell_idx, const FlCellW* d_cell_w, int nx, int ny,
-                        int px, int py, int crop_patches, unsigned flags,
+                        int px, int py, int sx, int sy, int crop_patches, unsigned flags,
                         FlCellIdx* d_out_idx, FlCellW* d_out_w, int* h_n_bx, int* h_n_by,
                         const int32_t* d_node_slot, FlCellIdx* d_out_idx_slot, void* stream);
 

@@ -170,15 +170,20 @@ def full_seq(traj, step_num, seq_len, seq_interval, resolution, patch_size, pers
     return np.stack(out).astype(F32), tri_index
 
 
-def unfold_patches(img, patch_size):
-    """F.unfold(kernel=stride=patch) + view, simple_dataloader.py:123-135.
+def unfold_patches(img, patch_size, stride=None):
+    """F.unfold(kernel=patch, stride) + view, simple_dataloader.py:123-135.
 
-    img (B, C, X, Y) -> (B, C, px, py, L) with L = (X/px)*(Y/py), l = bx*(Y/py) + by."""
+    img (B, C, X, Y) -> (B, C, px, py, L) with L = nbx*nby, l = bx*nby + by, nb* = floor((extent - patch) / stride) + 1
+    (F.unfold drops what is left over); patch (bx, by) starts at pixel (bx*sx, by*sy)."""
     B, C, X, Y = img.shape
     px, py = patch_size
-    nbx, nby = X // px, Y // py
-    v = img[:, :, :nbx * px, :nby * py].reshape(B, C, nbx, px, nby, py)
-    return np.ascontiguousarray(v.transpose(0, 1, 3, 5, 2, 4)).reshape(B, C, px, py, nbx * nby)
+    sx, sy = patch_size if stride is None else stride
+    nbx, nby = max((X - px) // sx + 1, 0), max((Y - py) // sy + 1, 0)
+    out = np.empty((B, C, px, py, nbx * nby), dtype=img.dtype)
+    for bx in range(nbx):
+        for by in range(nby):
+            out[..., bx * nby + by] = img[:, :, bx * sx:bx * sx + px, by * sy:by * sy + py]
+    return out
 
 
 CYL_MEANS = np.array([0.823, 0.0005865, 0.04763], dtype=F32)       # simple_dataloader.py:205-209
@@ -215,22 +220,28 @@ def get_pos_id(seq_len, n_x_patch, n_y_patch):
 
 def ds_get(traj, step_num, seq_len, seq_interval=1, resolution=238, patch_size=(16, 16),
            personality="cylinder", normalize_ds=True, pad=True, numpy_semantics="1.26",
-           means=None, stds=None, return_all=False):
+           means=None, stds=None, return_all=False, stride=None, n_patch=None):
     """simple_dataloader.py:72-102 / airfoil_ds.py:71-103 -> the 5-tuple (NumPy arrays)."""
     seq, tri_index = full_seq(traj, step_num, seq_len, seq_interval, resolution, patch_size,
                               personality, pad, numpy_semantics)
+    stride = patch_size if stride is None else stride
+    # simple_dataloader.py:52-56 / airfoil_ds.py:52-55: the patch-count attributes come from the uncropped frame (minus 2 for
+    # the airfoil), which is what unfold yields only for stride == patch_size; the position ids are made from the attributes
+    ring = 2 if personality == "airfoil" else 0
+    nxp = num_patches(seq.shape[2], patch_size[0], stride[0]) - ring
+    nyp = num_patches(seq.shape[3], patch_size[1], stride[1]) - ring
+    if n_patch is not None:         # the data set's attributes come from ITS probe file (save_files[1], :46-47), whose unpadded
+        nxp, nyp = n_patch          # grid may differ from this trajectory's: the caller passes them
     if personality == "airfoil":
         seq = np.ascontiguousarray(seq[:, :, :, ::-1])                       # airfoil_ds.py:80
         seq = seq[:, :, patch_size[0]:-patch_size[0], patch_size[1]:-patch_size[1]]  # :132-133
-    patches = unfold_patches(seq, patch_size)                                  # (T, 4, px, py, L)
+    patches = unfold_patches(seq, patch_size, stride)                          # (T, 4, px, py, L)
     states = np.ascontiguousarray(patches[:, :-1].transpose(0, 4, 1, 2, 3))    # (T, L, 3, px, py)
     masks = np.ascontiguousarray(patches[:, -1].transpose(0, 3, 1, 2))         # (T, L, px, py)
     if normalize_ds:
         states = normalize(states, masks, personality, means, stds)
     diffs = (states[1:] - states[:-1]).astype(F32)
     bc = np.repeat(masks[1:, :, None], 3, axis=2).astype(bool)
-    X, Y = seq.shape[2:]
-    nxp, nyp = X // patch_size[0], Y // patch_size[1]
     out = (states[:-1], states[1:], diffs, bc, get_pos_id(seq_len, nxp, nyp))
     if return_all:
         return out, dict(states=states, masks=masks, tri_index=tri_index, N_x_patch=nxp, N_y_patch=nyp)

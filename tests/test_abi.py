@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/fluidgrid.h but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES and the header disagree"
-    assert lib.fl_abi_version() == 8
+    assert lib.fl_abi_version() == 9
 
 
 def test_struct_layout_matches_header():
@@ -41,9 +41,9 @@ def test_argument_errors_without_a_device(lib):
     assert lib.fl_grid2mesh(None, None, None, 1, 1, 1, 1, 1, 0.0, 0.0, 1.0, 1.0, None, None) == -1
     assert lib.fl_interp_patchify(None, 1, 1, 16, 16, None, None, 0, None) == -1
     nbx, nby = ctypes.c_int(), ctypes.c_int()
-    assert lib.fl_plan_patch_table(None, None, 238, 60, 16, 16, 0, 0, None, None, ctypes.byref(nbx), ctypes.byref(nby), None, None, None) == 0
+    assert lib.fl_plan_patch_table(None, None, 238, 60, 16, 16, 0, 0, 0, 0, None, None, ctypes.byref(nbx), ctypes.byref(nby), None, None, None) == 0
     assert (nbx.value, nby.value) == (15, 4)
-    assert lib.fl_plan_patch_table(None, None, 238, 142, 16, 16, 1, 1, None, None, ctypes.byref(nbx), ctypes.byref(nby), None, None, None) == 0
+    assert lib.fl_plan_patch_table(None, None, 238, 142, 16, 16, 0, 0, 1, 1, None, None, ctypes.byref(nbx), ctypes.byref(nby), None, None, None) == 0
     assert (nbx.value, nby.value) == (13, 7)
     with pytest.raises(ValueError):
         _lib.check(-1, "x")

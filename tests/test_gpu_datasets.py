@@ -103,6 +103,53 @@ def test_cuda_path_reproduces_frozen_reference(kind):
     assert np.array_equal(np.repeat(mask.cpu().numpy()[1:, :, None], 3, axis=2).astype(bool), masks)
 
 
+@pytest.mark.parametrize("kind", ["cylinder", "airfoil"])
+def test_datasets_with_other_strides_and_pad_false(kind, tmp_path):
+    """tests/golden/ref_strided.npz: the reference's unmodified data sets with stride != patch_size, pad=False and a
+    non-square patch (oracle/make_golden_strided.py, NumPy 2.x).  The drop-in data sets reproduce every tensor bit for bit,
+    the N_x_patch / N_y_patch attributes (taken from the probe file like the reference's; for the airfoil with
+    stride != patch they are NOT the number of patches unfold yields, and the position ids follow the attributes), ds_min_max,
+    and agree with the oracle in the pinned NumPy 1.26 semantics; one batched call equals the per-sample calls."""
+    import hashlib
+    from fluid_llm_b200.airfoil_ds import AirfoilDataset
+    from fluid_llm_b200.simple_dataloader import MGNDataset
+    fix = np.load(os.path.join(GOLDEN, "ref_strided.npz"))
+    trajs = [trajectory(kind, 30, s, 10 + s) for s in (0, 1)]
+    g = np.load(os.path.join(GOLDEN, f"ref_{kind}.npz"))
+    assert np.array_equal(trajs[0]["mesh_pos"], g["mesh_pos"]) and np.array_equal(trajs[0]["velocity"][:8], g["velocity"])
+    d = _write(tmp_path, copy.deepcopy(trajs))
+    DS = MGNDataset if kind == "cylinder" else AirfoilDataset
+    for ci, case in enumerate(fix["cases"]):
+        patch, stride, pad = tuple(int(v) for v in case[:2]), tuple(int(v) for v in case[2:4]), bool(case[4])
+        k = f"{kind}_{ci}"
+        ds = DS(load_dir=d, resolution=238, patch_size=patch, stride=stride, seq_len=3, seq_interval=2, pad=pad, mode="valid",
+                numpy_semantics="2.x")
+        ds.max_step_num = 10
+        assert (ds.N_x_patch, ds.N_y_patch) == tuple(fix[k + "_n_patch"]), k
+        assert np.array_equal(np.array(ds.ds_min_max, dtype=np.float32), fix[k + "_min_max"]), k
+        got = [t.cpu().numpy() for t in ds.ds_get(ds.save_files[0], 1)]
+        for t, shape, digest in zip(got, fix[k + "_shapes"], fix[k + "_sha256"]):
+            assert list(t.shape) == [int(v) for v in shape[:t.ndim]], k
+            assert hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest() == str(digest), k
+        many = ds.ds_get_many([(0, 1), (1, 3)])
+        for a, b in zip(many[0], got):
+            assert np.array_equal(a.cpu().numpy(), b)
+        # pinned NumPy 1.26 semantics: against the oracle
+        ds = DS(load_dir=d, resolution=238, patch_size=patch, stride=stride, seq_len=3, seq_interval=2, pad=pad, mode="valid")
+        ds.max_step_num = 10
+        want = P.ds_get(trajs[1], 3, 3, 2, 238, patch, "airfoil" if kind == "airfoil" else "cylinder", pad=pad, stride=stride,
+                        n_patch=(ds.N_x_patch, ds.N_y_patch))
+        for a, b in zip(ds.ds_get(1, 3), want):
+            assert tuple(a.shape) == b.shape and np.array_equal(a.cpu().numpy(), b), k
+
+
+def test_a_patch_larger_than_the_frame_is_refused(tmp_path):
+    from fluid_llm_b200.simple_dataloader import MGNDataset
+    d = _write(tmp_path, [trajectory("cylinder", 30, s, 10 + s) for s in (0, 1)])
+    with pytest.raises(ValueError, match="no patches left"):
+        MGNDataset(load_dir=d, resolution=238, patch_size=(16, 64), stride=(16, 64), seq_len=3, pad=False)
+
+
 def test_full_size_properties_cylinder():
     """BASELINE config 1 at full size (T = 600): properties that need no oracle pass."""
     from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify

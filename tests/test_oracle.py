@@ -166,6 +166,35 @@ def test_oracle_reproduces_frozen_reference(kind):
         assert a.dtype == b.dtype and np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("kind", ["cylinder", "airfoil"])
+def test_oracle_reproduces_the_reference_for_other_strides_and_pad_false(kind):
+    """tests/golden/ref_strided.npz (oracle/make_golden_strided.py): the reference's unmodified data sets with stride != patch,
+    pad=False and a non-square patch, over the inputs stored in ref_{kind}.npz; SHA-256 of each of the five tensors."""
+    import hashlib
+    g, s = _gold(f"ref_{kind}.npz"), _gold("ref_strided.npz")
+    tr = {"mesh_pos": g["mesh_pos"], "cells": g["cells"], "velocity": g["velocity"], "pressure": g["pressure"]}
+    from fluid_llm_b200 import synth
+    probe = synth.make_trajectory(kind, 2, mesh_seed=1, field_seed=11)
+    for ci, case in enumerate(s["cases"]):
+        patch, stride, pad = tuple(int(v) for v in case[:2]), tuple(int(v) for v in case[2:4]), bool(case[4])
+        k = f"{kind}_{ci}"
+        # the reference takes N_x_patch / N_y_patch from its probe file, save_files[1] (the second seeded trajectory)
+        pos1 = probe["mesh_pos"]
+        if kind == "airfoil":
+            _, pos1, _ = P.airfoil_crop(pos1, probe["cells"])
+        nx1, ny1 = P.grid_shape(pos1[:, 0].min(), pos1[:, 0].max(), pos1[:, 1].min(), pos1[:, 1].max(), 238, "2.x")
+        if pad:
+            nx1, ny1 = nx1 + (-nx1) % patch[0], ny1 + (-ny1) % patch[1]
+        ring = 2 if kind == "airfoil" else 0
+        attrs = (P.num_patches(nx1, patch[0], stride[0]) - ring, P.num_patches(ny1, patch[1], stride[1]) - ring)
+        assert attrs == tuple(s[k + "_n_patch"]), k
+        out = P.ds_get(tr, 1, 3, 2, 238, patch, kind, pad=pad, numpy_semantics="2.x", stride=stride, n_patch=attrs)
+        for t, shape, digest in zip(out, s[k + "_shapes"], s[k + "_sha256"]):
+            assert list(t.shape) == [int(v) for v in shape[:t.ndim]], k
+            assert hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest() == str(digest), k
+        assert np.array_equal(out[0][0, ::7, :, ::5, ::5], s[k + "_sample"])
+
+
 def test_grid2mesh_oracle_reproduces_frozen_reference():
     g = _gold("ref_grid2mesh.npz")
     vg, pg = g["velocity_grid"].astype(np.float32), g["pressure_grid"].astype(np.float32)
