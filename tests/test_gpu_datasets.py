@@ -131,7 +131,7 @@ def test_datasets_with_other_strides_and_pad_false(kind, tmp_path):
         for t, shape, digest in zip(got, fix[k + "_shapes"], fix[k + "_sha256"]):
             assert list(t.shape) == [int(v) for v in shape[:t.ndim]], k
             assert hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest() == str(digest), k
-        many = ds.ds_get_many([(0, 1), (1, 3)])
+        many = ds.ds_get_many([(0, 1), (0, 3) if not pad else (1, 3)])   # (without padding two meshes need not share a patch grid)
         for a, b in zip(many[0], got):
             assert np.array_equal(a.cpu().numpy(), b)
         # pinned NumPy 1.26 semantics: against the oracle
