@@ -21,10 +21,87 @@ def strides(n_nodes):
     return 2 * ps, ps
 
 
-def load_trajectory(path, airfoil_crop):
-    """Unpickle `path` and crop if asked -> (mesh_pos f32 [N,2], cells i32 [F,3], velocity [T,N,2], pressure [T,N,1])."""
+_declined = 0             # consecutive files the lazy reader gave up on
+LAZY_BYTES = 1 << 18      # payloads of at least this many bytes are not copied out of the file while unpickling
+
+
+class _LazyFile:
+    """File object over a memory-mapped pickle for `pickle.Unpickler` that SKIPS large byte-string payloads.
+
+    The C unpickler reads a BINBYTES payload straight into the bytes object it has just allocated (`readinto`), and NumPy's
+    `__setstate__` keeps pointing into that bytes object when it is large and aligned.  For payloads >= LAZY_BYTES this file
+    only notes (address of the target, offset in the file, length) and copies nothing: the unpickled array then has the right
+    shape and dtype over memory nobody ever touched (no page is faulted in), and `lazy_arrays` swaps it for a view of the
+    mapped file.  A 600-step trajectory is ~18 MB of such payloads, a third of which (density) nobody reads."""
+
+    def __init__(self, mm):
+        self.mm, self.pos, self.lazy = mm, 0, {}
+
+    def read(self, n=-1):
+        end = len(self.mm) if n is None or n < 0 else min(self.pos + n, len(self.mm))
+        out = self.mm[self.pos:end]
+        self.pos = end
+        return out
+
+    def readline(self):
+        end = self.mm.find(b"\n", self.pos)
+        end = len(self.mm) if end < 0 else end + 1
+        out = self.mm[self.pos:end]
+        self.pos = end
+        return out
+
+    def readinto(self, b):
+        n = min(len(b), len(self.mm) - self.pos)
+        if n >= LAZY_BYTES and n == len(b):
+            self.lazy[np.frombuffer(b, dtype=np.uint8).ctypes.data] = (self.pos, n)
+        else:
+            b[:n] = self.mm[self.pos:self.pos + n]
+        self.pos += n
+        return n
+
+
+def unpickle_lazy(path, keys):
+    """-> {key: array} with the large arrays of `keys` as read-only views of the mapped file (which lives as long as they do), or
+    None when the file is not a plain dict of NumPy arrays unpickled the way _LazyFile expects (the caller then unpickles
+    normally).  Arrays of other keys may point at untouched memory and are dropped unread."""
+    import mmap
+    global _declined
+    if _declined >= 2:          # these files are not written the way the lazy reader needs: stop paying for the attempt
+        return None
     with open(path, "rb") as f:
-        d = pickle.load(f)
+        mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+    lf = _LazyFile(mm)
+    try:
+        d = pickle.Unpickler(lf).load()
+        if not isinstance(d, dict):
+            raise TypeError("not a dict")
+        out = {}
+        for k in keys:
+            a = d[k]
+            if not isinstance(a, np.ndarray) or a.dtype.hasobject:
+                raise TypeError("not a plain array")
+            if a.nbytes >= LAZY_BYTES:
+                where = lf.lazy.get(a.ctypes.data)
+                if where is None or where[1] != a.nbytes or not a.flags.c_contiguous:
+                    raise TypeError("payload not where expected")       # (NumPy copied it, or a view of a larger buffer)
+                a = np.ndarray(a.shape, dtype=a.dtype, buffer=mm, offset=where[0])
+            out[k] = a
+        _declined = 0
+        return out
+    except Exception:       # noqa: BLE001 -- anything unexpected: the plain unpickler decides
+        _declined += 1
+        return None
+
+
+def load_trajectory(path, airfoil_crop):
+    """Unpickle `path` and crop if asked -> (mesh_pos f32 [N,2], cells i32 [F,3], velocity [T,N,2], pressure [T,N,1]); the two
+    field arrays may be views of the mapped file (they are only read once more, by fill_slot)."""
+    got = unpickle_lazy(path, ("mesh_pos", "cells", "velocity", "pressure"))
+    if got is None:
+        with open(path, "rb") as f:
+            d = pickle.load(f)
+    else:
+        d = got
     pos, cells = np.asarray(d["mesh_pos"]), np.asarray(d["cells"])
     vel, prs = np.asarray(d["velocity"]), np.asarray(d["pressure"])
     if airfoil_crop:

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import warnings
 from dataclasses import dataclass
 
 import numpy as np
@@ -47,14 +48,24 @@ def shard_range(n_items: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def _as_tensor(a):
+    """NumPy -> float32 CPU tensor without a copy where possible (read-only views of a mapped file included: only read here)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.flags.writeable:
+        return torch.from_numpy(a)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        return torch.from_numpy(a)
+
+
 class DeviceTrajectory:
     """Node fields of one trajectory resident in HBM, in the pickle's own layout
     (velocity f32[T,N,2], pressure f32[T,N,1]; max/ds_download/torch_MGN.py:68-95)."""
 
     def __init__(self, velocity, pressure, plan: MeshPlan):
         dev = plan.device
-        v = velocity if torch.is_tensor(velocity) else torch.from_numpy(np.ascontiguousarray(velocity, dtype=np.float32))
-        p = pressure if torch.is_tensor(pressure) else torch.from_numpy(np.ascontiguousarray(pressure, dtype=np.float32))
+        v = velocity if torch.is_tensor(velocity) else _as_tensor(velocity)
+        p = pressure if torch.is_tensor(pressure) else _as_tensor(pressure)
         if v.dim() != 3 or v.shape[2] != 2 or v.shape[1] != plan.n_nodes:
             raise ValueError(f"velocity must be (T, {plan.n_nodes}, 2), got {tuple(v.shape)}")
         if p.dim() == 2:

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 from torch.utils.data import Dataset
 
+from ._ingest_worker import unpickle_lazy
 from ._lib import check, load, ptr, stream_ptr
 from .field_path import TrajBatch, CYLINDER, DeviceTrajectory, Personality, interp_patchify
 from .mesh_utils import MeshPlan, to_grid
@@ -181,8 +182,10 @@ class _GpuFieldDataset(Dataset):
             self._uploads.append((ev, release))
             self._reap_uploads()
         else:
-            with open(path, 'rb') as f:
-                save_data = pickle.load(f)
+            save_data = unpickle_lazy(path, ("mesh_pos", "cells", "velocity", "pressure"))      # field arrays as views of the file
+            if save_data is None:
+                with open(path, 'rb') as f:
+                    save_data = pickle.load(f)
             pos, faces, vel, prs = self._prepare_mesh(save_data)
             plan = self._new_plan(pos, faces)
             traj = DeviceTrajectory(vel, prs, plan)

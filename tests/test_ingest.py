@@ -1,0 +1,119 @@
+"""CPU: the pickle ingest path (fluid_llm_b200/ingest.py, _ingest_worker.py) against a plain `pickle.load`."""
+import copy
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pipeline as P
+
+from helpers import trajectory
+
+from fluid_llm_b200 import _ingest_worker as W
+from fluid_llm_b200.ingest import PickleIngest
+
+
+@pytest.fixture(autouse=True)
+def _fresh_lazy_reader():
+    W._declined = 0          # (a process stops trying the lazy reader after files it had to decline)
+    yield
+    W._declined = 0
+
+
+def _reference_pickle(tr, path, protocol=None, cells_dtype=np.int16):
+    """The reference's writer (max/ds_download/torch_MGN.py:66-93): velocity, pressure, density, then the static entries."""
+    d = {"velocity": tr["velocity"], "pressure": tr["pressure"], "density": np.ones_like(tr["pressure"]),
+         "cells": tr["cells"].astype(cells_dtype), "mesh_pos": tr["mesh_pos"],
+         "node_type": np.zeros((tr["mesh_pos"].shape[0], 1), dtype=np.int32)}
+    with open(path, "wb") as f:
+        pickle.dump(d, f, protocol=protocol)
+    return d
+
+
+@pytest.mark.parametrize("protocol", [2, 4, 5])
+def test_lazy_unpickle_equals_pickle_load(tmp_path, protocol):
+    tr = trajectory("cylinder", 60, 0, 3)
+    path = str(tmp_path / "a.pkl")
+    d = _reference_pickle(tr, path, protocol)
+    got = W.unpickle_lazy(path, ("mesh_pos", "cells", "velocity", "pressure"))
+    if protocol == 2:        # array data travels as a latin-1 string there: NumPy copies it, the lazy reader declines
+        assert got is None
+    else:
+        for k in ("velocity", "pressure"):
+            assert d[k].nbytes >= W.LAZY_BYTES and not got[k].flags.owndata and not got[k].flags.writeable   # a view of the file
+        for k, a in got.items():
+            assert a.dtype == d[k].dtype and a.shape == d[k].shape and np.array_equal(a, d[k])
+    pos, cells, vel, prs = W.load_trajectory(path, False)
+    assert cells.dtype == np.int32 and np.array_equal(cells, tr["cells"]) and np.array_equal(pos, tr["mesh_pos"])
+    assert np.array_equal(vel, tr["velocity"]) and np.array_equal(prs, tr["pressure"])
+
+
+def test_lazy_unpickle_declines_what_it_does_not_know(tmp_path):
+    tr = trajectory("cylinder", 60, 0, 3)
+    for i, d in enumerate(({"velocity": torch.from_numpy(tr["velocity"]), "pressure": tr["pressure"], "cells": tr["cells"],
+                            "mesh_pos": tr["mesh_pos"]},                                            # a tensor, not an array
+                           {"velocity": tr["velocity"][:, :, ::-1], "pressure": tr["pressure"], "cells": tr["cells"],
+                            "mesh_pos": tr["mesh_pos"]},                                            # pickled as a copy: fine either way
+                           [tr["velocity"]])):                                                     # not a dict
+        path = str(tmp_path / f"{i}.pkl")
+        with open(path, "wb") as f:
+            pickle.dump(d, f)
+        W._declined = 0
+        got = W.unpickle_lazy(path, ("mesh_pos", "cells", "velocity", "pressure"))
+        if i == 1:
+            assert got is not None and np.array_equal(got["velocity"], tr["velocity"][:, :, ::-1])
+        else:
+            assert got is None
+    # ... and load_trajectory falls back to the plain unpickler
+    pos, cells, vel, prs = W.load_trajectory(str(tmp_path / "0.pkl"), False)
+    assert np.array_equal(vel, tr["velocity"])
+    with open(tmp_path / "short.pkl", "wb") as f:
+        f.write(open(tmp_path / "1.pkl", "rb").read()[:500000])          # truncated inside a payload
+    W._declined = 0
+    assert W.unpickle_lazy(str(tmp_path / "short.pkl"), ("velocity",)) is None
+    assert W.unpickle_lazy(str(tmp_path / "short.pkl"), ("velocity",)) is None and W._declined == 2
+    assert W.unpickle_lazy(str(tmp_path / "1.pkl"), ("velocity",)) is None        # two files declined in a row: it stops trying
+    with pytest.raises(Exception):
+        W.load_trajectory(str(tmp_path / "short.pkl"), False)
+
+
+def test_airfoil_crop_in_the_worker_equals_the_oracle(tmp_path):
+    tr = trajectory("airfoil", 40, 1, 5)
+    path = str(tmp_path / "a.pkl")
+    _reference_pickle(tr, path, cells_dtype=np.int32)
+    pos, cells, vel, prs = W.load_trajectory(path, True)
+    nmask, pos_o, faces_o = P.airfoil_crop(tr["mesh_pos"], tr["cells"])
+    assert np.array_equal(pos, pos_o) and np.array_equal(cells, faces_o)
+    assert np.array_equal(vel, tr["velocity"][:, nmask]) and np.array_equal(prs, tr["pressure"][:, nmask])
+
+
+def test_pool_delivers_every_file_in_the_device_pitch(tmp_path):
+    trajs = [trajectory("cylinder", 30, s, 7 + s) for s in range(5)]
+    paths = []
+    for i, tr in enumerate(trajs):
+        paths.append(str(tmp_path / f"{i}.pkl"))
+        _reference_pickle(copy.deepcopy(tr), paths[-1])
+    pool = PickleIngest(workers=2, slot_bytes=4 << 20)
+    try:
+        pool.submit(paths)
+        for i in (3, 0, 4, 1, 2):                       # consumption order is free; only 4 slots for 5 files
+            pos, cells, vel, prs, release = pool.take(paths[i])
+            tr = trajs[i]
+            T, N = tr["velocity"].shape[:2]
+            vs, ps = W.strides(N)
+            assert tuple(vel.shape) == (T, vs) and tuple(prs.shape) == (T, ps)
+            assert np.array_equal(vel[:, :2 * N].numpy().reshape(T, N, 2), tr["velocity"]) and not vel[:, 2 * N:].any()
+            assert np.array_equal(prs[:, :N].numpy().reshape(T, N, 1), tr["pressure"]) and not prs[:, N:].any()
+            assert np.array_equal(pos, tr["mesh_pos"]) and np.array_equal(cells, tr["cells"])
+            release()
+        # a file larger than a slot is loaded in the calling process
+        big = trajectory("cylinder", 400, 0, 1)
+        _reference_pickle(big, str(tmp_path / "big.pkl"))
+        pos, cells, vel, prs, release = pool.take(str(tmp_path / "big.pkl"))
+        assert np.array_equal(vel[:, :2 * pos.shape[0]].numpy().reshape(400, -1, 2), big["velocity"])
+        release()
+        with pytest.raises(RuntimeError, match="ingest worker failed"):
+            pool.take(str(tmp_path / "missing.pkl"))
+    finally:
+        pool.close()
