@@ -17,6 +17,7 @@ import numpy as np
 import torch
 from torch.utils.data import Dataset
 
+from ._ingest_worker import unpickle_lazy
 from ._lib import FL_NO_NORM, check, load, ptr, stream_ptr
 from .airfoil_ds import crop_airfoil_mesh
 from .field_path import DeviceTrajectory
@@ -82,8 +83,10 @@ class EagleDataset(Dataset):
         """IMG_MGN.py:46-76 (cached per file)."""
         key = (save_file, os.path.getmtime(save_file))
         if key not in self._cache:
-            with open(save_file, "rb") as f:
-                save_data = pickle.load(f)
+            save_data = unpickle_lazy(save_file, ("mesh_pos", "cells", "velocity", "pressure"))   # field arrays as views of the file
+            if save_data is None:
+                with open(save_file, "rb") as f:
+                    save_data = pickle.load(f)
             pos, faces, vel, prs = save_data["mesh_pos"], save_data["cells"], save_data["velocity"], save_data["pressure"]
             if "airfoil" in self.fn:
                 m, pos, faces = crop_airfoil_mesh(pos, faces)
