@@ -3,10 +3,12 @@
 Run as a script by `subprocess.Popen` (NOT forked from the caller: a fork of a process with tens of GB of mapped memory
 leaves the parent paying copy-on-write faults for as long as the children live), so it imports nothing but NumPy:
 
-    python _ingest_worker.py <fd of the duplex pipe to the parent> <slot bytes> <airfoil crop 0/1> <slot name> [<slot name> ...]
+    python _ingest_worker.py <fd of the duplex pipe to the parent> <slot bytes> <airfoil crop 0/1> <grid resolution, 0 = no plan>
+                             <numpy semantics> <slot name> [<slot name> ...]
 
 Protocol (pickled tuples over a multiprocessing Connection): parent -> (ticket, path, slot index) or None to stop;
-worker -> (ticket, result dict).
+worker -> (ticket, result dict).  With a grid resolution the result also carries the host side of the trajectory's mesh plan
+(`_plan_host.prepare_plan`: validation, grid axes, Morton slots), so the parent only uploads it.
 """
 import pickle
 import sys
@@ -14,6 +16,11 @@ from multiprocessing import shared_memory
 from multiprocessing.connection import Connection
 
 import numpy as np
+
+try:
+    from . import _plan_host
+except ImportError:          # run as a script (by ingest.PickleIngest): the module lies next to this file
+    import _plan_host
 
 
 def strides(n_nodes):
@@ -132,11 +139,11 @@ def fill_slot(buf, nbytes, vel, prs):
 
 def main(argv):
     conn = Connection(int(argv[1]))
-    slot_bytes, airfoil_crop = int(argv[2]), argv[3] == "1"
+    slot_bytes, airfoil_crop, plan_res, plan_sem = int(argv[2]), argv[3] == "1", int(argv[4]), argv[5]
     # mapped once, for the life of the worker: a fresh mapping of a 20 MB slot costs ~20 ms of page faults.  The parent owns
     # (and unlinks) the segments: keep this process's resource tracker out of it.
     shms = []
-    for name in argv[4:]:
+    for name in argv[6:]:
         s = shared_memory.SharedMemory(name=name)
         try:
             from multiprocessing import resource_tracker
@@ -157,6 +164,11 @@ def main(argv):
                 pos, cells, vel, prs = load_trajectory(path, airfoil_crop)
                 need = fill_slot(shms[si].buf, slot_bytes, vel, prs)
                 r = {"too_small": need} if need else {"mesh_pos": pos, "cells": cells, "T": vel.shape[0], "N": pos.shape[0]}
+                if plan_res > 0 and not need:
+                    try:
+                        r["plan"] = _plan_host.prepare_plan(pos, cells, plan_res, plan_sem)
+                    except ValueError:       # an invalid triangulation: the parent validates again and raises it properly
+                        pass
             except Exception as e:      # noqa: BLE001 -- reported to the parent, which re-raises
                 r = {"error": f"{type(e).__name__}: {e}"}
             conn.send((ticket, r))

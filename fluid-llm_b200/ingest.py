@@ -13,7 +13,7 @@ The workers are separate interpreters (`_ingest_worker.py`, started with fork+ex
 
     pool = PickleIngest(workers=8)
     pool.submit(paths)                       # runs ahead; order of consumption is free
-    pos, cells, vel, prs, release = pool.take(path)     # vel [T, vel_stride], prs [T, prs_stride] pinned views
+    pos, cells, vel, prs, release, plan = pool.take(path)     # vel [T, vel_stride], prs [T, prs_stride] pinned views
     ... upload ...; release()
 
 Workers never touch CUDA.
@@ -57,7 +57,9 @@ class _Slot:
 
 
 class PickleIngest:
-    def __init__(self, workers=None, slot_bytes=24 << 20, airfoil_crop=False):
+    def __init__(self, workers=None, slot_bytes=24 << 20, airfoil_crop=False, plan_resolution=0, numpy_semantics="1.26"):
+        """`plan_resolution` > 0: the workers also prepare the host side of each trajectory's mesh plan for that grid resolution
+        (`_plan_host.prepare_plan`); `take` then returns it as its sixth value (else None)."""
         self.workers = workers or max(2, min(12, (os.cpu_count() or 4) - 2))
         self.slot_bytes = slot_bytes
         self.airfoil_crop = airfoil_crop
@@ -70,7 +72,8 @@ class PickleIngest:
             fd = child_c.fileno()
             os.set_inheritable(fd, True)
             p = subprocess.Popen([sys.executable, WORKER_SCRIPT, str(fd), str(slot_bytes), "1" if airfoil_crop else "0",
-                                  *[s.shm.name for s in self._slots[w]]], pass_fds=(fd,), close_fds=True)
+                                  str(int(plan_resolution)), str(numpy_semantics), *[s.shm.name for s in self._slots[w]]],
+                                 pass_fds=(fd,), close_fds=True)
             child_c.close()
             self._conns.append(parent_c)
             self._procs.append(p)
@@ -100,8 +103,9 @@ class PickleIngest:
         self._pump()
 
     def take(self, path):
-        """-> (mesh_pos, cells, vel [T, vel_stride], prs [T, prs_stride], release): the two field tensors are views of a
-        page-locked slot; call release() once the copies out of them have completed."""
+        """-> (mesh_pos, cells, vel [T, vel_stride], prs [T, prs_stride], release, plan): the two field tensors are views of a
+        page-locked slot; call release() once the copies out of them have completed.  `plan`: the prepared host side of the
+        mesh plan (see __init__), or None."""
         if path not in self._pending:
             if path in self._queue:            # jump the queue
                 self._queue.remove(path)
@@ -130,7 +134,7 @@ class PickleIngest:
         vs, ps = _strides(N)
         vel = slot.host[: 4 * T * vs].view(torch.float32).view(T, vs)
         prs = slot.host[4 * T * vs: 4 * T * (vs + ps)].view(torch.float32).view(T, ps)
-        return r["mesh_pos"], r["cells"], vel, prs, (lambda: self._release(w, si))
+        return r["mesh_pos"], r["cells"], vel, prs, (lambda: self._release(w, si)), r.get("plan")
 
     def _load_here(self, path):
         """In the calling process, into fresh pinned memory (no slot was free, or the file does not fit one)."""
@@ -141,7 +145,7 @@ class PickleIngest:
         _fill_slot(memoryview(host.numpy()), host.numel(), vel, prs)
         v = host[: 4 * T * vs].view(torch.float32).view(T, vs)
         p = host[4 * T * vs:].view(torch.float32).view(T, ps)
-        return pos, cells, v, p, (lambda: None)
+        return pos, cells, v, p, (lambda: None), None
 
     def _release(self, w, si):
         self._free.append((w, si))

@@ -20,42 +20,8 @@ import torch
 from . import _lib
 from ._lib import FL_FLIP_Y, FL_NO_PAD, check, load, ptr, stream_ptr
 
-F32, F64 = np.float32, np.float64
-
-
-def default_numpy_semantics() -> str:
-    """The reference pins NumPy 1.26.3 (environemnt.yml:177); its scalar promotion decides the last
-    bit of the grid coordinates.  "1.26" reproduces the pinned environment, "2.x" reproduces the
-    reference's code run under NumPy >= 2 (NEP 50)."""
-    return os.environ.get("FLUIDGRID_NUMPY_SEMANTICS", "1.26")
-
-
-def _grid_shape(x_min, x_max, y_min, y_max, grid_res, sem):
-    x_min, x_max, y_min, y_max = F32(x_min), F32(x_max), F32(y_min), F32(y_max)
-    dx, dy = F32(x_max - x_min), F32(y_max - y_min)
-    ratio = F32(min(dx, dy) / max(dx, dy))                       # mesh_utils.py:67-69, float32 scalars
-    n_short = int(F64(grid_res) * F64(ratio)) if sem == "1.26" else int(F32(F32(grid_res) * ratio))
-    return (int(grid_res), n_short) if dx > dy else (n_short, int(grid_res))   # :71-76
-
-
-def _grid_axis(start, stop, n, sem):
-    # np.mgrid[start:stop:n*1j]: indices * step + start with step = (stop - start) / (n - 1);
-    # float64 arithmetic under NumPy 1.26 (legacy promotion of the float32 scalars), float32 under 2.x
-    start, stop = F32(start), F32(stop)
-    i = np.arange(n)
-    if sem == "1.26":
-        step = F64(F32(stop - start)) / F64(n - 1) if n != 1 else F64(n)
-        return (i.astype(F64) * step + F64(start)).astype(F32)
-    step = F32(F32(stop - start) / F32(n - 1)) if n != 1 else F32(n)
-    return (i.astype(F32) * step + start).astype(F32)
-
-
-@lru_cache(maxsize=64)
-def _grid_axes(x_min, x_max, y_min, y_max, grid_res, sem):
-    nx, ny = _grid_shape(x_min, x_max, y_min, y_max, grid_res, sem)
-    if nx < 1 or ny < 1:
-        raise ValueError(f"degenerate grid {nx} x {ny} for extents ({x_min}, {x_max}) x ({y_min}, {y_max})")
-    return _grid_axis(x_min, x_max, nx, sem), _grid_axis(y_min, y_max, ny, sem)
+from ._plan_host import (F32, F64, _grid_axes, _grid_axis, _grid_shape, default_numpy_semantics, morton_slots,  # noqa: F401
+                         prepare_plan)
 
 
 def grid_pos(x_min, x_max, y_min, y_max, grid_res, numpy_semantics=None):
@@ -337,27 +303,6 @@ class PatchTable:
         return plan
 
 
-def morton_slots(pos32, n_padded):
-    """Slot of every node in a Z-order (Morton) sort of the positions: spatial neighbours get neighbouring
-    slots, so the 32 adjacent pixels one gather instruction serves read neighbouring 16-byte records
-    (distinct bank groups) instead of colliding at random.  Pad nodes keep their own index."""
-    n = len(pos32)
-    lo, hi = pos32.min(axis=0).astype(np.float64), pos32.max(axis=0).astype(np.float64)
-    q = ((pos32.astype(np.float64) - lo) / np.maximum(hi - lo, 1e-300) * 65535.0).astype(np.uint64)
-
-    def spread(v):
-        v = (v | (v << 8)) & np.uint64(0x00FF00FF)
-        v = (v | (v << 4)) & np.uint64(0x0F0F0F0F)
-        v = (v | (v << 2)) & np.uint64(0x33333333)
-        v = (v | (v << 1)) & np.uint64(0x55555555)
-        return v
-    code = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1))
-    order = np.argsort(code, kind="stable")
-    slot = np.arange(n_padded, dtype=np.int32)
-    slot[order] = np.arange(n, dtype=np.int32)
-    return slot
-
-
 class MeshPlan:
     """Device-side stand-in for `matplotlib.tri.Triangulation` + its trifinder (mesh_utils.py:103-104).
 
@@ -365,7 +310,8 @@ class MeshPlan:
     `x`, `y`, `triangles` are kept (host) because the reference's interpolator checks `z` against
     `triangulation.x.shape` (src/_triinterpolate.py:37-39)."""
 
-    def __init__(self, pos, faces, grid_res=238, numpy_semantics=None, device=None, allow_degenerate=False, sync=True):
+    def __init__(self, pos, faces, grid_res=238, numpy_semantics=None, device=None, allow_degenerate=False, sync=True,
+                 prepared=None):
         """`allow_degenerate`: matplotlib's trapezoid-map trifinder is undefined on triangles of zero area (three colinear
         nodes: their edges overlap, its map builder raises or loops), and its plane fit takes a pseudo-inverse branch there
         (`calculate_plane_coefficients`); the data sets contain none.  By default such input raises ValueError like an
@@ -373,49 +319,27 @@ class MeshPlan:
         other and a grid point located in it gets the value of the triangle's first vertex (weights 0, 0).
         `sync=False` (the data sets' ingest path): nothing in the constructor waits for the GPU -- one pinned upload, the
         locate kernels with their status word left on the device; call `ready()` before trusting the tables (it re-locates
-        with a larger workspace if the bin store overflowed, and says so)."""
+        with a larger workspace if the bin store overflowed, and says so).  `prepared`: the result of
+        `_plan_host.prepare_plan` for the same arguments, computed elsewhere (pos / faces / grid_res are then not looked at)."""
         _lib.require_cuda()
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
-        pos = np.asarray(pos)
-        if pos.ndim != 2 or pos.shape[1] != 2:
-            raise ValueError(f"x and y must be equal-length 1D arrays, but found pos of shape {pos.shape!r}")
-        try:
-            tri = np.array(faces, dtype=np.int32, order="C")   # matplotlib: int32 C-contiguous copy
-        except (ValueError, TypeError) as e:
-            raise ValueError(f"triangles must be a (N, 3) int array, not {faces!r}") from e
-        if tri.ndim != 2 or tri.shape[1] != 3:
-            raise ValueError(f"triangles must be a (N, 3) int array, but found shape {tri.shape!r}")
-        if tri.size and tri.max() >= len(pos):
-            raise ValueError("triangles are indices into the points and must be in the range "
-                             f"0 <= i < {len(pos)} but found value {tri.max()}")
-        if tri.size and tri.min() < 0:
-            raise ValueError("triangles are indices into the points and must be in the range "
-                             f"0 <= i < {len(pos)} but found value {tri.min()}")
-        if tri.shape[0] == 0:
-            raise ValueError("triangles must be a (N, 3) int array with N >= 1")
-        pos32 = np.ascontiguousarray(pos, dtype=F32)
-        p = pos32.astype(F64)[tri]                              # the same fp64 cross product as correct_triangles
-        area2 = (p[:, 1, 0] - p[:, 0, 0]) * (p[:, 2, 1] - p[:, 0, 1]) - (p[:, 1, 1] - p[:, 0, 1]) * (p[:, 2, 0] - p[:, 0, 0])
-        self.n_degenerate = int((area2 == 0).sum())
-        if self.n_degenerate and not allow_degenerate:
-            raise ValueError(f"{self.n_degenerate} triangle(s) of zero area (first: triangle {int(np.argmax(area2 == 0))}): "
-                             "the triangulation is invalid for the trapezoid-map trifinder; pass allow_degenerate=True to "
-                             "locate with the stated rule anyway")
-        self.x, self.y, self.triangles = pos32[:, 0].astype(F64), pos32[:, 1].astype(F64), tri
+        # host side of the plan (validation as matplotlib's Triangulation does it, grid axes, Morton slots): NumPy only, so the
+        # ingest workers can do it ahead of this process (`prepared`)
+        h = prepared if prepared is not None else prepare_plan(pos, faces, grid_res, numpy_semantics, allow_degenerate)
+        pos32, tri = h["pos32"], h["tri"]
+        self.n_degenerate = int(h["n_degenerate"])
+        self._pos32, self.triangles = pos32, tri
         self.n_nodes, self.n_cells = len(pos32), len(tri)
-        self.numpy_semantics = numpy_semantics or default_numpy_semantics()
-        x_min, y_min = np.min(pos32, axis=0)                    # mesh_utils.py:99-100
-        x_max, y_max = np.max(pos32, axis=0)
-        self.ax, self.ay = _grid_axes(float(x_min), float(x_max), float(y_min), float(y_max), int(grid_res),
-                                      self.numpy_semantics)
+        self.numpy_semantics = h["numpy_semantics"]
+        self.ax, self.ay = h["ax"], h["ay"]
         self.nx, self.ny = len(self.ax), len(self.ay)
         dev = self.device
         with torch.cuda.device(dev):
             self.n_padded = (self.n_nodes + 3) // 4 * 4
-            slots = morton_slots(pos32, self.n_padded)
+            slots = h["slots"]
             # one pinned pack, one upload: positions | triangles | grid axes | node slots (16-byte aligned pieces)
             parts = [pos32.reshape(-1).view(np.uint8), tri.reshape(-1).view(np.uint8), np.ascontiguousarray(self.ax).view(np.uint8),
                      np.ascontiguousarray(self.ay).view(np.uint8), slots.view(np.uint8)]
@@ -502,6 +426,15 @@ class MeshPlan:
         self._tri_index_host = None
 
     # -- reference-shaped views -------------------------------------------------------------
+    @property
+    def x(self):
+        """float64 node x (matplotlib's `Triangulation.x`, which the interpolator checks `z` against)."""
+        return self._pos32[:, 0].astype(F64)
+
+    @property
+    def y(self):
+        return self._pos32[:, 1].astype(F64)
+
     @property
     def grid_x(self):
         return np.ascontiguousarray(np.broadcast_to(self.ax[:, None], (self.nx, self.ny)))

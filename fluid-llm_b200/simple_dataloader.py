@@ -169,9 +169,9 @@ class _GpuFieldDataset(Dataset):
             # a worker process unpickled (and cropped) it into a page-locked slot: only the copies are issued here
             import time as _time
             t0 = _time.perf_counter()
-            pos, faces, vel, prs, release = self._ingest.take(path)
+            pos, faces, vel, prs, release, prepared = self._ingest.take(path)
             t1 = _time.perf_counter()
-            plan = self._new_plan(pos, faces)
+            plan = self._new_plan(pos, faces, prepared)
             t2 = _time.perf_counter()
             traj = DeviceTrajectory.from_padded(vel, prs, plan)
             t3 = _time.perf_counter()
@@ -199,10 +199,10 @@ class _GpuFieldDataset(Dataset):
             self._cache_bytes -= self._traj_bytes(old)
         return traj
 
-    def _new_plan(self, pos, faces):
+    def _new_plan(self, pos, faces, prepared=None):
         """A mesh plan built without waiting for the GPU (MeshPlan(sync=False)); `_verify_plans` checks it before the sample
-        that used it is handed out."""
-        plan = MeshPlan(pos, faces, self.resolution, self.numpy_semantics, self.device, sync=False)
+        that used it is handed out.  `prepared`: its host side, when an ingest worker has done it already."""
+        plan = MeshPlan(pos, faces, self.resolution, self.numpy_semantics, self.device, sync=False, prepared=prepared)
         self._unverified.append(plan)
         return plan
 
@@ -228,7 +228,10 @@ class _GpuFieldDataset(Dataset):
         """The unpickling pool (created on first use), or None when disabled."""
         if self._ingest is None and self.ingest_workers != 0:
             from .ingest import PickleIngest
-            self._ingest = PickleIngest(workers=self.ingest_workers, airfoil_crop=self.ingest_airfoil_crop)
+            from .mesh_utils import default_numpy_semantics
+            self._ingest = PickleIngest(workers=self.ingest_workers, airfoil_crop=self.ingest_airfoil_crop,
+                                        plan_resolution=self.resolution,
+                                        numpy_semantics=self.numpy_semantics or default_numpy_semantics())
         return self._ingest
 
     def _reap_uploads(self, wait=False):

@@ -11,6 +11,7 @@ from oracle import pipeline as P
 from helpers import trajectory
 
 from fluid_llm_b200 import _ingest_worker as W
+from fluid_llm_b200._plan_host import prepare_plan
 from fluid_llm_b200.ingest import PickleIngest
 
 
@@ -94,12 +95,16 @@ def test_pool_delivers_every_file_in_the_device_pitch(tmp_path):
     for i, tr in enumerate(trajs):
         paths.append(str(tmp_path / f"{i}.pkl"))
         _reference_pickle(copy.deepcopy(tr), paths[-1])
-    pool = PickleIngest(workers=2, slot_bytes=4 << 20)
+    pool = PickleIngest(workers=2, slot_bytes=4 << 20, plan_resolution=238, numpy_semantics="2.x")
     try:
         pool.submit(paths)
         for i in (3, 0, 4, 1, 2):                       # consumption order is free; only 4 slots for 5 files
-            pos, cells, vel, prs, release = pool.take(paths[i])
+            pos, cells, vel, prs, release, plan = pool.take(paths[i])
             tr = trajs[i]
+            want = prepare_plan(tr["mesh_pos"], tr["cells"], 238, "2.x")          # the workers prepared the host side of the mesh plan
+            assert set(plan) == set(want) and plan["numpy_semantics"] == "2.x" and plan["n_degenerate"] == 0
+            for k in ("pos32", "tri", "ax", "ay", "slots"):
+                assert plan[k].dtype == want[k].dtype and np.array_equal(plan[k], want[k])
             T, N = tr["velocity"].shape[:2]
             vs, ps = W.strides(N)
             assert tuple(vel.shape) == (T, vs) and tuple(prs.shape) == (T, ps)
@@ -110,7 +115,8 @@ def test_pool_delivers_every_file_in_the_device_pitch(tmp_path):
         # a file larger than a slot is loaded in the calling process
         big = trajectory("cylinder", 400, 0, 1)
         _reference_pickle(big, str(tmp_path / "big.pkl"))
-        pos, cells, vel, prs, release = pool.take(str(tmp_path / "big.pkl"))
+        pos, cells, vel, prs, release, plan = pool.take(str(tmp_path / "big.pkl"))
+        assert plan is None
         assert np.array_equal(vel[:, :2 * pos.shape[0]].numpy().reshape(400, -1, 2), big["velocity"])
         release()
         with pytest.raises(RuntimeError, match="ingest worker failed"):
