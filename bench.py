@@ -712,6 +712,8 @@ def run_ours(args, w):
 
 
 def main():
+    # stdout carries ONE JSON line: NCCL's own chatter (its version line at init, anything NCCL_DEBUG asks for) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
