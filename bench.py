@@ -713,6 +713,9 @@ def run_ours(args, w):
 
 def main():
     # stdout carries ONE JSON line: NCCL's own chatter (its version line at init, anything NCCL_DEBUG asks for) goes to stderr
+    # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, which is what prints that line)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
