@@ -188,7 +188,16 @@ class _GpuFieldDataset(Dataset):
                     save_data = pickle.load(f)
             pos, faces, vel, prs = self._prepare_mesh(save_data)
             plan = self._new_plan(pos, faces)
-            traj = DeviceTrajectory(vel, prs, plan)
+            # the only host copy: file mapping (or unpickled arrays) -> reused pinned buffers in the device pitch -> one upload
+            T, N = int(np.shape(vel)[0]), plan.n_nodes
+            hv, hp = self._pinned.get("vel", (T, 2 * plan.n_padded)), self._pinned.get("prs", (T, plan.n_padded))
+            hv_np, hp_np = hv.numpy(), hp.numpy()
+            hv_np[:, :2 * N] = np.asarray(vel).reshape(T, 2 * N)
+            hv_np[:, 2 * N:] = 0
+            hp_np[:, :N] = np.asarray(prs).reshape(T, N)
+            hp_np[:, N:] = 0
+            traj = DeviceTrajectory.from_padded(hv, hp, plan)
+            torch.cuda.current_stream(plan.device).synchronize()       # the pinned buffers are reused by the next load
         self._cache[key] = traj
         self._cache_bytes += self._traj_bytes(traj)
         budget = self._cache_budget(traj.plan.device)
@@ -226,7 +235,9 @@ class _GpuFieldDataset(Dataset):
 
     def _ingest_pool(self):
         """The unpickling pool (created on first use), or None when disabled."""
-        if self._ingest is None and self.ingest_workers != 0:
+        if self.ingest_workers == 0:
+            return None
+        if self._ingest is None:
             from .ingest import PickleIngest
             from .mesh_utils import default_numpy_semantics
             self._ingest = PickleIngest(workers=self.ingest_workers, airfoil_crop=self.ingest_airfoil_crop,

@@ -51,6 +51,11 @@ def test_dataset_five_tuple_matches_oracle(kind, tmp_path):
     raw = P.full_seq(trajs[1], 20, 1, 1, 238, PATCH, pers)[0][0, :3]
     for c in range(3):
         assert ds.ds_min_max[c][0] == raw[c].min() and ds.ds_min_max[c][1] == raw[c].max()
+    # the same sample with the pool switched off: unpickled (lazily) in this process, one pinned hop
+    ds.ingest_workers = 0
+    ds._cache.clear()
+    for a, b in zip(ds.ds_get(0, 10 ** 6), want):
+        assert np.array_equal(a.cpu().numpy(), b)
     # normalize=False and host output
     ds2 = DS(load_dir=d, resolution=238, patch_size=PATCH, stride=PATCH, seq_len=3, seq_interval=1, mode="test",
              normalize=False, output_device="cpu")
