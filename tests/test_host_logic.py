@@ -108,3 +108,31 @@ def test_load_eagle_sim_reads_the_reference_layout(tmp_path):
     assert np.array_equal(vel, tr["velocity"][1:5]) and np.array_equal(prs, tr["pressure"][1:5, :, 0])
     pos_all, _, _, _ = load_eagle_sim(str(tmp_path))
     assert pos_all.shape[0] == T
+
+
+def test_prepare_plan_validates_like_matplotlibs_triangulation():
+    """`_plan_host.prepare_plan` (NumPy only; run by the ingest workers and by MeshPlan): the errors `matplotlib.tri.Triangulation`
+    raises for the reference at mesh_utils.py:103, the grid of mesh_utils.py:64-79, and slots that are a permutation."""
+    from fluid_llm_b200._plan_host import prepare_plan
+    from oracle import pipeline as P
+    pos = np.array([[0, 0], [1, 0], [0, 1], [1, 1], [2, 0.5]], dtype=np.float32)
+    tri = np.array([[0, 1, 2], [1, 3, 2], [1, 4, 3]], dtype=np.int16)
+    h = prepare_plan(pos, tri, 17, "1.26")
+    assert h["tri"].dtype == np.int32 and h["pos32"].dtype == np.float32 and h["n_degenerate"] == 0
+    gx, gy = P.grid_pos(0.0, 2.0, 0.0, 1.0, 17, "1.26")
+    assert np.array_equal(h["ax"], gx[:, 0]) and np.array_equal(h["ay"], gy[0, :])
+    assert h["slots"].shape == (8,) and sorted(h["slots"][:5]) == [0, 1, 2, 3, 4] and list(h["slots"][5:]) == [5, 6, 7]
+    with pytest.raises(ValueError, match=r"triangles must be a \(N, 3\) int array"):
+        prepare_plan(pos, tri[:, :2], 17)
+    with pytest.raises(ValueError, match=r"with N >= 1"):
+        prepare_plan(pos, np.zeros((0, 3), dtype=np.int32), 17)
+    with pytest.raises(ValueError, match="0 <= i < 5 but found value 5"):
+        prepare_plan(pos, np.array([[0, 1, 5]]), 17)
+    with pytest.raises(ValueError, match="but found value -1"):
+        prepare_plan(pos, np.array([[0, 1, -1]]), 17)
+    with pytest.raises(ValueError, match="equal-length 1D arrays"):
+        prepare_plan(pos[:, :1], tri, 17)
+    with pytest.raises(ValueError, match="zero area"):
+        prepare_plan(np.array([[0, 0], [1, 0], [2, 0], [0, 1]], dtype=np.float32), np.array([[0, 1, 2], [0, 1, 3]]), 17)
+    assert prepare_plan(np.array([[0, 0], [1, 0], [2, 0], [0, 1]], dtype=np.float32), np.array([[0, 1, 2], [0, 1, 3]]), 17,
+                        allow_degenerate=True)["n_degenerate"] == 1
