@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+from collections import OrderedDict
 import pickle
 import random
 import re
@@ -50,7 +51,9 @@ def interp_frames(traj: DeviceTrajectory, t0, n_frames, interval=1, crop=0, mean
 
 
 class EagleDataset(Dataset):
-    """IMG_MGN.py:12 -- the name is the reference's (it loads MGN pickles, not EAGLE)."""
+    """IMG_MGN.py:12 -- the name is the reference's (it loads MGN pickles, not EAGLE).  Trajectories (node fields + mesh plan) stay
+    resident on the device, the `cache_size` most recently used ones (a 600-step trajectory is ~15 MB of HBM)."""
+    cache_size = 256
 
     def __init__(self, data_path, mode="test", window_length=990, with_mesh=False, device=None, output_device="cpu"):
         super().__init__()
@@ -67,7 +70,7 @@ class EagleDataset(Dataset):
         self.dataloc = _natsorted(self.dataloc)
         self.mode, self.length, self.with_mesh = mode, 990, with_mesh
         self.device, self.output_device = device, output_device
-        self._cache = {}
+        self._cache = OrderedDict()
 
     def __len__(self):
         return len(self.dataloc)
@@ -82,7 +85,9 @@ class EagleDataset(Dataset):
     def _load_step(self, save_file) -> DeviceTrajectory:
         """IMG_MGN.py:46-76 (cached per file)."""
         key = (save_file, os.path.getmtime(save_file))
-        if key not in self._cache:
+        if key in self._cache:
+            self._cache.move_to_end(key)
+        else:
             save_data = unpickle_lazy(save_file, ("mesh_pos", "cells", "velocity", "pressure"))   # field arrays as views of the file
             if save_data is None:
                 with open(save_file, "rb") as f:
@@ -91,7 +96,9 @@ class EagleDataset(Dataset):
             if "airfoil" in self.fn:
                 m, pos, faces = crop_airfoil_mesh(pos, faces)
                 vel, prs = np.ascontiguousarray(vel[:, m]), np.ascontiguousarray(prs[:, m])
-            self._cache = {key: DeviceTrajectory(vel, prs, MeshPlan(pos, faces, 238, None, self.device))}
+            self._cache[key] = DeviceTrajectory(vel, prs, MeshPlan(pos, faces, 238, None, self.device))
+            while len(self._cache) > max(1, self.cache_size):
+                self._cache.popitem(last=False)
         return self._cache[key]
 
     def __getitem__(self, item):
