@@ -83,6 +83,7 @@ class PickleIngest:
         self._done = {}                        # ticket -> result (arrived, not yet taken)
         self._queue = []                       # paths waiting for a free slot
         self._ticket = 0
+        self.grow_to = 0                       # > 0: a file did not fit a slot; the owner should rebuild the pool with slots this large
         atexit.register(self.close)
 
     def _pump(self):
@@ -129,6 +130,7 @@ class PickleIngest:
             self._release(w, si)
             if "error" in r:
                 raise RuntimeError(f"ingest worker failed on {path}: {r['error']}")
+            self.grow_to = max(self.grow_to, (int(r["too_small"] * 1.25) + (1 << 20) - 1) >> 20 << 20)
             return self._load_here(path)       # a trajectory larger than the slots
         T, N = r["T"], r["N"]
         vs, ps = _strides(N)

@@ -62,6 +62,7 @@ class _GpuFieldDataset(Dataset):
     cache_size = 4096          # trajectories kept resident on the device (plan + node fields), at most ...
     cache_fraction = 0.25      # ... this fraction of the device's memory (a 1000-trajectory MGN data set is ~18 GB of 180)
     ingest_workers = None      # processes that unpickle ahead of the GPU (None: min(12, cores - 2); 0: unpickle in-process)
+    ingest_slot_bytes = 24 << 20   # page-locked bytes per ingest slot (two per worker); grows when a trajectory does not fit
     ingest_airfoil_crop = False
     plan_cache_size = 256   # mesh plans kept resident (static tables, ~1 MB each) for window loads from .fgt files
     window_loads = True     # .fgt file not resident: read and upload only the time steps the sample needs
@@ -237,10 +238,17 @@ class _GpuFieldDataset(Dataset):
         """The unpickling pool (created on first use), or None when disabled."""
         if self.ingest_workers == 0:
             return None
+        if self._ingest is not None and self._ingest.grow_to > self.ingest_slot_bytes:
+            # a trajectory did not fit the page-locked slots (it was unpickled in this process instead): larger slots from here on
+            self._reap_uploads(wait=True)                  # no copy out of the old slots is still in flight
+            self.ingest_slot_bytes = self._ingest.grow_to
+            self._ingest.close()
+            self._ingest = None
         if self._ingest is None:
             from .ingest import PickleIngest
             from .mesh_utils import default_numpy_semantics
-            self._ingest = PickleIngest(workers=self.ingest_workers, airfoil_crop=self.ingest_airfoil_crop,
+            self._ingest = PickleIngest(workers=self.ingest_workers, slot_bytes=self.ingest_slot_bytes,
+                                        airfoil_crop=self.ingest_airfoil_crop,
                                         plan_resolution=self.resolution,
                                         numpy_semantics=self.numpy_semantics or default_numpy_semantics())
         return self._ingest

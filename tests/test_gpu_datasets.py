@@ -148,6 +148,24 @@ def test_datasets_with_other_strides_and_pad_false(kind, tmp_path):
             assert tuple(a.shape) == b.shape and np.array_equal(a.cpu().numpy(), b), k
 
 
+def test_ingest_slots_grow_when_a_trajectory_does_not_fit(tmp_path):
+    from fluid_llm_b200.simple_dataloader import MGNDataset
+    trajs = [trajectory("cylinder", 140, s, 10 + s) for s in (0, 1, 2)]
+    d = _write(tmp_path, copy.deepcopy(trajs))
+
+    class Small(MGNDataset):
+        ingest_slot_bytes = 1 << 20            # 140 steps x 1 855 nodes x 12 B = 3.1 MB do not fit
+        ingest_workers = 2
+    ds = Small(load_dir=d, resolution=238, patch_size=PATCH, stride=PATCH, seq_len=4, seq_interval=2, mode="valid")
+    ds.cache_size = 0
+    for i in (0, 1, 2, 0):
+        ds.prefetch([(j, 100) for j in range(3)])
+        want = P.ds_get(trajs[i], 100, 4, 2, 238, PATCH, "cylinder")
+        for a, b in zip(ds[i], want):
+            assert np.array_equal(a.cpu().numpy(), b)
+    assert ds.ingest_slot_bytes > 3 << 20 and ds._ingest.slot_bytes == ds.ingest_slot_bytes and ds._ingest.grow_to == 0
+
+
 def test_a_patch_larger_than_the_frame_is_refused(tmp_path):
     from fluid_llm_b200.simple_dataloader import MGNDataset
     d = _write(tmp_path, [trajectory("cylinder", 30, s, 10 + s) for s in (0, 1)])

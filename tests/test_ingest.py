@@ -115,8 +115,9 @@ def test_pool_delivers_every_file_in_the_device_pitch(tmp_path):
         # a file larger than a slot is loaded in the calling process
         big = trajectory("cylinder", 400, 0, 1)
         _reference_pickle(big, str(tmp_path / "big.pkl"))
+        assert pool.grow_to == 0
         pos, cells, vel, prs, release, plan = pool.take(str(tmp_path / "big.pkl"))
-        assert plan is None
+        assert plan is None and pool.grow_to >= 400 * 12 * pos.shape[0]      # ... and the pool asks for larger slots
         assert np.array_equal(vel[:, :2 * pos.shape[0]].numpy().reshape(400, -1, 2), big["velocity"])
         release()
         with pytest.raises(RuntimeError, match="ingest worker failed"):
