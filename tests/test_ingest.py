@@ -70,7 +70,7 @@ def test_lazy_unpickle_declines_what_it_does_not_know(tmp_path):
     pos, cells, vel, prs = W.load_trajectory(str(tmp_path / "0.pkl"), False)
     assert np.array_equal(vel, tr["velocity"])
     with open(tmp_path / "short.pkl", "wb") as f:
-        f.write(open(tmp_path / "1.pkl", "rb").read()[:500000])          # truncated inside a payload
+        f.write((tmp_path / "1.pkl").read_bytes()[:500000])          # truncated inside a payload
     W._declined = 0
     assert W.unpickle_lazy(str(tmp_path / "short.pkl"), ("velocity",)) is None
     assert W.unpickle_lazy(str(tmp_path / "short.pkl"), ("velocity",)) is None and W._declined == 2
