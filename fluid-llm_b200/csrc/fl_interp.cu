@@ -26,7 +26,8 @@ static thread_local const char* g_last_kernel = "";     // what fl_interp_patchi
 
 namespace {
 
-// Generic kernel: one CTA = one patch (px*py threads) x a chunk of frames of one trajectory.
+// Generic kernel: one CTA = one patch x a chunk of frames of one trajectory; a thread takes pixels k, k + blockDim.x, ... of
+// the patch (one pixel each for patches of up to 256 pixels), so ANY patch size works.
 // Each thread keeps its cell record in registers and walks the frames; node values are gathered
 // straight from global memory (L1/L2 hits: a patch touches ~100 nodes per frame).
 // Works for any mesh size; the staged kernel below is the fast path for meshes that fit in smem.
@@ -38,13 +39,13 @@ __global__ void __launch_bounds__(256) k_interp_patchify_gather(const FlTraj* __
     if (f0 >= tr.n_frames) return;
     const int f1 = min(tr.n_frames, f0 + frames_per_cta);
     const int l = blockIdx.x;
-    const int k = threadIdx.x;
+    const bool mask_aware = flags & FL_MASK_AWARE_NORM, no_norm = flags & FL_NO_NORM;
+    for (int k = threadIdx.x; k < ppx; k += blockDim.x) {
     const size_t o = (size_t)l * ppx + k;
     const FlCellIdx id = tr.d_idx[o];
     const FlCellW w = tr.d_w[o];
     const double w0 = 1.0 - w.w1 - w.w2;
     const bool outside = id.tri < 0;
-    const bool mask_aware = flags & FL_MASK_AWARE_NORM, no_norm = flags & FL_NO_NORM;
     for (int f = f0; f < f1; ++f) {
         const size_t t = (size_t)tr.t0 + (size_t)f * tr.interval;
         float v[3] = {0.f, 0.f, 0.f};
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) k_interp_patchify_gather(const FlTraj* __
             fl_stg_stream1(dst + (size_t)c * ppx, x);
         }
         if (tr.d_mask) tr.d_mask[((size_t)f * n_patches + l) * ppx + k] = masked ? 1 : 0;
+    }
     }
 }
 
@@ -390,7 +392,8 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
     int fpc = 16;
     while (fpc > 1 && ctas_per_frame * ((max_frames + fpc - 1) / fpc) < 4L * FL_SM_COUNT * 8) fpc >>= 1;
     dim3 grid(n_patches, (max_frames + fpc - 1) / fpc, n_traj);
-    k_interp_patchify_gather<<<grid, ppx, 0, st>>>(d_trajs, n_patches, ppx, fpc, nc, flags);
+    const int threads = ppx >= 256 ? 256 : (ppx + 31) / 32 * 32;
+    k_interp_patchify_gather<<<grid, threads, 0, st>>>(d_trajs, n_patches, ppx, fpc, nc, flags);
     FL_LAUNCH_CHECK();
     g_last_kernel = "k_interp_patchify_gather";
     return FL_OK;
@@ -445,8 +448,7 @@ extern "C" int fl_interp_patchify_dev(const FlTraj* d_trajs, const FlTraj* h_tra
     int rc = check_trajs("fl_interp_patchify_dev", h_trajs, n_traj, &max_frames);
     if (rc) return rc;
     FL_REQUIRE(n_patches > 0, FL_E_ARG, "fl_interp_patchify_dev: n_patches=%d", n_patches);
-    FL_REQUIRE(px > 0 && py > 0 && px * py <= 256 && (px * py) % 32 == 0, FL_E_ARG,
-               "fl_interp_patchify_dev: patch of %dx%d pixels unsupported (need px*py <= 256, multiple of 32)", px, py);
+    FL_REQUIRE(px > 0 && py > 0 && (long)px * py <= (1L << 20), FL_E_ARG, "fl_interp_patchify_dev: patch of %dx%d pixels unsupported", px, py);
     FL_REQUIRE((h_mean && h_std) || (flags & FL_NO_NORM), FL_E_ARG, "fl_interp_patchify_dev: mean/std missing");
     return launch_interp(d_trajs, h_trajs, n_traj, max_frames, n_patches, px, py, h_mean, h_std, flags, (cudaStream_t)stream);
 }

@@ -138,8 +138,9 @@ typedef struct FlTraj {
 } FlTraj;
 /* prs_stride a multiple of 4, vel_stride >= 2 * prs_stride, 16-byte aligned bases and pad floats
  * that are readable and finite select the staged kernel: whole frames are staged in shared memory
- * as 16-byte node records and gathered there.  Anything else runs the gather-from-global kernel --
- * same results, slower. */
+ * as 16-byte node records and gathered there (patches of a multiple of 128 pixels).  Anything else runs
+ * the gather-from-global kernel -- same results, slower.  px, py: ANY patch size F.unfold takes
+ * (simple_dataloader.py:131), e.g. 5 x 5 or 32 x 32; the reference's configs use 16 x 16. */
 
 int fl_interp_patchify(const FlTraj* h_trajs, int n_traj, int n_patches, int px, int py,
                        const float* h_mean, const float* h_std, unsigned flags, void* stream);

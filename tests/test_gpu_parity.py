@@ -316,9 +316,10 @@ def test_big_mesh_tiled_and_gather_paths_match_oracle():
         assert _same_bits(states.cpu().numpy(), extra["states"]), kw
 
 
-@pytest.mark.parametrize("patch", [(8, 8), (16, 8), (8, 16), (4, 8)])
+@pytest.mark.parametrize("patch", [(8, 8), (16, 8), (8, 16), (4, 8), (5, 5), (10, 7), (32, 32), (24, 16), (20, 20), (64, 8)])
 def test_other_patch_sizes(patch):
-    """Patch sizes other than the reference's 16 x 16: (16,8)/(8,16) run the staged kernel, (8,8)/(4,8) the gather kernel."""
+    """Patch sizes other than the reference's 16 x 16: multiples of 128 pixels run the staged kernel ((16,8), (8,16), (32,32),
+    (24,16), (64,8)), everything else the gather kernel -- any size the reference's F.unfold takes."""
     from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
     tr = trajectory("cylinder")
     plan, _, _ = _plan("cylinder")
@@ -331,12 +332,16 @@ def test_other_patch_sizes(patch):
         assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool)), kw
 
 
-def test_unsupported_patch_size_is_an_error():
+def test_other_patch_sizes_kernel_choice():
+    from fluid_llm_b200._lib import load
     from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
     tr = trajectory("cylinder")
     plan, _, _ = _plan("cylinder")
+    for patch, kernel in (((32, 32), b"k_interp_patchify_staged"), ((20, 20), b"k_interp_patchify_gather"), ((5, 5), b"k_interp_patchify_gather")):
+        interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 0, 2, 1, patch, CYLINDER)
+        assert load().fl_last_interp_kernel() == kernel
     with pytest.raises(ValueError):
-        interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 0, 2, 1, (5, 5), CYLINDER)
+        interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 0, 2, 1, (0, 5), CYLINDER)
 
 
 def test_c_abi_called_directly_as_integration_md_shows():
