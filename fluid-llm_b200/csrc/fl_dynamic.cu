@@ -34,11 +34,12 @@ __global__ void __launch_bounds__(256) k_dyn_locate_interp(
     int nby, int nbins, int capacity, const float* __restrict__ ax, const float* __restrict__ ay, DynGeom g, NormConst nc,
     unsigned flags, int frame0, float* __restrict__ states, uint8_t* __restrict__ mask, int32_t* __restrict__ tri_out) {
     const int fl = blockIdx.y, f = frame0 + fl;          // frame inside the chunk / inside the call
-    const int l = blockIdx.x, k = threadIdx.x, ppx = g.px * g.py;
+    const int l = blockIdx.x, ppx = g.px * g.py;
     const float* pos = pos_all + (size_t)f * 2 * n_nodes;
     const int* tri_v = tri_v_all + (size_t)fl * 3 * n_cells;
     const int* bin_start = bin_start_all + (size_t)fl * (nbins + 1);
     const int* items = items_all + (size_t)fl * capacity;
+    for (int k = threadIdx.x; k < ppx; k += blockDim.x) {      // (one pixel per thread for patches of up to 256 pixels)
     // output pixel -> grid cell: the same map as k_plan_patch_table (fl_locate.cu)
     const int j = k % g.py, i = k / g.py;
     const int bx = l / g.n_by, by = l - bx * g.n_by;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(256) k_dyn_locate_interp(
     }
     if (mask) mask[((size_t)f * n_patches + l) * ppx + k] = masked ? 1 : 0;
     if (tri_out) tri_out[((size_t)f * n_patches + l) * ppx + k] = id.tri;
+    }
 }
 
 
@@ -298,8 +300,8 @@ extern "C" int fl_dyn_interp_patchify(const float* d_pos, const int32_t* d_cells
     FL_REQUIRE(n_frames > 0 && n_nodes > 0 && n_cells > 0 && nx > 0 && ny > 0, FL_E_ARG,
                "fl_dyn_interp_patchify: sizes must be positive");
     FL_REQUIRE(nx <= 32767 * BIN && ny <= 32767 * BIN, FL_E_ARG, "fl_dyn_interp_patchify: grid too large");
-    FL_REQUIRE(px > 0 && py > 0 && px * py <= 256 && (px * py) % 32 == 0 && crop_patches >= 0, FL_E_ARG,
-               "fl_dyn_interp_patchify: patch of %dx%d pixels unsupported (need px*py <= 256, multiple of 32)", px, py);
+    FL_REQUIRE(px > 0 && py > 0 && (long)px * py <= (1L << 20) && crop_patches >= 0, FL_E_ARG,
+               "fl_dyn_interp_patchify: patch of %dx%d pixels unsupported", px, py);
     FL_REQUIRE((h_mean && h_std) || (flags & FL_NO_NORM), FL_E_ARG, "fl_dyn_interp_patchify: mean/std missing");
     FL_REQUIRE(((uintptr_t)d_workspace & 255) == 0 && ((uintptr_t)d_velocity & 7) == 0 && ((uintptr_t)d_pos & 7) == 0, FL_E_ALIGN,
                "fl_dyn_interp_patchify: workspace must be 256-byte aligned, positions and velocity 8-byte aligned");
@@ -341,7 +343,7 @@ extern "C" int fl_dyn_interp_patchify(const float* d_pos, const int32_t* d_cells
                             d_grid_ax, d_grid_ay, nx, ny, w, true, st);
         if (rc) return rc;
         dim3 grid(g.n_bx * g.n_by, w.n_frames);
-        k_dyn_locate_interp<<<grid, px * py, 0, st>>>(d_pos, d_velocity, d_pressure, n_nodes, n_cells, w.tri_v, w.bin_start,
+        k_dyn_locate_interp<<<grid, px * py >= 256 ? 256 : (px * py + 31) / 32 * 32, 0, st>>>(d_pos, d_velocity, d_pressure, n_nodes, n_cells, w.tri_v, w.bin_start,
                                                       w.items, w.nby, w.nbins, w.capacity, d_grid_ax, d_grid_ay, g, nc, flags,
                                                       f0, d_states, d_mask, d_tri);
         FL_LAUNCH_CHECK();

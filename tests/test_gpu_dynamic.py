@@ -80,6 +80,24 @@ def test_dynamic_equals_static_path_on_a_static_mesh():
     assert torch.equal(s_bin, s_dyn) and torch.equal(m_bin, m_dyn) and torch.equal(tri_bin, tri_dyn)
 
 
+@pytest.mark.parametrize("patch", [(5, 5), (10, 7), (32, 32), (24, 16), (8, 8)])
+def test_dynamic_other_patch_sizes(patch):
+    """Any patch size: both forms against the static path on a repeated mesh (which is checked against the oracle for the same
+    sizes in test_gpu_parity.py::test_other_patch_sizes)."""
+    from fluid_llm_b200.dynamic_mesh import DynamicTrajectory
+    from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
+    from fluid_llm_b200.mesh_utils import MeshPlan
+    tr = synth.make_trajectory("cylinder", 3, mesh_seed=1, field_seed=2)
+    T = 3
+    dt = DynamicTrajectory(np.repeat(tr["mesh_pos"][None], T, 0), np.repeat(tr["cells"][None], T, 0), tr["velocity"], tr["pressure"])
+    plan = MeshPlan(tr["mesh_pos"], tr["cells"], 238)
+    s_st, m_st, tab = interp_patchify(DeviceTrajectory(tr["velocity"], tr["pressure"], plan), 0, T, 1, patch, CYLINDER)
+    for force_binned in (False, True):
+        s_dyn, m_dyn, tri_dyn = dt.interp_patchify(0, T, 1, patch, CYLINDER, want_tri=True, force_binned=force_binned)
+        assert torch.equal(s_dyn, s_st) and torch.equal(m_dyn, m_st)
+        assert torch.equal(tri_dyn[0].reshape(-1), tab.idx[:, 3])
+
+
 def test_dynamic_binned_and_raster_forms_agree_on_moving_meshes():
     from fluid_llm_b200.dynamic_mesh import DynamicTrajectory
     from fluid_llm_b200.field_path import AIRFOIL, CYLINDER
