@@ -96,6 +96,27 @@ __global__ void k_rollout_step(const float4* __restrict__ img, const uchar4* __r
     }
 }
 
+// The same, one value per unit: patch widths that are not a multiple of 4, or unaligned buffers.
+__global__ void k_rollout_step1(const float* __restrict__ img, const uint8_t* __restrict__ mask, const float* __restrict__ last,
+                                float* __restrict__ diffs, float* __restrict__ next, __nv_bfloat16* __restrict__ next_bf16,
+                                long total, int n_bx, int n_by, int C, int px, int py) {
+    long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= total) return;
+    int j = (int)(u % py);
+    long r = u / py;
+    int i = (int)(r % px); r /= px;
+    int c = (int)(r % C); r /= C;
+    int by = (int)(r % n_by); r /= n_by;
+    int bx = (int)(r % n_bx);
+    long b = r / n_bx;
+    long img_u = (((b * C + c) * n_bx + bx) * px + i) * ((long)n_by * py) + (long)by * py + j;
+    const float d = mask[u] ? 0.f : __ldg(img + img_u);
+    const float n = __fadd_rn(__ldg(last + u), d);
+    diffs[u] = d;
+    next[u] = n;
+    if (next_bf16) next_bf16[u] = __float2bfloat16_rn(n);
+}
+
 // simple_dataloader.py:93,100: diffs = states[1:] - states[:-1]; masks = mask[1:] repeated over the 3 channels, as bool bytes.
 // One unit = 4 pixels of one (frame, patch): 3 x float4 of two frames in, 3 x float4 + 3 x uchar4 out.
 __global__ void k_sample_assemble(const float4* __restrict__ states, const uchar4* __restrict__ mask, float4* __restrict__ diffs,
@@ -114,6 +135,25 @@ __global__ void k_sample_assemble(const float4* __restrict__ states, const uchar
         const float4 a = __ldg(states + fi * 3 * frame_units + o), n = __ldg(states + (fi + 1) * 3 * frame_units + o);
         diffs[fo * 3 * frame_units + o] = make_float4(n.x - a.x, n.y - a.y, n.z - a.z, n.w - a.w);
         mask3[fo * 3 * frame_units + o] = m;
+    }
+}
+
+// The same, one pixel per unit: patches whose pixel count is not a multiple of 4 (5 x 5, 10 x 7, ...) or unaligned buffers.
+__global__ void k_sample_assemble1(const float* __restrict__ states, const uint8_t* __restrict__ mask, float* __restrict__ diffs,
+                                   uint8_t* __restrict__ mask3, long units, long frame_px /* L * ppx */, int ppx,
+                                   long frames_out_per_sample, long frames_in_per_sample) {
+    const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;       // over [B][T-1][L][ppx]
+    if (u >= units) return;
+    const long fo = u / frame_px, r = u - fo * frame_px;
+    const long b = fo / frames_out_per_sample, t = fo - b * frames_out_per_sample;
+    const long fi = b * frames_in_per_sample + t;
+    const long l = r / ppx, k = r - l * ppx;
+    const uint8_t m = mask[(fi + 1) * frame_px + r];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const long o = ((l * 3 + c) * ppx + k);
+        diffs[fo * 3 * frame_px + o] = __fsub_rn(__ldg(states + (fi + 1) * 3 * frame_px + o), __ldg(states + fi * 3 * frame_px + o));
+        mask3[fo * 3 * frame_px + o] = m;
     }
 }
 
@@ -229,12 +269,19 @@ extern "C" int fl_img_to_patch(const void* d_img, void* d_patches, int B, int n_
 extern "C" int fl_rollout_step(const float* d_pred_img, const uint8_t* d_mask, const float* d_last, float* d_diffs,
                                float* d_next, void* d_next_bf16, int B, int n_bx, int n_by, int C, int px, int py, void* stream) {
     FL_REQUIRE(d_pred_img && d_mask && d_last && d_diffs && d_next, FL_E_ARG, "fl_rollout_step: null pointer");
-    FL_REQUIRE((uintptr_t)d_next_bf16 % 8 == 0, FL_E_ALIGN, "fl_rollout_step: the bf16 token buffer must be 8-byte aligned");
     FL_REQUIRE(B > 0 && n_bx > 0 && n_by > 0 && C > 0 && px > 0 && py > 0, FL_E_ARG, "fl_rollout_step: sizes must be positive");
-    FL_REQUIRE(py % 4 == 0, FL_E_ARG, "fl_rollout_step: patch width %d must be a multiple of 4", py);
-    FL_REQUIRE((((uintptr_t)d_pred_img | (uintptr_t)d_last | (uintptr_t)d_diffs | (uintptr_t)d_next) % 16 == 0) &&
-                   ((uintptr_t)d_mask % 4 == 0),
-               FL_E_ALIGN, "fl_rollout_step: float buffers must be 16-byte aligned, mask 4-byte aligned");
+    FL_REQUIRE(((uintptr_t)d_pred_img | (uintptr_t)d_last | (uintptr_t)d_diffs | (uintptr_t)d_next) % 4 == 0 && (uintptr_t)d_next_bf16 % 2 == 0,
+               FL_E_ALIGN, "fl_rollout_step: float buffers must be 4-byte aligned, the bf16 token buffer 2-byte aligned");
+    const bool vec = py % 4 == 0 && (((uintptr_t)d_pred_img | (uintptr_t)d_last | (uintptr_t)d_diffs | (uintptr_t)d_next) % 16 == 0) &&
+                     ((uintptr_t)d_mask % 4 == 0) && ((uintptr_t)d_next_bf16 % 8 == 0);
+    if (!vec) {       // any patch width / alignment: one value per thread
+        const long total = (long)B * n_bx * n_by * C * px * py;
+        FL_REQUIRE((total + 255) / 256 < 0x7fffffffL, FL_E_ARG, "fl_rollout_step: tensor too large");
+        k_rollout_step1<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            d_pred_img, d_mask, d_last, d_diffs, d_next, (__nv_bfloat16*)d_next_bf16, total, n_bx, n_by, C, px, py);
+        FL_LAUNCH_CHECK();
+        return FL_OK;
+    }
     long units = (long)B * n_bx * n_by * C * px * py / 4;
     k_rollout_step<<<(unsigned)((units + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         (const float4*)d_pred_img, (const uchar4*)d_mask, (const float4*)d_last, (float4*)d_diffs, (float4*)d_next,
@@ -246,10 +293,19 @@ extern "C" int fl_rollout_step(const float* d_pred_img, const uint8_t* d_mask, c
 extern "C" int fl_sample_assemble(const float* d_states, const uint8_t* d_mask, int B, int T, int L, int px, int py, float* d_diffs,
                                   uint8_t* d_mask3, void* stream) {
     FL_REQUIRE(d_states && d_mask && d_diffs && d_mask3, FL_E_ARG, "fl_sample_assemble: null pointer");
-    FL_REQUIRE(B > 0 && T > 1 && L > 0 && px > 0 && py > 0 && (px * py) % 4 == 0, FL_E_ARG,
-               "fl_sample_assemble: need B > 0, T > 1, L > 0 and px*py a multiple of 4");
-    FL_REQUIRE((((uintptr_t)d_states | (uintptr_t)d_diffs) % 16 == 0) && (((uintptr_t)d_mask | (uintptr_t)d_mask3) % 4 == 0), FL_E_ALIGN,
-               "fl_sample_assemble: float buffers must be 16-byte aligned, masks 4-byte aligned");
+    FL_REQUIRE(B > 0 && T > 1 && L > 0 && px > 0 && py > 0, FL_E_ARG, "fl_sample_assemble: need B > 0, T > 1, L > 0, px > 0, py > 0");
+    FL_REQUIRE(((uintptr_t)d_states | (uintptr_t)d_diffs) % 4 == 0, FL_E_ALIGN, "fl_sample_assemble: float buffers must be 4-byte aligned");
+    const bool vec = (px * py) % 4 == 0 && (((uintptr_t)d_states | (uintptr_t)d_diffs) % 16 == 0) &&
+                     (((uintptr_t)d_mask | (uintptr_t)d_mask3) % 4 == 0);
+    if (!vec) {
+        const int ppx = px * py;
+        const long frame_px = (long)L * ppx, units = (long)B * (T - 1) * frame_px;
+        FL_REQUIRE((units + 255) / 256 < 0x7fffffffL, FL_E_ARG, "fl_sample_assemble: too many pixels");
+        k_sample_assemble1<<<(unsigned)((units + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_states, d_mask, d_diffs, d_mask3, units,
+                                                                                               frame_px, ppx, T - 1, T);
+        FL_LAUNCH_CHECK();
+        return FL_OK;
+    }
     const int upp = px * py / 4;
     const long frame_units = (long)L * upp, units = (long)B * (T - 1) * frame_units;
     k_sample_assemble<<<(unsigned)((units + 255) / 256), 256, 0, (cudaStream_t)stream>>>(

@@ -148,6 +148,22 @@ def test_datasets_with_other_strides_and_pad_false(kind, tmp_path):
             assert tuple(a.shape) == b.shape and np.array_equal(a.cpu().numpy(), b), k
 
 
+@pytest.mark.parametrize("patch,stride", [((10, 7), (10, 7)), ((5, 5), (3, 4)), ((32, 32), (32, 32))])
+def test_datasets_with_any_patch_size(patch, stride, tmp_path):
+    """Patch sizes the vectorised kernels do not take (pixel counts that are not multiples of 4 / 32) and one larger than 256 pixels."""
+    from fluid_llm_b200.airfoil_ds import AirfoilDataset
+    from fluid_llm_b200.simple_dataloader import MGNDataset
+    for kind, DS in (("cylinder", MGNDataset), ("airfoil", AirfoilDataset)):
+        trajs = [trajectory(kind, 30, s, 10 + s) for s in (0, 1)]
+        (tmp_path / kind).mkdir()
+        d = _write(tmp_path / kind, copy.deepcopy(trajs))
+        ds = DS(load_dir=d, resolution=238, patch_size=patch, stride=stride, seq_len=3, seq_interval=2, mode="valid")
+        ds.max_step_num = 10
+        want = P.ds_get(trajs[1], 3, 3, 2, 238, patch, kind, stride=stride, n_patch=(ds.N_x_patch, ds.N_y_patch))
+        for a, b in zip(ds.ds_get(1, 3), want):
+            assert tuple(a.shape) == b.shape and np.array_equal(a.cpu().numpy(), b), (kind, patch)
+
+
 def test_ingest_slots_grow_when_a_trajectory_does_not_fit(tmp_path):
     from fluid_llm_b200.simple_dataloader import MGNDataset
     trajs = [trajectory("cylinder", 140, s, 10 + s) for s in (0, 1, 2)]
@@ -282,7 +298,7 @@ def test_sample_assemble_equals_the_reference_tensor_ops():
     """simple_dataloader.py:93,100 in one launch: diffs = states[1:] - states[:-1], masks = mask[1:] x 3 channels as bool."""
     from fluid_llm_b200.simple_dataloader import sample_assemble
     g = torch.Generator(device="cuda").manual_seed(3)
-    for B, T, L, px, py in ((1, 10, 60, 16, 16), (3, 4, 7, 16, 8), (2, 2, 5, 16, 16), (2, 1, 5, 16, 16)):
+    for B, T, L, px, py in ((1, 10, 60, 16, 16), (3, 4, 7, 16, 8), (2, 2, 5, 16, 16), (2, 1, 5, 16, 16), (2, 3, 6, 5, 5), (1, 4, 3, 10, 7)):
         states = torch.randn(B, T, L, 3, px, py, device="cuda", generator=g)
         mask = (torch.rand(B, T, L, px, py, device="cuda", generator=g) < 0.3).to(torch.uint8)
         diffs, m3 = sample_assemble(states, mask)

@@ -86,6 +86,25 @@ def test_rollout_step_matches_reference_glue():
         rollout_step(last, pred[..., :32], mask, props)
 
 
+@pytest.mark.parametrize("patch", [(5, 5), (10, 7), (8, 6), (16, 12)])
+def test_rollout_step_and_patch_ops_for_other_patch_sizes(patch):
+    """utils_model.py:77-109 / model.py:204-210 for patch sizes whose width is not a multiple of 4 (scalar kernels)."""
+    from fluid_llm_b200.ds_props import DSProps
+    from fluid_llm_b200.utils_model import img_to_patch, patch_to_img, rollout_step
+    props = DSProps(3, 4, patch, 2)
+    X, Y, L = 3 * patch[0], 4 * patch[1], 12
+    g = torch.Generator(device="cuda").manual_seed(5)
+    last = torch.randn(2, 1, L, 3, *patch, device="cuda", generator=g)
+    mask = torch.rand(2, 1, L, 3, *patch, device="cuda", generator=g) < 0.25
+    pred = torch.randn(2, 1, 3, X, Y, device="cuda", generator=g)
+    nxt, diffs, tok = rollout_step(last, pred, mask, props, tokens_bf16=True)
+    want_next, want_d = P.rollout_step(last.cpu().numpy(), pred.cpu().numpy(), mask.cpu().numpy(), patch)
+    assert np.array_equal(nxt.cpu().numpy(), want_next) and np.array_equal(diffs.cpu().numpy(), want_d)
+    assert torch.equal(tok.view(-1), nxt.bfloat16().view(-1))
+    img = patch_to_img(last, props)
+    assert np.array_equal(img.cpu().numpy(), P.patch_to_img(last.cpu().numpy(), 3, 4)) and torch.equal(img_to_patch(img, props), last)
+
+
 def test_rollout_loop_stays_exact_over_many_steps():
     """251 rollout steps (src/inference.py:87) through the fused kernel == the reference's three-op glue."""
     from fluid_llm_b200.utils_model import img_to_patch, rollout_step
