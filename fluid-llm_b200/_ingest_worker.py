@@ -75,10 +75,10 @@ def unpickle_lazy(path, keys):
     global _declined
     if _declined >= 2:          # these files are not written the way the lazy reader needs: stop paying for the attempt
         return None
-    with open(path, "rb") as f:
-        mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
-    lf = _LazyFile(mm)
     try:
+        with open(path, "rb") as f:
+            mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        lf = _LazyFile(mm)
         d = pickle.Unpickler(lf).load()
         if not isinstance(d, dict):
             raise TypeError("not a dict")
