@@ -67,6 +67,20 @@ class _LazyFile:
         return n
 
 
+class _ArraysOnly(pickle.Unpickler):
+    """Only NumPy's own array / dtype / scalar reconstruction may run over a _LazyFile: nothing of it looks INTO a large payload
+    while unpickling.  Any other class (a tensor rebuilt from its storage bytes, say) would be handed untouched memory, so its
+    pickle is refused before that happens and goes to the plain unpickler."""
+    _ALLOWED = {("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"), ("numpy", "ndarray"),
+                ("numpy", "dtype"), ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+                ("numpy.core.numeric", "_frombuffer"), ("numpy._core.numeric", "_frombuffer")}
+
+    def find_class(self, module, name):
+        if (module, name) not in self._ALLOWED:
+            raise TypeError(f"{module}.{name} in the pickle")
+        return super().find_class(module, name)
+
+
 def unpickle_lazy(path, keys):
     """-> {key: array} with the large arrays of `keys` as read-only views of the mapped file (which lives as long as they do), or
     None when the file is not a plain dict of NumPy arrays unpickled the way _LazyFile expects (the caller then unpickles
@@ -79,7 +93,7 @@ def unpickle_lazy(path, keys):
         with open(path, "rb") as f:
             mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
         lf = _LazyFile(mm)
-        d = pickle.Unpickler(lf).load()
+        d = _ArraysOnly(lf).load()
         if not isinstance(d, dict):
             raise TypeError("not a dict")
         out = {}
@@ -95,8 +109,10 @@ def unpickle_lazy(path, keys):
             out[k] = a
         _declined = 0
         return out
-    except Exception:       # noqa: BLE001 -- anything unexpected: the plain unpickler decides
+    except TypeError:       # not the kind of pickle this reader handles
         _declined += 1
+        return None
+    except Exception:       # noqa: BLE001 -- a missing / truncated / foreign file: the plain unpickler decides (and raises)
         return None
 
 

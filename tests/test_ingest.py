@@ -72,9 +72,11 @@ def test_lazy_unpickle_declines_what_it_does_not_know(tmp_path):
     with open(tmp_path / "short.pkl", "wb") as f:
         f.write((tmp_path / "1.pkl").read_bytes()[:500000])          # truncated inside a payload
     W._declined = 0
-    assert W.unpickle_lazy(str(tmp_path / "short.pkl"), ("velocity",)) is None
-    assert W.unpickle_lazy(str(tmp_path / "short.pkl"), ("velocity",)) is None and W._declined == 2
-    assert W.unpickle_lazy(str(tmp_path / "1.pkl"), ("velocity",)) is None        # two files declined in a row: it stops trying
+    assert W.unpickle_lazy(str(tmp_path / "short.pkl"), ("velocity",)) is None        # a broken file ...
+    assert W.unpickle_lazy(str(tmp_path / "nowhere.pkl"), ("velocity",)) is None and W._declined == 0     # ... says nothing about the format
+    assert W.unpickle_lazy(str(tmp_path / "0.pkl"), ("velocity",)) is None
+    assert W.unpickle_lazy(str(tmp_path / "2.pkl"), ("velocity",)) is None and W._declined == 2
+    assert W.unpickle_lazy(str(tmp_path / "1.pkl"), ("velocity",)) is None        # two files of another kind in a row: it stops trying
     with pytest.raises(Exception):
         W.load_trajectory(str(tmp_path / "short.pkl"), False)
 
