@@ -72,6 +72,7 @@ SIGNATURES = {
     "fl_ds_stats": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fl_stats_merge": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "fl_cast_bf16": (c_int, [c_void_p, c_void_p, ctypes.c_long, c_void_p]),
+    "fl_cast_bf16_rows": (c_int, [c_void_p, c_void_p, ctypes.c_long, c_int, c_int, c_void_p]),
     "fl_patch_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
 }

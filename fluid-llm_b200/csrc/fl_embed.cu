@@ -351,6 +351,26 @@ extern "C" int fl_cast_bf16(const float* d_in, void* d_out_bf16, long n, void* s
     return FL_OK;
 }
 
+// rows of `cols` floats -> rows of `out_cols` >= cols bf16 values, the tail of every row zero: tokens whose length is not a multiple
+// of the GEMM's K step (patches other than 16 x 16) meet weights padded with zero columns the same way
+__global__ void k_cast_bf16_rows(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long rows, int cols, int out_cols) {
+    const long u = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= rows * out_cols) return;
+    const long r = u / out_cols;
+    const int c = (int)(u - r * out_cols);
+    out[u] = c < cols ? __float2bfloat16_rn(__ldg(in + r * cols + c)) : __float2bfloat16_rn(0.f);
+}
+
+extern "C" int fl_cast_bf16_rows(const float* d_in, void* d_out_bf16, long rows, int cols, int out_cols, void* stream) {
+    FL_REQUIRE(d_in && d_out_bf16 && rows > 0 && cols > 0 && out_cols >= cols, FL_E_ARG, "fl_cast_bf16_rows: need non-null buffers, rows > 0, 0 < cols <= out_cols");
+    FL_REQUIRE(((uintptr_t)d_in % 4 == 0) && ((uintptr_t)d_out_bf16 % 2 == 0), FL_E_ALIGN, "fl_cast_bf16_rows: unaligned buffer");
+    const long n = rows * out_cols;
+    FL_REQUIRE((n + 255) / 256 < 0x7fffffffL, FL_E_ARG, "fl_cast_bf16_rows: too many values");
+    k_cast_bf16_rows<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_in, (__nv_bfloat16*)d_out_bf16, rows, cols, out_cols);
+    FL_LAUNCH_CHECK();
+    return FL_OK;
+}
+
 extern "C" int fl_patch_embed(const void* d_x_bf16, const void* d_w1_bf16, const float* d_b1, const void* d_w2_bf16,
                               const float* d_b2, const float* d_x_emb, const float* d_y_emb, const float* d_t_emb,
                               const long long* d_pos_ids, int max_x, int max_y, int max_t, void* d_hidden_bf16, float* d_out,

@@ -27,6 +27,11 @@ class PatchEmbedder:
         self.b2 = b2.detach().to(dev, torch.bfloat16).float().contiguous()
         self.hid_dim, self.in_dim = self.w1.shape
         self.out_dim = self.w2.shape[0]
+        # the GEMM steps through K in blocks of 64: a token length that is not a multiple of it (patches other than 16 x 16,
+        # e.g. 3 * 10 * 7 = 210) is padded with zeros, weights and tokens alike -- the products are exact zeros
+        self.k_dim = (self.in_dim + 63) // 64 * 64
+        if self.k_dim != self.in_dim:
+            self.w1 = torch.nn.functional.pad(self.w1, (0, self.k_dim - self.in_dim)).contiguous()
         if self.w2.shape[1] != self.hid_dim or self.b1.numel() != self.hid_dim or self.b2.numel() != self.out_dim:
             raise ValueError("PatchEmbedder: weight shapes do not chain (in -> hid -> out)")
         self.pos = None
@@ -70,12 +75,16 @@ class PatchEmbedder:
         n = xf.shape[0]
         lib = load()
         with torch.cuda.device(x.device):
-            if xf.dtype == torch.bfloat16:
+            if xf.dtype == torch.bfloat16 and self.k_dim == self.in_dim:
                 xb = xf.contiguous()
-            else:
+            elif self.k_dim == self.in_dim and (n * self.in_dim) % 4 == 0:
                 xf = xf.float().contiguous()
                 xb = torch.empty((n, self.in_dim), dtype=torch.bfloat16, device=x.device)
                 check(lib.fl_cast_bf16(ptr(xf), ptr(xb), n * self.in_dim, stream_ptr()), "fl_cast_bf16")
+            else:                                       # zero-padded rows (bf16 -> fp32 -> bf16 is exact)
+                xf = xf.float().contiguous()
+                xb = torch.empty((n, self.k_dim), dtype=torch.bfloat16, device=x.device)
+                check(lib.fl_cast_bf16_rows(ptr(xf), ptr(xb), n, self.in_dim, self.k_dim, stream_ptr()), "fl_cast_bf16_rows")
             hidden = torch.empty((n, self.hid_dim), dtype=torch.bfloat16, device=x.device)
             if out is None:
                 out = torch.empty((n, self.out_dim), dtype=torch.float32, device=x.device)
@@ -93,7 +102,7 @@ class PatchEmbedder:
             xe, ye, te = self.pos if self.pos is not None else (None, None, None)
             check(lib.fl_patch_embed(ptr(xb), ptr(self.w1), ptr(self.b1), ptr(self.w2), ptr(self.b2), ptr(xe), ptr(ye), ptr(te),
                                      ptr(ids), xe.shape[0] if xe is not None else 0, ye.shape[0] if ye is not None else 0,
-                                     te.shape[0] if te is not None else 0, ptr(hidden), ptr(out), n, self.in_dim, self.hid_dim,
+                                     te.shape[0] if te is not None else 0, ptr(hidden), ptr(out), n, self.k_dim, self.hid_dim,
                                      self.out_dim, stream_ptr()), "fl_patch_embed")
         return out.view(*lead, self.out_dim)
 

@@ -32,7 +32,7 @@ extern "C" {
 #define FL_E_WORKSPACE (-3)/* workspace too small */
 #define FL_E_ALIGN (-4)    /* pointer not aligned as documented */
 
-#define FL_ABI_VERSION 9
+#define FL_ABI_VERSION 10
 
 /* personality flags of fl_plan_patch_table / fl_interp_patchify */
 #define FL_FLIP_Y 1u          /* airfoil_ds.py:80  -- y axis reversed after padding */
@@ -248,6 +248,9 @@ int fl_stats_merge(const double* d_parts, int n_parts, double* d_out, void* stre
  * d_hidden_bf16 [n_tokens, hid_dim] workspace, d_out fp32 [n_tokens, out_dim].
  * in_dim, hid_dim multiples of 64; hid_dim, out_dim multiples of 256. */
 int fl_cast_bf16(const float* d_in, void* d_out_bf16, long n, void* stream);
+/* rows of `cols` floats -> rows of `out_cols` >= cols bf16 values with a zero tail: tokens of patches whose 3*px*py is not a
+ * multiple of 64 (fl_patch_embed's K step) against weights padded with zero columns in the same way */
+int fl_cast_bf16_rows(const float* d_in, void* d_out_bf16, long rows, int cols, int out_cols, void* stream);
 /* The positional add of fl_patch_embed on its own, over a ring of cached pre-positional embeddings (fl_patch_embed with
  * d_pos_ids = NULL): src/models/model.py:196-199 re-bases the time ids of the whole context at every rollout step, but only ONE
  * state of the context is new -- the others' bf16(h W2^T + b2) rows are unchanged and only their positional term moves.

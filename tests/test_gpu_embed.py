@@ -45,6 +45,33 @@ def test_patch_embed_matches_autocast_reference(n_tokens):
     assert float((out - exact).abs().max()) < 6e-2 and float(((out - exact).abs() > 1e-6).float().mean()) < 0.05
 
 
+@pytest.mark.parametrize("patch", [(10, 7), (5, 5), (8, 8), (32, 32)])
+def test_patch_embed_for_other_patch_sizes(patch):
+    """Token lengths 3 * px * py that are not a multiple of the GEMM's K step (210, 75) are zero-padded, weights and tokens alike."""
+    from fluid_llm_b200.patch_embed import PatchEmbedder
+    n, k = 777, 3 * patch[0] * patch[1]
+    g = torch.Generator(device="cuda").manual_seed(k)
+    x = torch.randn(n, 3, *patch, device="cuda", generator=g)
+    w1 = torch.randn(256, k, device="cuda", generator=g) * k ** -0.5
+    b1 = torch.randn(256, device="cuda", generator=g) * 0.1
+    w2 = torch.randn(512, 256, device="cuda", generator=g) * 256 ** -0.5
+    b2 = torch.randn(512, device="cuda", generator=g) * 0.1
+    tabs = [torch.randn(m, 512, device="cuda", generator=g) * 0.05 for m in (9, 7, 5)]
+    ids = torch.stack([torch.randint(0, m, (n,), device="cuda", generator=g) for m in (9, 7, 5)], dim=1)
+    emb = PatchEmbedder(w1, b1, w2, b2, *tabs)
+    assert emb.in_dim == k and emb.k_dim % 64 == 0 and emb.k_dim - k < 64
+    out = emb(x, ids)
+    ref = _reference(x.reshape(n, -1), w1, b1, w2, b2, tabs, ids)
+    torch.testing.assert_close(out, ref, rtol=2e-2, atol=2e-2)
+    xb, w1b, w2b = x.reshape(n, -1).bfloat16().double(), w1.bfloat16().double(), w2.bfloat16().double()
+    h = (xb @ w1b.T + b1.bfloat16().double()).float().bfloat16().float()
+    h = torch.where(h > 0, h, 0.01 * h).bfloat16().double()
+    y = (h @ w2b.T + b2.bfloat16().double()).float().bfloat16().float()
+    exact = y + (tabs[0][ids[:, 0]] + tabs[1][ids[:, 1]] + tabs[2][ids[:, 2]])
+    assert float((out - exact).abs().max()) < 6e-2 and float(((out - exact).abs() > 1e-6).float().mean()) < 0.05
+    assert torch.equal(emb(x.bfloat16(), ids), emb(x.bfloat16().float(), ids))          # bf16 tokens take the same path
+
+
 def test_patch_embed_shapes_and_errors():
     from fluid_llm_b200.patch_embed import PatchEmbedder
     w1, b1, w2, b2 = torch.randn(512, 768), torch.zeros(512), torch.randn(768, 512), torch.zeros(768)
