@@ -26,7 +26,7 @@ class FlTraj(ctypes.Structure):
                 ("n_nodes", c_int32), ("t0", c_int32), ("interval", c_int32), ("n_frames", c_int32),
                 ("vel_stride", c_int32), ("prs_stride", c_int32),
                 ("d_idx_tile", c_void_p), ("d_tile_nodes", c_void_p), ("d_tile_desc", c_void_p), ("d_tile_patches", c_void_p),
-                ("d_tile_quads", c_void_p), ("d_tile_qslots", c_void_p), ("n_tiles", c_int32), ("max_tile_nodes", c_int32), ("max_tile_patches", c_int32), ("reserved_", c_int32)]
+                ("d_tile_quads", c_void_p), ("d_tile_qslots", c_void_p), ("n_tiles", c_int32), ("max_tile_nodes", c_int32), ("max_tile_patches", c_int32), ("idx_slot_format", c_int32)]
 
 
 class FluidGridError(RuntimeError):
@@ -45,6 +45,7 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "fl_plan_patch_table": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_uint, c_void_p, c_void_p,
                                     POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p]),
+    "fl_pack_idx16": (c_int, [c_void_p, ctypes.c_long, c_int, c_void_p, c_void_p]),
     "fl_interp_patchify": (c_int, [POINTER(FlTraj), c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                    c_uint, c_void_p]),
     "fl_interp_patchify_dev": (c_int, [c_void_p, POINTER(FlTraj), c_int, c_int, c_int, c_int, POINTER(c_float),

@@ -138,7 +138,7 @@ __device__ __forceinline__ void load_wide(uint32_t addr, double& u, double& v, d
     u = __longlong_as_double((long long)((A & 0xffffffff00000000ull) | __byte_perm(bits, 0u, 0x0444)));
 }
 
-template <bool CHECKED, int WIDE>
+template <bool CHECKED, int WIDE, bool IDX16 = false>
 __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned char* __restrict__ s_nodes, uint32_t s_base, int slot_b,
                                             int fbeg, int nf, int n_patches, int ppx, int ppx_shift, const StagedConst& sc,
                                             unsigned flags) {
@@ -162,7 +162,13 @@ __device__ __forceinline__ void staged_item(const FlTraj& tr, const unsigned cha
         unsigned mbits = 0;     // byte r = 1 if pixel r is outside the mesh
 #pragma unroll
         for (int r = 0; r < NP; ++r) {
-            const int4 id = __ldg((const int4*)idx_tab + o + 32 * r);
+            int4 id;
+            if (IDX16) {       // compact table: {v0 | v1 << 16, v2 | outside << 16}, node slots below 65536
+                const uint2 q = __ldg((const uint2*)idx_tab + o + 32 * r);
+                id = make_int4((int)(q.x & 0xffffu), (int)(q.x >> 16), (int)(q.y & 0xffffu), (q.y >> 16) ? -1 : 0);
+            } else {
+                id = __ldg((const int4*)idx_tab + o + 32 * r);
+            }
             const double2 ww = __ldg((const double2*)tr.d_w + o + 32 * r);
             const bool out = id.w < 0;
             mbits |= out ? (1u << (8 * r)) : 0u;
@@ -312,7 +318,10 @@ k_interp_patchify_staged(const FlTraj* __restrict__ trajs, int n_items, int grou
         const int bad = __syncthreads_or(!(nanacc == 0.f) || amax > 1.0e30f || !sc.fast_div);
         const unsigned char* snb = (const unsigned char*)s_nodes;
         const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(fl_smem);
-        if (wide) {
+        if (tr.idx_slot_format == 1) {            // d_idx_slot holds the compact 8-byte records (wide node records only)
+            if (bad) staged_item<true, 1, true>(tr, snb, s_base, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+            else staged_item<false, 1, true>(tr, snb, s_base, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
+        } else if (wide) {
             if (bad) staged_item<true, 1>(tr, snb, s_base, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
             else staged_item<false, 1>(tr, snb, s_base, slot_nodes * 16, fbeg, nf, n_patches, ppx, ppx_shift, sc, flags);
         } else {
@@ -378,6 +387,7 @@ int launch_interp(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int 
             const int grid = n_items < FL_SM_COUNT ? (int)n_items : FL_SM_COUNT;      // one persistent CTA per SM
             int wide = 1;        // fully pre-widened records (round 2: +4 % on all three workloads); FLUIDGRID_WIDE=0 keeps {u, v f32, p f64}
             if (const char* e = getenv("FLUIDGRID_WIDE")) wide = atoi(e);
+            for (int i = 0; i < n_traj; ++i) if (h_trajs[i].idx_slot_format == 1) wide = 1;      // compact table records go with the wide node records
             k_interp_patchify_staged<<<grid, ST_THREADS, smem, st>>>(d_trajs, (int)n_items, gpt, TF, n_patches, ppx, ppx_shift, slot_prs,
                                                                      sc, flags, wide);
             FL_LAUNCH_CHECK();
@@ -433,6 +443,8 @@ static int check_trajs(const char* who, const FlTraj* h_trajs, int n_traj, int* 
         FL_REQUIRE((long long)t.interval * t.vel_stride < 0x7fffffffLL, FL_E_ARG, "%s: trajectory %d: interval * vel_stride overflows", who, i);
         FL_REQUIRE((t.d_idx_slot == nullptr) == (t.d_node_slot == nullptr), FL_E_ARG,
                    "%s: trajectory %d: d_idx_slot and d_node_slot must be given together", who, i);
+        FL_REQUIRE(t.idx_slot_format == 0 || (t.idx_slot_format == 1 && t.d_idx_slot && t.prs_stride <= 65536 && (uintptr_t)t.d_idx_slot % 8 == 0),
+                   FL_E_ARG, "%s: trajectory %d: idx_slot_format must be 0, or 1 with compact d_idx_slot records and at most 65536 slots", who, i);
         mf = t.n_frames > mf ? t.n_frames : mf;
     }
     *max_frames = mf;
@@ -440,6 +452,25 @@ static int check_trajs(const char* who, const FlTraj* h_trajs, int n_traj, int* 
 }
 
 extern "C" const char* fl_last_interp_kernel(void) { return g_last_kernel; }
+
+__global__ void k_pack_idx16(const FlCellIdx* __restrict__ in, uint2* __restrict__ out, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FlCellIdx r = in[i];
+    const bool outside = r.tri < 0;
+    out[i] = outside ? make_uint2(0u, 1u << 16)
+                     : make_uint2((unsigned)r.v0 | ((unsigned)r.v1 << 16), (unsigned)r.v2);
+}
+
+extern "C" int fl_pack_idx16(const FlCellIdx* d_idx_slot, long n, int n_slots, void* d_out, void* stream) {
+    FL_REQUIRE(d_idx_slot && d_out && n > 0, FL_E_ARG, "fl_pack_idx16: null pointer or n <= 0");
+    FL_REQUIRE(n_slots > 0 && n_slots <= 65536, FL_E_ARG, "fl_pack_idx16: %d slots do not fit 16 bits", n_slots);
+    FL_REQUIRE((uintptr_t)d_idx_slot % 16 == 0 && (uintptr_t)d_out % 8 == 0, FL_E_ALIGN, "fl_pack_idx16: unaligned buffer");
+    FL_REQUIRE((n + 255) / 256 < 0x7fffffffL, FL_E_ARG, "fl_pack_idx16: too many records");
+    k_pack_idx16<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_idx_slot, (uint2*)d_out, n);
+    FL_LAUNCH_CHECK();
+    return FL_OK;
+}
 
 extern "C" int fl_interp_patchify_dev(const FlTraj* d_trajs, const FlTraj* h_trajs, int n_traj, int n_patches, int px, int py,
                                       const float* h_mean, const float* h_std, unsigned flags, void* stream) {

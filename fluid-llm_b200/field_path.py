@@ -123,9 +123,12 @@ class TrajBatch:
     """Pre-built launch descriptors for a fixed batch (descriptor array already on the device), so
     the steady-state call is exactly one kernel launch and no host->device traffic."""
 
-    def __init__(self, trajs, tables, t0s, interval, n_frames, want_mask=True, use_slots=None, out=None, tile_patches=None):
+    def __init__(self, trajs, tables, t0s, interval, n_frames, want_mask=True, use_slots=None, out=None, tile_patches=None,
+                 compact_idx=None):
         if use_slots is None:
             use_slots = os.environ.get("FLUIDGRID_SLOTS", "1") != "0"
+        if compact_idx is None:        # 8-byte table records (FlTraj::idx_slot_format = 1) wherever the staged kernel may run
+            compact_idx = os.environ.get("FLUIDGRID_IDX16", "1") != "0"
         if not (len(trajs) == len(tables) == len(t0s)) or not trajs:
             raise ValueError("trajs, tables and t0s must be non-empty and of equal length")
         tab0 = tables[0]
@@ -171,6 +174,9 @@ class TrajBatch:
             idx_slot, node_slot = tab.idx_slot, tr.plan.node_slot_d
             if colour and use_slots and idx_slot is not None and tpl is None:
                 node_slot, idx_slot = tab.coloured_slots(tr.prs_stride)
+            fmt = 0
+            if compact_idx and use_slots and idx_slot is not None and tpl is None and tr.prs_stride <= 65536 and ppx % 128 == 0:
+                idx_slot, fmt = tab.idx_slot16(tr.prs_stride), 1        # 8-byte table records for the staged kernel
             arr[i] = FlTraj(tr.vel_buf.data_ptr(), tr.prs_buf.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(),
                             idx_slot.data_ptr() if use_slots and idx_slot is not None else 0,
                             node_slot.data_ptr() if use_slots and idx_slot is not None else 0,
@@ -179,7 +185,7 @@ class TrajBatch:
                             tpl.idx_tile.data_ptr() if tpl else 0, tpl.tile_nodes.data_ptr() if tpl else 0,
                             tpl.tile_desc.data_ptr() if tpl else 0, tpl.tile_patches.data_ptr() if tpl else 0,
                             tpl.tile_quads.data_ptr() if tpl else 0, tpl.tile_qslots.data_ptr() if tpl else 0,
-                            tpl.n_tiles if tpl else 0, tpl.max_tile_nodes if tpl else 0, min(tpl.tp, tab.n_patches) if tpl else 0, 0)
+                            tpl.n_tiles if tpl else 0, tpl.max_tile_nodes if tpl else 0, min(tpl.tp, tab.n_patches) if tpl else 0, fmt)
         self.host_desc = arr
         raw = np.frombuffer(bytes(arr), dtype=np.uint8).copy()
         self.desc = torch.from_numpy(raw).to(dev)
@@ -204,12 +210,12 @@ class TrajBatch:
 
 def interp_patchify(traj: DeviceTrajectory, step_num: int, seq_len: int, seq_interval: int, patch_size,
                     personality: Personality, normalize=True, means=None, stds=None, force_gather=False, force_staged=False,
-                    tile_patches=None, force_ring=False, stride=None, pad=True):
+                    tile_patches=None, force_ring=False, stride=None, pad=True, compact_idx=None):
     """One trajectory, frames step_num, step_num+interval, ... -> (states (T,L,3,px,py) f32,
     mask (T,L,px,py) u8, table).  `stride` / `pad`: the data sets' unfold stride (default: the patch size) and padding switch."""
     _lib.require_cuda()
     tab = traj.plan.patch_table(patch_size, personality.crop_patches, personality.flip_y, stride, pad)
-    batch = TrajBatch([traj], [tab], [step_num], seq_interval, seq_len, tile_patches=tile_patches)
+    batch = TrajBatch([traj], [tab], [step_num], seq_interval, seq_len, tile_patches=tile_patches, compact_idx=compact_idx)
     states, mask = batch.run(personality, normalize, means, stds, force_gather, force_staged, force_ring)
     return states[0], mask[0], tab
 

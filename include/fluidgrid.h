@@ -32,7 +32,7 @@ extern "C" {
 #define FL_E_WORKSPACE (-3)/* workspace too small */
 #define FL_E_ALIGN (-4)    /* pointer not aligned as documented */
 
-#define FL_ABI_VERSION 10
+#define FL_ABI_VERSION 11
 
 /* personality flags of fl_plan_patch_table / fl_interp_patchify */
 #define FL_FLIP_Y 1u          /* airfoil_ds.py:80  -- y axis reversed after padding */
@@ -134,13 +134,21 @@ typedef struct FlTraj {
     const int32_t* d_tile_qslots;  /* with d_tile_quads: [quads][4] the slots of each quad's 4 nodes (-1: not used by the tile); lets the
                                       kernel stage with coalesced 128-bit loads when the frames are 16-byte aligned and padded to quads */
     int32_t n_tiles, max_tile_nodes;
-    int32_t max_tile_patches, reserved_;   /* patches of the largest tile: at most 7 (px*py = 256) or 14 (128), one per patch group */
+    int32_t max_tile_patches;      /* patches of the largest tile: at most 7 (px*py = 256) or 14 (128), one per patch group */
+    int32_t idx_slot_format;       /* 0: d_idx_slot holds FlCellIdx records (16 B per output pixel); 1: the compact records
+                                      fl_pack_idx16 makes of them (8 B: v0 | v1 << 16, v2 | outside << 16; slots below 65536).
+                                      The staged kernel reads its table records once per work item: a third fewer bytes there
+                                      are 2 - 5 % of the launch (profiles/README.md) */
 } FlTraj;
 /* prs_stride a multiple of 4, vel_stride >= 2 * prs_stride, 16-byte aligned bases and pad floats
  * that are readable and finite select the staged kernel: whole frames are staged in shared memory
  * as 16-byte node records and gathered there (patches of a multiple of 128 pixels).  Anything else runs
  * the gather-from-global kernel -- same results, slower.  px, py: ANY patch size F.unfold takes
  * (simple_dataloader.py:131), e.g. 5 x 5 or 32 x 32; the reference's configs use 16 x 16. */
+
+/* FlCellIdx records with node SLOTS (fl_plan_patch_table's d_out_idx_slot) -> the compact 8-byte form of
+ * FlTraj::idx_slot_format = 1.  d_out: uint32[n][2].  n_slots: slots are 0 <= s < n_slots <= 65536. */
+int fl_pack_idx16(const FlCellIdx* d_idx_slot, long n, int n_slots, void* d_out, void* stream);
 
 int fl_interp_patchify(const FlTraj* h_trajs, int n_traj, int n_patches, int px, int py,
                        const float* h_mean, const float* h_std, unsigned flags, void* stream);

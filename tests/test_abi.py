@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/fluidgrid.h but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes SIGNATURES and the header disagree"
-    assert lib.fl_abi_version() == 10
+    assert lib.fl_abi_version() == 11
 
 
 def test_struct_layout_matches_header():

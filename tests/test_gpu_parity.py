@@ -11,13 +11,14 @@ from helpers import PATCH, oracle_ds_get, personality_of, tie_mesh, trajectory
 pytestmark = pytest.mark.gpu
 
 
-KERNELS = ["staged", "gather", "tiled", "ring"]
+KERNELS = ["staged", "staged_idx32", "gather", "tiled", "ring"]      # staged_idx32: 16-byte table records instead of the compact ones
 
 
 def _kernel_args(kernel, ppx=256):
     """interp_patchify / TrajBatch arguments that force one of the per-step kernels (csrc/fl_interp.cu, fl_tiled.cu, and the
     experimental fl_ring.cu)."""
-    return {"staged": dict(tile_patches=0), "gather": dict(tile_patches=0, force_gather=True),
+    return {"staged": dict(tile_patches=0), "staged_idx32": dict(tile_patches=0, compact_idx=False),
+            "gather": dict(tile_patches=0, force_gather=True),
             "tiled": dict(tile_patches=14 * 128 // ppx), "ring": dict(tile_patches=12 * 128 // ppx, force_ring=True)}[kernel]
 
 
@@ -168,10 +169,11 @@ def test_interp_patchify_batch_of_meshes(kernel):
         tabs.append(plan.patch_table(PATCH))
         want.append(oracle_ds_get("cylinder", t0, 4, 1, mesh_seed=seed, field_seed=10 + seed)[1])
     ka = _kernel_args(kernel)
-    batch = TrajBatch(trajs, tabs, t0s, 1, 4, tile_patches=ka["tile_patches"])
+    batch = TrajBatch(trajs, tabs, t0s, 1, 4, tile_patches=ka["tile_patches"], compact_idx=ka.get("compact_idx"))
     assert (batch.tile_plans is not None) == (kernel in ("tiled", "ring"))
     states, mask = batch.run(CYLINDER, force_gather=ka.get("force_gather", False), force_ring=ka.get("force_ring", False))
-    assert fluid_llm_b200.load().fl_last_interp_kernel().decode() == "k_interp_patchify_" + kernel
+    assert fluid_llm_b200.load().fl_last_interp_kernel().decode() == "k_interp_patchify_" + kernel.split("_")[0]
+    assert [d.idx_slot_format for d in batch.host_desc] == [1 if kernel in ("staged", "gather") else 0] * 3   # (gather ignores the slot tables)
     torch.cuda.synchronize()
     for i, ex in enumerate(want):
         assert np.array_equal(states[i].cpu().numpy(), ex["states"])
@@ -364,7 +366,7 @@ def test_c_abi_called_directly_as_integration_md_shows():
                     ("d_idx_tile", ctypes.c_void_p), ("d_tile_nodes", ctypes.c_void_p), ("d_tile_desc", ctypes.c_void_p),
                     ("d_tile_patches", ctypes.c_void_p), ("d_tile_quads", ctypes.c_void_p), ("d_tile_qslots", ctypes.c_void_p),
                     ("n_tiles", ctypes.c_int32), ("max_tile_nodes", ctypes.c_int32),
-                    ("max_tile_patches", ctypes.c_int32), ("reserved_", ctypes.c_int32)]
+                    ("max_tile_patches", ctypes.c_int32), ("idx_slot_format", ctypes.c_int32)]
 
     lib.fl_interp_patchify.restype = ctypes.c_int
     lib.fl_interp_patchify.argtypes = [ctypes.POINTER(FlTraj), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -416,7 +418,7 @@ def test_interp_patchify_writes_stay_inside_the_output_buffers(kind, kernel):
     states = sbuf[G:G + 3 * n].view(n_traj, T, L, 3, 16, 16)
     mask = mbuf[G:G + n].view(n_traj, T, L, 16, 16)
     ka = _kernel_args(kernel)
-    batch = TrajBatch(trajs, [tab, tab], [0, 1], 1, T, out=(states, mask), tile_patches=ka["tile_patches"])
+    batch = TrajBatch(trajs, [tab, tab], [0, 1], 1, T, out=(states, mask), tile_patches=ka["tile_patches"], compact_idx=ka.get("compact_idx"))
     batch.run(pers, force_gather=ka.get("force_gather", False), force_ring=ka.get("force_ring", False))
     torch.cuda.synchronize()
     assert bool((sbuf[:G] == 777.0).all()) and bool((sbuf[-G:] == 777.0).all())
@@ -547,7 +549,7 @@ def test_ragged_batch_through_the_c_abi(kernel):
     ka = _kernel_args(kernel)
     run_kw = dict(force_gather=ka.get("force_gather", False), force_ring=ka.get("force_ring", False))
     n_max = max(s[0] for s in spec)
-    batch = TrajBatch(trajs, tabs, [0] * len(spec), 1, n_max, tile_patches=ka["tile_patches"])
+    batch = TrajBatch(trajs, tabs, [0] * len(spec), 1, n_max, tile_patches=ka["tile_patches"], compact_idx=ka.get("compact_idx"))
     for i, (nf, t0, iv) in enumerate(spec):
         batch.host_desc[i].n_frames, batch.host_desc[i].t0, batch.host_desc[i].interval = nf, t0, iv
     batch.desc = torch.from_numpy(np.frombuffer(bytes(batch.host_desc), dtype=np.uint8).copy()).cuda()
