@@ -110,7 +110,8 @@ __global__ void k_to_grid(const FlCellIdx* __restrict__ idx, const FlCellW* __re
 //             L2-resident) and reused for all TF frames.
 //   output    128 B per warp store (streaming, no L1 allocate); each (frame, patch, channel) block of
 //             1 KB is written whole by two warps.
-// HBM traffic: 12 N + 12 P bytes per frame (compulsory); L2 -> SM adds 32 P / TF (table).
+// HBM traffic: 12 N + 12 P bytes per frame (compulsory); L2 -> SM adds 24 P / TF (table: compact 8-byte index records +
+// two fp64 weights per pixel; 32 P / TF with FlCellIdx records).
 // Arithmetic per pixel-frame: 9 PRMT, 3 DMUL + 6 DFMA, 3 f64->f32, then (v - mean) / std as
 // a reciprocal multiply with one Markstein correction step on the packed fp32 pipe (bit-identical to
 // IEEE division for the ranges checked on the host and in the staging scan; anything else takes the
