@@ -175,7 +175,7 @@ class TrajBatch:
             if colour and use_slots and idx_slot is not None and tpl is None:
                 node_slot, idx_slot = tab.coloured_slots(tr.prs_stride)
             fmt = 0
-            if compact_idx and use_slots and idx_slot is not None and tpl is None and tr.prs_stride <= 65536 and ppx % 128 == 0:
+            if compact_idx and not colour and use_slots and idx_slot is not None and tpl is None and tr.prs_stride <= 65536 and ppx % 128 == 0:
                 idx_slot, fmt = tab.idx_slot16(tr.prs_stride), 1        # 8-byte table records for the staged kernel
             arr[i] = FlTraj(tr.vel_buf.data_ptr(), tr.prs_buf.data_ptr(), tab.idx.data_ptr(), tab.w.data_ptr(),
                             idx_slot.data_ptr() if use_slots and idx_slot is not None else 0,
