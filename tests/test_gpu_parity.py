@@ -334,6 +334,27 @@ def test_other_patch_sizes(patch):
         assert np.array_equal(mask.cpu().numpy().astype(bool), extra["masks"].astype(bool)), kw
 
 
+def test_compact_table_records_are_what_the_header_says():
+    """fl_pack_idx16 (include/fluidgrid.h): {v0 | v1 << 16, v2 | outside << 16} from the slot form of the table; refused when the
+    slots do not fit 16 bits."""
+    import ctypes
+    from fluid_llm_b200._lib import load, ptr
+    plan, _, _ = _plan("airfoil")
+    tab = plan.patch_table(PATCH, 1, True)
+    packed = tab.idx_slot16(plan.n_padded).cpu().numpy().view(np.uint32)
+    src = tab.idx_slot.cpu().numpy()
+    inside = src[:, 3] >= 0
+    assert inside.any() and (~inside).any() and src[inside, :3].max() < plan.n_padded
+    want = np.zeros((len(src), 2), dtype=np.uint32)
+    want[inside, 0] = src[inside, 0].astype(np.uint32) | (src[inside, 1].astype(np.uint32) << 16)
+    want[inside, 1] = src[inside, 2].astype(np.uint32)
+    want[~inside, 1] = 1 << 16
+    assert np.array_equal(packed, want)
+    out = torch.empty((len(src), 2), dtype=torch.int32, device="cuda")
+    assert load().fl_pack_idx16(ptr(tab.idx_slot), len(src), 65537, ptr(out), None) == -1
+    assert b"16 bits" in load().fl_last_error()
+
+
 def test_other_patch_sizes_kernel_choice():
     from fluid_llm_b200._lib import load
     from fluid_llm_b200.field_path import CYLINDER, DeviceTrajectory, interp_patchify
