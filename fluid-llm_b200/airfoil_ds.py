@@ -7,7 +7,6 @@ normalisation (:216-244), natural-sorted file list (:44).
 """
 from __future__ import annotations
 
-import os
 import re
 
 import numpy as np

@@ -22,14 +22,12 @@ from __future__ import annotations
 
 import atexit
 import os
-import pickle
 from collections import OrderedDict
 import subprocess
 import sys
 from multiprocessing import Pipe, shared_memory
 from multiprocessing.connection import wait as conn_wait
 
-import numpy as np
 import torch
 
 from ._ingest_worker import fill_slot as _fill_slot, load_trajectory, strides as _strides

@@ -12,7 +12,6 @@ from __future__ import annotations
 import contextlib
 import ctypes
 import os
-from functools import lru_cache
 
 import numpy as np
 import torch
